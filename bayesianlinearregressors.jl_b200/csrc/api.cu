@@ -1,0 +1,792 @@
+// C ABI of libblr_cuda (declared in include/blr_cuda.h): contexts, handles, and the entry points the Julia
+// glue / Python host mirror bind.  No torch types, no exceptions across the boundary, no CPU fallback.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "internal.h"
+
+namespace blr {
+
+int set_err(blr_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+int cuda_fail(blr_ctx* ctx, cudaError_t e, const char* what) {
+    if (ctx) ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();  // clear the sticky-less error state
+    return (e == cudaErrorMemoryAllocation) ? BLR_E_NOMEM : BLR_E_CUDA;
+}
+static int grow(blr_ctx* ctx, double** buf, size_t* cap, size_t bytes) {
+    if (*cap >= bytes) return 0;
+    if (*buf) {
+        BLR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        BLR_CUDA_OK(ctx, cudaFree(*buf));
+        *buf = nullptr;
+        *cap = 0;
+    }
+    BLR_CUDA_OK(ctx, cudaMalloc(buf, bytes));
+    *cap = bytes;
+    return 0;
+}
+int ensure_ws(blr_ctx* ctx, size_t bytes) { return grow(ctx, &ctx->ws, &ctx->ws_bytes, bytes); }
+int ensure_nbuf(blr_ctx* ctx, size_t bytes) { return grow(ctx, &ctx->nbuf, &ctx->nbuf_bytes, bytes); }
+
+// ---------------------------------------------------------------------------------------------- NCCL via dlopen
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string why;
+};
+static NcclApi* nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return &api;
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.handle) break;
+    }
+    if (!api.handle) {
+        api.why = std::string("dlopen(libnccl.so.2) failed: ") + dlerror();
+        return &api;
+    }
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+    api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.GetErrorString) {
+        api.why = "libnccl is missing required symbols";
+        api.handle = nullptr;
+    }
+    return &api;
+}
+static int nccl_fail(blr_ctx* ctx, ncclResult_t r, const char* what) {
+    NcclApi* a = nccl_api();
+    return set_err(ctx, BLR_E_NCCL, std::string(what) + ": " + (a->GetErrorString ? a->GetErrorString(r) : "?"));
+}
+
+static int noise_args(blr_ctx* ctx, const blr_noise* noise, int64_t N, const double** vec, double* scalar) {
+    if (!noise) return set_err(ctx, BLR_E_INVALID, "noise is NULL");
+    *vec = nullptr;
+    *scalar = 0.0;
+    if (noise->kind == BLR_NOISE_SCALAR) {
+        *scalar = noise->scalar;
+        return 0;
+    }
+    if (noise->kind == BLR_NOISE_VECTOR) {
+        if (!noise->vec) return set_err(ctx, BLR_E_INVALID, "noise.vec is NULL");
+        if (noise->vec->n != N) return set_err(ctx, BLR_E_DIM, "length(diag(Σy)) != number of inputs");
+        *vec = noise->vec->p;
+        return 0;
+    }
+    return set_err(ctx, BLR_E_INVALID, "unknown noise kind");
+}
+
+}  // namespace blr
+
+using namespace blr;
+
+#define CTX_ENTER(ctx)                                                   \
+    do {                                                                 \
+        if (!(ctx)) return BLR_E_INVALID;                                \
+        cudaError_t _e = cudaSetDevice((ctx)->device);                   \
+        if (_e != cudaSuccess) return cuda_fail(ctx, _e, "cudaSetDevice"); \
+    } while (0)
+
+extern "C" {
+
+int blr_version(void) { return BLR_VERSION; }
+
+int blr_ctx_create(blr_ctx** out, int device) {
+    if (!out) return BLR_E_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return BLR_E_NODEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return BLR_E_NODEVICE;
+    if (prop.major != 10) return BLR_E_NODEVICE;  // sm_100a cubin only: no other architecture, no fallback
+    if (cudaSetDevice(device) != cudaSuccess) return BLR_E_CUDA;
+    blr_ctx* ctx = new (std::nothrow) blr_ctx();
+    if (!ctx) return BLR_E_NOMEM;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->small, (size_t)SMALL_TOTAL * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_info, sizeof(int));
+    if (e != cudaSuccess || ctx->sm_count * 16 > SMALL_SC) {
+        blr_ctx_destroy(ctx);
+        return BLR_E_CUDA;
+    }
+    ctx->small_bytes = (size_t)SMALL_TOTAL * sizeof(double);
+    *out = ctx;
+    return 0;
+}
+
+int blr_ctx_destroy(blr_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    blr_comm_destroy(ctx);
+    cudaFree(ctx->ws);
+    cudaFree(ctx->nbuf);
+    cudaFree(ctx->small);
+    cudaFree(ctx->d_info);
+    cudaFree(ctx->stage[0]);
+    cudaFree(ctx->stage[1]);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+        if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < 8; ++i)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+const char* blr_last_error(const blr_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int blr_ctx_sync(blr_ctx* ctx) {
+    CTX_ENTER(ctx);
+    BLR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int blr_ctx_stream(blr_ctx* ctx, void** stream_out) {
+    if (!ctx || !stream_out) return BLR_E_INVALID;
+    *stream_out = (void*)ctx->stream;
+    return 0;
+}
+int64_t blr_launch_count(const blr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int blr_last_timings(blr_ctx* ctx, double* out8) {
+    CTX_ENTER(ctx);
+    if (!out8) return BLR_E_INVALID;
+    for (int i = 0; i < 8; ++i) out8[i] = 0.0;
+    BLR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms;
+    if (ctx->ev_valid[0]) {
+        for (int i = 0; i < 3; ++i) {
+            BLR_CUDA_OK(ctx, cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]));
+            out8[i] = ms;
+        }
+    }
+    if (ctx->ev_valid[3]) {
+        BLR_CUDA_OK(ctx, cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
+        out8[3] = ms;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- NCCL
+int blr_nccl_unique_id(void* out128) {
+    NcclApi* a = nccl_api();
+    if (!a->handle || !out128) return BLR_E_NCCL;
+    ncclUniqueId id;
+    if (a->GetUniqueId(&id) != ncclSuccess) return BLR_E_NCCL;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(out128, &id, 128);
+    return 0;
+}
+int blr_comm_init_rank(blr_ctx* ctx, const void* id128, int nranks, int rank) {
+    CTX_ENTER(ctx);
+    NcclApi* a = nccl_api();
+    if (!a->handle) return set_err(ctx, BLR_E_NCCL, a->why);
+    if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return set_err(ctx, BLR_E_INVALID, "bad communicator args");
+    blr_comm_destroy(ctx);
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclComm_t comm;
+    ncclResult_t r = a->CommInitRank(&comm, nranks, id, rank);
+    if (r != ncclSuccess) return nccl_fail(ctx, r, "ncclCommInitRank");
+    ctx->nccl_comm = (void*)comm;
+    ctx->nranks = nranks;
+    ctx->rank = rank;
+    return 0;
+}
+int blr_comm_destroy(blr_ctx* ctx) {
+    if (!ctx || !ctx->nccl_comm) return 0;
+    NcclApi* a = nccl_api();
+    if (a->handle) a->CommDestroy((ncclComm_t)ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+    ctx->nranks = 1;
+    ctx->rank = 0;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- handles
+static int check_x_shape(blr_ctx* ctx, int64_t D, int64_t N, int64_t ld, int layout) {
+    if (D < 1 || N < 0) return set_err(ctx, BLR_E_INVALID, "bad design-matrix shape");
+    if (layout != BLR_COLVECS && layout != BLR_ROWVECS) return set_err(ctx, BLR_E_INVALID, "unknown layout");
+    const int64_t rows = (layout == BLR_COLVECS) ? D : N;
+    if (ld < std::max<int64_t>(rows, 1)) return set_err(ctx, BLR_E_INVALID, "leading dimension too small");
+    return 0;
+}
+
+int blr_x_alloc(blr_ctx* ctx, int64_t D, int64_t N, int layout, blr_x** out) {
+    CTX_ENTER(ctx);
+    if (!out) return BLR_E_INVALID;
+    const int64_t rows = (layout == BLR_COLVECS) ? D : N, cols = (layout == BLR_COLVECS) ? N : D;
+    const int64_t ld = std::max<int64_t>(rows + (rows & 1), 2);  // even leading dimension: 16-byte aligned columns
+    BLR_TRY(check_x_shape(ctx, D, N, ld, layout));
+    blr_x* x = new blr_x();
+    x->D = D;
+    x->N = N;
+    x->ld = ld;
+    x->layout = layout;
+    x->owned = true;
+    cudaError_t e = cudaMalloc(&x->p, std::max<size_t>((size_t)ld * cols * sizeof(double), 16));
+    if (e != cudaSuccess) {
+        delete x;
+        return cuda_fail(ctx, e, "cudaMalloc(X)");
+    }
+    *out = x;
+    return 0;
+}
+
+int blr_x_upload(blr_ctx* ctx, const double* host, int64_t D, int64_t N, int64_t ld, int layout, blr_x** out) {
+    CTX_ENTER(ctx);
+    if (!out || (!host && N > 0)) return set_err(ctx, BLR_E_INVALID, "null pointer");
+    BLR_TRY(check_x_shape(ctx, D, N, ld, layout));
+    blr_x* x = nullptr;
+    BLR_TRY(blr_x_alloc(ctx, D, N, layout, &x));
+    const int64_t rows = (layout == BLR_COLVECS) ? D : N, cols = (layout == BLR_COLVECS) ? N : D;
+    if (rows > 0 && cols > 0) {
+        cudaError_t e = cudaMemcpy2DAsync(x->p, (size_t)x->ld * sizeof(double), host, (size_t)ld * sizeof(double),
+                                          (size_t)rows * sizeof(double), (size_t)cols, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            blr_x_free(ctx, x);
+            return cuda_fail(ctx, e, "upload X");
+        }
+    }
+    *out = x;
+    return 0;
+}
+
+int blr_x_wrap_device(blr_ctx* ctx, const double* dev, int64_t D, int64_t N, int64_t ld, int layout, blr_x** out) {
+    if (!ctx || !out || !dev) return BLR_E_INVALID;
+    BLR_TRY(check_x_shape(ctx, D, N, ld, layout));
+    blr_x* x = new blr_x();
+    x->p = const_cast<double*>(dev);
+    x->D = D;
+    x->N = N;
+    x->ld = ld;
+    x->layout = layout;
+    x->owned = false;
+    *out = x;
+    return 0;
+}
+
+int blr_x_device_ptr(blr_ctx* ctx, const blr_x* x, double** dev_out, int64_t* ld_out) {
+    if (!ctx || !x) return BLR_E_INVALID;
+    if (dev_out) *dev_out = x->p;
+    if (ld_out) *ld_out = x->ld;
+    return 0;
+}
+
+int blr_x_free(blr_ctx* ctx, blr_x* x) {
+    if (!x) return 0;
+    if (ctx) cudaSetDevice(ctx->device);
+    if (x->owned && x->p) {
+        if (ctx && ctx->stream) cudaStreamSynchronize(ctx->stream);
+        cudaFree(x->p);
+    }
+    delete x;
+    return 0;
+}
+
+int blr_vec_alloc(blr_ctx* ctx, int64_t n, blr_vec** out) {
+    CTX_ENTER(ctx);
+    if (!out || n < 0) return BLR_E_INVALID;
+    blr_vec* v = new blr_vec();
+    v->n = n;
+    v->owned = true;
+    cudaError_t e = cudaMalloc(&v->p, std::max<size_t>((size_t)n * sizeof(double), 16));
+    if (e != cudaSuccess) {
+        delete v;
+        return cuda_fail(ctx, e, "cudaMalloc(vec)");
+    }
+    *out = v;
+    return 0;
+}
+int blr_vec_upload(blr_ctx* ctx, const double* host, int64_t n, blr_vec** out) {
+    CTX_ENTER(ctx);
+    if (!out || (!host && n > 0)) return set_err(ctx, BLR_E_INVALID, "null pointer");
+    blr_vec* v = nullptr;
+    BLR_TRY(blr_vec_alloc(ctx, n, &v));
+    if (n > 0) {
+        cudaError_t e = cudaMemcpyAsync(v->p, host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            blr_vec_free(ctx, v);
+            return cuda_fail(ctx, e, "upload vec");
+        }
+    }
+    *out = v;
+    return 0;
+}
+int blr_vec_wrap_device(blr_ctx* ctx, const double* dev, int64_t n, blr_vec** out) {
+    if (!ctx || !out || !dev || n < 0) return BLR_E_INVALID;
+    blr_vec* v = new blr_vec();
+    v->p = const_cast<double*>(dev);
+    v->n = n;
+    v->owned = false;
+    *out = v;
+    return 0;
+}
+int blr_vec_device_ptr(blr_ctx* ctx, const blr_vec* v, double** dev_out) {
+    if (!ctx || !v || !dev_out) return BLR_E_INVALID;
+    *dev_out = v->p;
+    return 0;
+}
+int blr_vec_download(blr_ctx* ctx, const blr_vec* v, double* host) {
+    CTX_ENTER(ctx);
+    if (!v || !host) return BLR_E_INVALID;
+    if (v->n == 0) return 0;
+    BLR_CUDA_OK(ctx, cudaMemcpyAsync(host, v->p, (size_t)v->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    BLR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int blr_vec_free(blr_ctx* ctx, blr_vec* v) {
+    if (!v) return 0;
+    if (ctx) cudaSetDevice(ctx->device);
+    if (v->owned && v->p) {
+        if (ctx && ctx->stream) cudaStreamSynchronize(ctx->stream);
+        cudaFree(v->p);
+    }
+    delete v;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- synthetic data
+int blr_x_synth(blr_ctx* ctx, blr_x* x, uint64_t seed, int64_t n_offset) {
+    CTX_ENTER(ctx);
+    if (!x) return BLR_E_INVALID;
+    if (x->layout != BLR_COLVECS) return set_err(ctx, BLR_E_INVALID, "blr_x_synth generates ColVecs data");
+    return synth_normal(ctx, x->p, x->D, x->N, x->ld, seed, 0, n_offset);
+}
+int blr_vec_synth_noise(blr_ctx* ctx, blr_vec* sigma2, uint64_t seed, int64_t n_offset) {
+    CTX_ENTER(ctx);
+    if (!sigma2) return BLR_E_INVALID;
+    return synth_noise(ctx, sigma2->p, sigma2->n, seed, n_offset);
+}
+int blr_vec_synth_targets(blr_ctx* ctx, const blr_x* x, const blr_vec* sigma2, uint64_t seed, int64_t n_offset,
+                          blr_vec* y) {
+    CTX_ENTER(ctx);
+    if (!x || !sigma2 || !y) return BLR_E_INVALID;
+    if (sigma2->n != x->N || y->n != x->N) return set_err(ctx, BLR_E_DIM, "vector lengths do not match X");
+    return synth_targets(ctx, x, sigma2->p, seed, n_offset, y->p);
+}
+
+int blr_x_rff(blr_ctx* ctx, const blr_x* xin, const double* W, const double* b, int64_t D, blr_x** out) {
+    CTX_ENTER(ctx);
+    if (!xin || !W || !b || !out || D < 1) return set_err(ctx, BLR_E_INVALID, "bad rff arguments");
+    const int64_t din = xin->D;
+    double *Wd = nullptr, *bd = nullptr;
+    blr_x* phi = nullptr;
+    BLR_TRY(blr_x_alloc(ctx, D, xin->N, BLR_COLVECS, &phi));
+    cudaError_t e = cudaMalloc(&Wd, (size_t)D * din * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&bd, (size_t)D * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(Wd, W, (size_t)D * din * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bd, b, (size_t)D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    int rc = (e == cudaSuccess) ? rff_features(ctx, xin, Wd, bd, D, phi->p, phi->ld) : cuda_fail(ctx, e, "rff upload");
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(Wd);
+    cudaFree(bd);
+    if (rc != 0) {
+        blr_x_free(ctx, phi);
+        return rc;
+    }
+    *out = phi;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- inference
+int blr_stats_create(blr_ctx* ctx, int64_t D, blr_stats** out) {
+    CTX_ENTER(ctx);
+    if (!out || D < 1 || D > SMALL_VEC) return set_err(ctx, BLR_E_INVALID, "bad D (1 <= D <= 16384)");
+    blr_stats* s = new blr_stats();
+    s->D = D;
+    cudaError_t e = cudaMalloc(&s->p, (size_t)s->len() * sizeof(double));
+    if (e != cudaSuccess) {
+        delete s;
+        return cuda_fail(ctx, e, "cudaMalloc(stats)");
+    }
+    *out = s;
+    return blr_stats_zero(ctx, s);
+}
+int blr_stats_free(blr_ctx* ctx, blr_stats* s) {
+    if (!s) return 0;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(s->p);
+    delete s;
+    return 0;
+}
+int blr_stats_zero(blr_ctx* ctx, blr_stats* s) {
+    CTX_ENTER(ctx);
+    if (!s) return BLR_E_INVALID;
+    BLR_CUDA_OK(ctx, cudaMemsetAsync(s->p, 0, (size_t)s->len() * sizeof(double), ctx->stream));
+    return 0;
+}
+
+int blr_stats_accumulate(blr_ctx* ctx, blr_stats* s, const double* mw_host, const blr_x* x, const blr_vec* y,
+                         const blr_noise* noise) {
+    CTX_ENTER(ctx);
+    if (!s || !x || !y || !mw_host) return set_err(ctx, BLR_E_INVALID, "null argument");
+    if (x->D != s->D) return set_err(ctx, BLR_E_INVALID, "size(X, 1) != length(mw)");
+    if (y->n != x->N) return set_err(ctx, BLR_E_DIM, "length(y) != size(fx.x.X, 2)");
+    const double* sig = nullptr;
+    double sig_scalar = 0.0;
+    BLR_TRY(noise_args(ctx, noise, x->N, &sig, &sig_scalar));
+    bool zero = true;
+    for (int64_t i = 0; i < s->D; ++i)
+        if (mw_host[i] != 0.0) {
+            zero = false;
+            break;
+        }
+    double* mwd = ctx->small + SMALL_MW;
+    if (!zero)
+        BLR_CUDA_OK(ctx, cudaMemcpyAsync(mwd, mw_host, (size_t)s->D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return gram_accumulate(ctx, s, mwd, zero, x, y->p, sig, sig_scalar);
+}
+
+int blr_stats_accumulate_host(blr_ctx* ctx, blr_stats* s, const double* mw_host, const double* X, int64_t D, int64_t N,
+                              int64_t ld, int layout, const double* y, int noise_kind, double noise_scalar,
+                              const double* sigma2_host, int64_t chunk) {
+    CTX_ENTER(ctx);
+    if (!s || !mw_host || (N > 0 && (!X || !y))) return set_err(ctx, BLR_E_INVALID, "null argument");
+    if (D != s->D) return set_err(ctx, BLR_E_INVALID, "size(X, 1) != length(mw)");
+    BLR_TRY(check_x_shape(ctx, D, N, ld, layout));
+    if (noise_kind != BLR_NOISE_SCALAR && noise_kind != BLR_NOISE_VECTOR) return set_err(ctx, BLR_E_INVALID, "unknown noise kind");
+    if (noise_kind == BLR_NOISE_VECTOR && N > 0 && !sigma2_host) return set_err(ctx, BLR_E_INVALID, "sigma2_host is NULL");
+    if (N == 0) return 0;
+    if (chunk <= 0) chunk = 1 << 16;
+    chunk = std::min<int64_t>((chunk + 15) / 16 * 16, (N + 15) / 16 * 16);
+    // staging slot: X chunk (D x chunk, ld = D rounded to even; or chunk x D) | y chunk | σ² chunk
+    const int64_t ldx = (layout == BLR_COLVECS) ? D + (D & 1) : chunk;
+    const size_t x_elems = (size_t)((layout == BLR_COLVECS) ? ldx * chunk : chunk * D);
+    const size_t slot_bytes = (x_elems + 2 * (size_t)chunk) * sizeof(double);
+    if (!ctx->copy_stream) {
+        BLR_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            BLR_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+            BLR_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming));
+        }
+    }
+    if (ctx->stage_bytes < slot_bytes) {
+        BLR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        BLR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        for (int i = 0; i < 2; ++i) {
+            if (ctx->stage[i]) BLR_CUDA_OK(ctx, cudaFree(ctx->stage[i]));
+            ctx->stage[i] = nullptr;
+        }
+        ctx->stage_bytes = 0;
+        for (int i = 0; i < 2; ++i) BLR_CUDA_OK(ctx, cudaMalloc(&ctx->stage[i], slot_bytes));
+        ctx->stage_bytes = slot_bytes;
+    }
+    bool zero = true;
+    for (int64_t i = 0; i < D; ++i)
+        if (mw_host[i] != 0.0) {
+            zero = false;
+            break;
+        }
+    double* mwd = ctx->small + SMALL_MW;
+    if (!zero)
+        BLR_CUDA_OK(ctx, cudaMemcpyAsync(mwd, mw_host, (size_t)D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    int it = 0;
+    for (int64_t a = 0; a < N; a += chunk, ++it) {
+        const int64_t nb = std::min(chunk, N - a);
+        const int b = it & 1;
+        double* xs = ctx->stage[b];
+        double* ys = xs + x_elems;
+        double* ss = ys + chunk;
+        if (it >= 2) BLR_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[b], 0));
+        if (layout == BLR_COLVECS)
+            BLR_CUDA_OK(ctx, cudaMemcpy2DAsync(xs, (size_t)ldx * sizeof(double), X + a * ld, (size_t)ld * sizeof(double),
+                                               (size_t)D * sizeof(double), (size_t)nb, cudaMemcpyHostToDevice,
+                                               ctx->copy_stream));
+        else
+            BLR_CUDA_OK(ctx, cudaMemcpy2DAsync(xs, (size_t)ldx * sizeof(double), X + a, (size_t)ld * sizeof(double),
+                                               (size_t)nb * sizeof(double), (size_t)D, cudaMemcpyHostToDevice,
+                                               ctx->copy_stream));
+        BLR_CUDA_OK(ctx, cudaMemcpyAsync(ys, y + a, (size_t)nb * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (noise_kind == BLR_NOISE_VECTOR)
+            BLR_CUDA_OK(ctx, cudaMemcpyAsync(ss, sigma2_host + a, (size_t)nb * sizeof(double), cudaMemcpyHostToDevice,
+                                             ctx->copy_stream));
+        BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+        BLR_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
+        blr_x xv;
+        xv.p = xs;
+        xv.D = D;
+        xv.N = nb;
+        xv.ld = ldx;
+        xv.layout = layout;
+        BLR_TRY(gram_accumulate(ctx, s, mwd, zero, &xv, ys, noise_kind == BLR_NOISE_VECTOR ? ss : nullptr, noise_scalar));
+        BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev_consumed[b], ctx->stream));
+    }
+    return 0;
+}
+
+int blr_stats_allreduce(blr_ctx* ctx, blr_stats* s) {
+    CTX_ENTER(ctx);
+    if (!s) return BLR_E_INVALID;
+    if (!ctx->nccl_comm || ctx->nranks == 1) return 0;
+    NcclApi* a = nccl_api();
+    ncclResult_t r =
+        a->AllReduce(s->p, s->p, (size_t)s->len(), ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+    if (r != ncclSuccess) return nccl_fail(ctx, r, "ncclAllReduce");
+    return 0;
+}
+int blr_stats_device_ptr(blr_ctx* ctx, const blr_stats* s, double** dev_out, int64_t* len_out) {
+    if (!ctx || !s) return BLR_E_INVALID;
+    if (dev_out) *dev_out = s->p;
+    if (len_out) *len_out = s->len();
+    return 0;
+}
+int blr_stats_download(blr_ctx* ctx, const blr_stats* s, double* host) {
+    CTX_ENTER(ctx);
+    if (!s || !host) return BLR_E_INVALID;
+    BLR_CUDA_OK(ctx, cudaMemcpyAsync(host, s->p, (size_t)s->len() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    BLR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int blr_stats_upload(blr_ctx* ctx, blr_stats* s, const double* host) {
+    CTX_ENTER(ctx);
+    if (!s || !host) return BLR_E_INVALID;
+    BLR_CUDA_OK(ctx, cudaMemcpyAsync(s->p, host, (size_t)s->len() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    BLR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int blr_infer_from_stats(blr_ctx* ctx, const blr_prior* prior, const blr_stats* s, double* logpdf_out, double* m_post,
+                         double* T_post, double* L_post, blr_post** post_out) {
+    CTX_ENTER(ctx);
+    if (!prior || !s || !prior->mw || !prior->lambda) return set_err(ctx, BLR_E_INVALID, "null argument");
+    return infer_solve(ctx, prior, s, logpdf_out, m_post, T_post, L_post, post_out);
+}
+
+int blr_infer(blr_ctx* ctx, const blr_prior* prior, const blr_x* x, const blr_vec* y, const blr_noise* noise,
+              double* logpdf_out, double* m_post, double* T_post, double* L_post, blr_post** post_out) {
+    CTX_ENTER(ctx);
+    if (!prior || !x) return set_err(ctx, BLR_E_INVALID, "null argument");
+    blr_stats* s = nullptr;
+    BLR_TRY(blr_stats_create(ctx, x->D, &s));
+    int rc = blr_stats_accumulate(ctx, s, prior->mw, x, y, noise);
+    if (rc == 0) rc = blr_stats_allreduce(ctx, s);
+    if (rc == 0) rc = blr_infer_from_stats(ctx, prior, s, logpdf_out, m_post, T_post, L_post, post_out);
+    blr_stats_free(ctx, s);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------- prediction
+int blr_post_create(blr_ctx* ctx, const blr_prior* prior, int64_t D, blr_post** out) {
+    CTX_ENTER(ctx);
+    if (!prior || !out || !prior->mw || !prior->lambda || D < 1 || D > SMALL_VEC)
+        return set_err(ctx, BLR_E_INVALID, "bad prior");
+    return post_from_prior(ctx, prior, D, out);
+}
+int blr_post_free(blr_ctx* ctx, blr_post* p) {
+    if (!p) return 0;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    }
+    post_release(p);
+    return 0;
+}
+int blr_post_dim(const blr_post* p, int64_t* D_out) {
+    if (!p || !D_out) return BLR_E_INVALID;
+    *D_out = p->D;
+    return 0;
+}
+
+int blr_mean_var_dev(blr_ctx* ctx, blr_post* p, const blr_x* x, const blr_noise* noise, double* mean_dev,
+                     double* var_dev) {
+    CTX_ENTER(ctx);
+    if (!p || !x) return set_err(ctx, BLR_E_INVALID, "null argument");
+    if (x->D != p->D) return set_err(ctx, BLR_E_INVALID, "size(X, 1) != length(mw)");
+    const double* sig = nullptr;
+    double sig_scalar = 0.0;
+    BLR_TRY(noise_args(ctx, noise, x->N, &sig, &sig_scalar));
+    return predict_mean_var(ctx, p, x, sig, sig_scalar, mean_dev, var_dev);
+}
+
+int blr_mean_var(blr_ctx* ctx, blr_post* p, const blr_x* x, const blr_noise* noise, double* mean_host,
+                 double* var_host) {
+    CTX_ENTER(ctx);
+    if (!p || !x) return set_err(ctx, BLR_E_INVALID, "null argument");
+    const int64_t N = x->N;
+    if (N == 0) return 0;
+    double* buf = nullptr;
+    BLR_CUDA_OK(ctx, cudaMalloc(&buf, (size_t)2 * N * sizeof(double)));
+    int rc = blr_mean_var_dev(ctx, p, x, noise, mean_host ? buf : nullptr, var_host ? buf + N : nullptr);
+    cudaError_t e = cudaSuccess;
+    if (rc == 0 && mean_host)
+        e = cudaMemcpyAsync(mean_host, buf, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (rc == 0 && e == cudaSuccess && var_host)
+        e = cudaMemcpyAsync(var_host, buf + N, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(buf);
+    if (rc != 0) return rc;
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "download mean/var");
+    if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "mean_var sync");
+    return 0;
+}
+
+int blr_cov(blr_ctx* ctx, blr_post* p, const blr_x* x, const blr_noise* noise, double* C_host) {
+    CTX_ENTER(ctx);
+    if (!p || !x || !C_host) return set_err(ctx, BLR_E_INVALID, "null argument");
+    if (x->D != p->D) return set_err(ctx, BLR_E_INVALID, "size(X, 1) != length(mw)");
+    const int64_t N = x->N;
+    if (N == 0) return 0;
+    const double* sig = nullptr;
+    double sig_scalar = 0.0;
+    BLR_TRY(noise_args(ctx, noise, N, &sig, &sig_scalar));
+    double* C = nullptr;
+    BLR_CUDA_OK(ctx, cudaMalloc(&C, (size_t)N * N * sizeof(double)));
+    int rc = predict_cov(ctx, p, x, sig, sig_scalar, C);
+    cudaError_t e = cudaSuccess;
+    if (rc == 0) e = cudaMemcpyAsync(C_host, C, (size_t)N * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(C);
+    if (rc != 0) return rc;
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "download cov");
+    if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "cov sync");
+    return 0;
+}
+
+int blr_rand_weights(blr_ctx* ctx, blr_post* p, int64_t S, const double* Z, uint64_t seed, double* W_host) {
+    CTX_ENTER(ctx);
+    if (!p || !W_host || S < 0) return set_err(ctx, BLR_E_INVALID, "null argument");
+    if (S == 0) return 0;
+    const int64_t D = p->D;
+    double* buf = nullptr;
+    BLR_CUDA_OK(ctx, cudaMalloc(&buf, (size_t)2 * (D + 1) * S * sizeof(double)));
+    double *Zd = buf, *Wd = buf + (D + 1) * S;
+    int rc = 0;
+    cudaError_t e = cudaSuccess;
+    if (Z)
+        e = cudaMemcpyAsync(Zd, Z, (size_t)D * S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    else
+        rc = synth_normal(ctx, Zd, D, S, D, seed, 5, 0);
+    if (rc == 0 && e == cudaSuccess) rc = sample_weights(ctx, p, S, Zd, Wd);
+    if (rc == 0 && e == cudaSuccess)
+        e = cudaMemcpyAsync(W_host, Wd, (size_t)D * S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(buf);
+    if (rc != 0) return rc;
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "rand_weights copy");
+    if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "rand_weights sync");
+    return 0;
+}
+
+int blr_rand_finite_dev(blr_ctx* ctx, blr_post* p, const blr_x* x, const blr_noise* noise, int64_t S,
+                        const double* Zw_host, const double* Zy_dev, uint64_t seed, double* Y_dev) {
+    CTX_ENTER(ctx);
+    if (!p || !x || !Y_dev || S < 0) return set_err(ctx, BLR_E_INVALID, "null argument");
+    if (x->D != p->D) return set_err(ctx, BLR_E_INVALID, "size(X, 1) != length(mw)");
+    if (S == 0 || x->N == 0) return 0;
+    const int64_t D = p->D;
+    const double* sig = nullptr;
+    double sig_scalar = 0.0;
+    BLR_TRY(noise_args(ctx, noise, x->N, &sig, &sig_scalar));
+    double* buf = nullptr;
+    BLR_CUDA_OK(ctx, cudaMalloc(&buf, (size_t)2 * (D + 1) * S * sizeof(double)));
+    double *Zd = buf, *Wd = buf + (D + 1) * S;
+    int rc = 0;
+    cudaError_t e = cudaSuccess;
+    if (Zw_host)
+        e = cudaMemcpyAsync(Zd, Zw_host, (size_t)D * S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    else
+        rc = synth_normal(ctx, Zd, D, S, D, seed, 5, 0);
+    if (rc == 0 && e == cudaSuccess) rc = sample_weights(ctx, p, S, Zd, Wd);
+    if (rc == 0 && e == cudaSuccess) rc = sample_finite(ctx, x, Wd, S, sig, sig_scalar, Zy_dev, seed, Y_dev);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(buf);
+    if (rc != 0) return rc;
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "rand_finite copy");
+    if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "rand_finite sync");
+    return 0;
+}
+
+int blr_rand_finite(blr_ctx* ctx, blr_post* p, const blr_x* x, const blr_noise* noise, int64_t S, const double* Zw,
+                    const double* Zy, uint64_t seed, double* Y_host) {
+    CTX_ENTER(ctx);
+    if (!p || !x || !Y_host || S < 0) return set_err(ctx, BLR_E_INVALID, "null argument");
+    const int64_t N = x->N;
+    if (S == 0 || N == 0) return 0;
+    double *Yd = nullptr, *Zyd = nullptr;
+    BLR_CUDA_OK(ctx, cudaMalloc(&Yd, (size_t)N * S * sizeof(double)));
+    cudaError_t e = cudaSuccess;
+    if (Zy) {
+        e = cudaMalloc(&Zyd, (size_t)N * S * sizeof(double));
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(Zyd, Zy, (size_t)N * S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    }
+    int rc = (e == cudaSuccess) ? blr_rand_finite_dev(ctx, p, x, noise, S, Zw, Zyd, seed, Yd) : 0;
+    if (rc == 0 && e == cudaSuccess)
+        e = cudaMemcpyAsync(Y_host, Yd, (size_t)N * S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(Yd);
+    cudaFree(Zyd);
+    if (rc != 0) return rc;
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "rand_finite copy");
+    if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "rand_finite sync");
+    return 0;
+}
+
+int blr_apply_weights(blr_ctx* ctx, const blr_x* x, const double* w_host, double* out_host) {
+    CTX_ENTER(ctx);
+    if (!x || !w_host || !out_host) return set_err(ctx, BLR_E_INVALID, "null argument");
+    if (x->N == 0) return 0;
+    double* buf = nullptr;
+    BLR_CUDA_OK(ctx, cudaMalloc(&buf, (size_t)(x->N + x->D) * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(buf + x->N, w_host, (size_t)x->D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    int rc = (e == cudaSuccess) ? apply_weights(ctx, x, buf + x->N, buf) : 0;
+    if (rc == 0 && e == cudaSuccess)
+        e = cudaMemcpyAsync(out_host, buf, (size_t)x->N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(buf);
+    if (rc != 0) return rc;
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "apply_weights copy");
+    if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "apply_weights sync");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- calibration
+int blr_calibrate_dmma(blr_ctx* ctx, double* tflops_out) {
+    CTX_ENTER(ctx);
+    if (!tflops_out) return BLR_E_INVALID;
+    return calib_dmma(ctx, tflops_out);
+}
+int blr_calibrate_dfma(blr_ctx* ctx, double* tflops_out) {
+    CTX_ENTER(ctx);
+    if (!tflops_out) return BLR_E_INVALID;
+    return calib_dfma(ctx, tflops_out);
+}
+int blr_calibrate_hbm(blr_ctx* ctx, double* gbs_out) {
+    CTX_ENTER(ctx);
+    if (!gbs_out) return BLR_E_INVALID;
+    return calib_hbm(ctx, gbs_out);
+}
+
+}  // extern "C"

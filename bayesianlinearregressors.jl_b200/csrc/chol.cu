@@ -1,0 +1,551 @@
+// K3/K4: the replicated D x D phase -- blocked Cholesky, triangular solves, logdet, posterior assembly.
+//
+// Reference work replaced (src/bayesian_linear_regression.jl): `_cholesky(Λw)` :78, `_cholesky(Symmetric(Bt'Bt + I))`
+// :86, `Λεy.U' \ (Bt'δy)` + `logdet(Λεy)` :57, `Λεy \ (Bt'δy)` :64, `Λεy.U * Uw` :67, `Uw \ mεy` :68, `U'U` :92.
+// In closed form on the reduced statistics:
+//     Λ' = Λw + G,  L' = chol(Λ') (lower),  z = L'^-1 r,  m' = mw + L'^-T z,
+//     logpdf = -1/2 [ n log 2π + ℓ + q + logdet Λ' - logdet Λw - z'z ],   T = L'^T.
+// All matrices column-major; factors are stored LOWER (T of the reference is the transpose).
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "blockgemm.cuh"
+#include "common.cuh"
+#include "internal.h"
+
+namespace blr {
+
+constexpr int NB = 64;  // block size of the D x D phase
+
+// ---------------------------------------------------------------------------------------------
+// Factor a 64 x 64 diagonal block held in shared memory (Ls[c * 65 + r], lower part used).
+// Blocks smaller than 64 are padded with the identity by the caller.  Returns (to all threads) the
+// 1-based index of the first non-positive pivot, or 0.
+__device__ int factor_block_smem(double* Ls, int nthreads) {
+    __shared__ int fail;
+    if (threadIdx.x == 0) fail = 0;
+    __syncthreads();
+    for (int k = 0; k < NB; ++k) {
+        if (threadIdx.x == 0) {
+            const double d = Ls[k * 65 + k];
+            if (!(d > 0.0) && fail == 0) fail = k + 1;
+            Ls[k * 65 + k] = sqrt(d);
+        }
+        __syncthreads();
+        const double inv = 1.0 / Ls[k * 65 + k];
+        for (int i = k + 1 + threadIdx.x; i < NB; i += nthreads) Ls[k * 65 + i] *= inv;
+        __syncthreads();
+        const int m = NB - k - 1;
+        for (int e = threadIdx.x; e < m * m; e += nthreads) {
+            const int j = k + 1 + e / m, i = k + 1 + e % m;
+            if (i >= j) Ls[j * 65 + i] -= Ls[k * 65 + i] * Ls[k * 65 + j];
+        }
+        __syncthreads();
+    }
+    return fail;
+}
+
+// Panel step j of the right-looking Cholesky: every CTA factors the diagonal block A[j0:j0+64, j0:j0+64]
+// redundantly in shared memory (saves a launch + a dependency), CTA 0 writes it back, and each CTA solves
+// 128 rows of the panel below:  L21 = A21 * L11^-T  (one thread per row, unrolled substitution in registers).
+constexpr int PANEL_THREADS = 128;
+__global__ void __launch_bounds__(PANEL_THREADS) potrf_panel_kernel(double* __restrict__ A, int64_t ld, int D, int j0,
+                                                                    int* __restrict__ info) {
+    __shared__ double Ls[NB * 65];
+    const int nbj = min(NB, D - j0);
+    for (int e = threadIdx.x; e < NB * NB; e += PANEL_THREADS) {
+        const int r = e % NB, c = e / NB;
+        double v = (r == c) ? 1.0 : 0.0;
+        if (r < nbj && c < nbj && r >= c) v = A[(int64_t)(j0 + c) * ld + j0 + r];
+        Ls[c * 65 + r] = v;
+    }
+    __syncthreads();
+    const int fail = factor_block_smem(Ls, PANEL_THREADS);
+    if (blockIdx.x == 0) {
+        for (int e = threadIdx.x; e < NB * NB; e += PANEL_THREADS) {
+            const int r = e % NB, c = e / NB;
+            if (r < nbj && c < nbj) A[(int64_t)(j0 + c) * ld + j0 + r] = (r >= c) ? Ls[c * 65 + r] : 0.0;
+        }
+        if (threadIdx.x == 0 && fail != 0 && *info == 0) *info = j0 + fail;
+    }
+    const int row = j0 + NB + blockIdx.x * PANEL_THREADS + threadIdx.x;
+    if (row < D) {
+        double a[NB];
+#pragma unroll
+        for (int c = 0; c < NB; ++c) a[c] = A[(int64_t)(j0 + c) * ld + row];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+            const double xk = a[k] / Ls[k * 65 + k];
+            a[k] = xk;
+#pragma unroll
+            for (int c = k + 1; c < NB; ++c) a[c] = fma(-xk, Ls[k * 65 + c], a[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < NB; ++c) A[(int64_t)(j0 + c) * ld + row] = a[c];
+    }
+}
+
+// Trailing update of step j:  A22 -= L21 L21'  on the 64 x 64 blocks of the lower triangle (DMMA).
+__global__ void __launch_bounds__(bg::THREADS) potrf_update_kernel(double* __restrict__ A, int64_t ld, int D, int j0) {
+    __shared__ double smA[bg::SMEM_A], smB[bg::SMEM_B];
+    int bi, bj;
+    {
+        int i = 0;
+        const int idx = blockIdx.x;
+        while ((i + 1) * (i + 2) / 2 <= idx) ++i;
+        bi = i;
+        bj = idx - i * (i + 1) / 2;
+    }
+    const int r0 = j0 + NB + bi * NB, c0 = j0 + NB + bj * NB;
+    double acc[4][4][2];
+    acc_zero(acc);
+    // A operand: L[r0 + m, j0 + k] (m contiguous); B operand (k, n) = L[c0 + n, j0 + k] (n contiguous)
+    cta_gemm64<false>(acc, A + (int64_t)j0 * ld + r0, ld, D - r0, A + (int64_t)j0 * ld + c0, ld, D - c0, NB, smA, smB);
+    acc_foreach(acc, [&](int row, int col, double& v) {
+        const int gr = r0 + row, gc = c0 + col;
+        if (gr < D && gc < D && gr >= gc) A[(int64_t)gc * ld + gr] -= v;
+    });
+}
+
+__global__ void zero_strict_upper_kernel(double* __restrict__ A, int64_t ld, int D) {
+    const int64_t total = (int64_t)D * D;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(e % D), c = (int)(e / D);
+        if (r < c) A[(int64_t)c * ld + r] = 0.0;
+    }
+}
+
+int potrf_lower(blr_ctx* ctx, double* A, int64_t D64, int* info_dev) {
+    const int D = (int)D64;
+    cudaStream_t sm = ctx->stream;
+    BLR_CUDA_OK(ctx, cudaMemsetAsync(info_dev, 0, sizeof(int), sm));
+    for (int j0 = 0; j0 < D; j0 += NB) {
+        const int below = D - j0 - NB;
+        const int pgrid = below > 0 ? (below + PANEL_THREADS - 1) / PANEL_THREADS : 1;
+        potrf_panel_kernel<<<pgrid, PANEL_THREADS, 0, sm>>>(A, D64, D, j0, info_dev);
+        BLR_CHECK_LAUNCH(ctx, "potrf_panel_kernel");
+        if (below > 0) {
+            const int nblk = (below + NB - 1) / NB;
+            potrf_update_kernel<<<nblk * (nblk + 1) / 2, bg::THREADS, 0, sm>>>(A, D64, D, j0);
+            BLR_CHECK_LAUNCH(ctx, "potrf_update_kernel");
+        }
+    }
+    zero_strict_upper_kernel<<<std::min(ctx->sm_count * 4, (int)((D64 * D64 + 255) / 256)), 256, 0, sm>>>(A, D64, D);
+    BLR_CHECK_LAUNCH(ctx, "zero_strict_upper_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Triangular solves with a single right-hand side (single CTA; the D x D factor is streamed once).
+constexpr int TRSV_THREADS = 512;
+
+// L z = b
+__global__ void __launch_bounds__(TRSV_THREADS) trsv_forward_kernel(const double* __restrict__ L, int64_t ld, int D,
+                                                                    double* __restrict__ b) {
+    __shared__ double Ls[NB * 65];
+    __shared__ double zb[NB];
+    const int tid = threadIdx.x;
+    for (int j0 = 0; j0 < D; j0 += NB) {
+        const int nbj = min(NB, D - j0);
+        __syncthreads();
+        for (int e = tid; e < NB * NB; e += TRSV_THREADS) {
+            const int r = e % NB, c = e / NB;
+            Ls[c * 65 + r] = (r < nbj && c < nbj && r >= c) ? L[(int64_t)(j0 + c) * ld + j0 + r] : (r == c ? 1.0 : 0.0);
+        }
+        if (tid < NB) zb[tid] = (tid < nbj) ? b[j0 + tid] : 0.0;
+        __syncthreads();
+        if (tid < 32) {  // warp 0: substitution inside the block, lane owns rows lane and lane + 32
+            double x0 = zb[tid], x1 = zb[tid + 32];
+            for (int c = 0; c < NB; ++c) {
+                const double src = (c < 32) ? x0 : x1;
+                const double zc = __shfl_sync(0xffffffffu, src, c & 31) / Ls[c * 65 + c];
+                if (tid == (c & 31)) {
+                    if (c < 32) x0 = zc; else x1 = zc;
+                }
+                if (tid > c) x0 = fma(-zc, Ls[c * 65 + tid], x0);
+                if (tid + 32 > c) x1 = fma(-zc, Ls[c * 65 + tid + 32], x1);
+            }
+            zb[tid] = x0;
+            zb[tid + 32] = x1;
+        }
+        __syncthreads();
+        if (tid < nbj) b[j0 + tid] = zb[tid];
+        // rows below the block: b[i] -= Σ_c L[i, j0 + c] z_c   (column-major: coalesced over i)
+        for (int i = j0 + NB + tid; i < D; i += TRSV_THREADS) {
+            double acc = b[i];
+#pragma unroll 8
+            for (int c = 0; c < NB; ++c) acc = fma(-L[(int64_t)(j0 + c) * ld + i], zb[c], acc);
+            b[i] = acc;
+        }
+    }
+}
+
+// L' u = z
+__global__ void __launch_bounds__(TRSV_THREADS) trsv_backward_kernel(const double* __restrict__ L, int64_t ld, int D,
+                                                                     double* __restrict__ b) {
+    __shared__ double Ls[NB * 65];
+    __shared__ double zb[NB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nblk = (D + NB - 1) / NB;
+    for (int jb = nblk - 1; jb >= 0; --jb) {
+        const int j0 = jb * NB;
+        const int nbj = min(NB, D - j0);
+        __syncthreads();
+        // z_c -= Σ_{k >= j0 + 64} L[k, j0 + c] u_k : one warp per column, lanes stride over k (contiguous)
+        for (int c = warp; c < nbj; c += TRSV_THREADS / 32) {
+            const double* col = L + (int64_t)(j0 + c) * ld;
+            double acc = 0.0;
+            for (int k = j0 + NB + lane; k < D; k += 32) acc = fma(col[k], b[k], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) zb[c] = b[j0 + c] - acc;
+        }
+        for (int e = tid; e < NB * NB; e += TRSV_THREADS) {
+            const int r = e % NB, c = e / NB;
+            Ls[c * 65 + r] = (r < nbj && c < nbj && r >= c) ? L[(int64_t)(j0 + c) * ld + j0 + r] : (r == c ? 1.0 : 0.0);
+        }
+        if (tid >= nbj && tid < NB) zb[tid] = 0.0;
+        __syncthreads();
+        if (tid < 32) {  // solve the transposed 64 x 64 block from the bottom up
+            double x0 = zb[tid], x1 = zb[tid + 32];
+            for (int c = NB - 1; c >= 0; --c) {
+                const double src = (c < 32) ? x0 : x1;
+                const double uc = __shfl_sync(0xffffffffu, src, c & 31) / Ls[c * 65 + c];
+                if (tid == (c & 31)) {
+                    if (c < 32) x0 = uc; else x1 = uc;
+                }
+                // row i < c of L': (L')[i, c] = L[c, i]
+                if (tid < c) x0 = fma(-uc, Ls[tid * 65 + c], x0);
+                if (tid + 32 < c) x1 = fma(-uc, Ls[(tid + 32) * 65 + c], x1);
+            }
+            zb[tid] = x0;
+            zb[tid + 32] = x1;
+        }
+        __syncthreads();
+        if (tid < nbj) b[j0 + tid] = zb[tid];
+    }
+}
+
+int trsv_lower_forward(blr_ctx* ctx, const double* L, int64_t D, double* b) {
+    trsv_forward_kernel<<<1, TRSV_THREADS, 0, ctx->stream>>>(L, D, (int)D, b);
+    BLR_CHECK_LAUNCH(ctx, "trsv_forward_kernel");
+    return 0;
+}
+int trsv_lower_backward(blr_ctx* ctx, const double* L, int64_t D, double* b) {
+    trsv_backward_kernel<<<1, TRSV_THREADS, 0, ctx->stream>>>(L, D, (int)D, b);
+    BLR_CHECK_LAUNCH(ctx, "trsv_backward_kernel");
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) logdet_kernel(const double* __restrict__ L, int64_t ld, int D,
+                                                     double* __restrict__ out) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < D; i += 256) acc += log(L[(int64_t)i * ld + i]);
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) out[0] = 2.0 * acc;
+}
+int logdet_from_chol(blr_ctx* ctx, const double* L, int64_t D, double* out_dev) {
+    logdet_kernel<<<1, 256, 0, ctx->stream>>>(L, D, (int)D, out_dev);
+    BLR_CHECK_LAUNCH(ctx, "logdet_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// W = inv(L), lower triangular.  Diagonal 64 x 64 blocks are inverted by substitution; off-diagonal
+// blocks follow by block distance d = i - j:  W_ij = -W_ii Σ_{k=j}^{i-1} L_ik W_kj   (DMMA block GEMMs).
+__global__ void __launch_bounds__(NB) trtri_diag_kernel(const double* __restrict__ L, int64_t ld, int D,
+                                                        double* __restrict__ W) {
+    __shared__ double Ls[NB * 65];
+    const int j0 = blockIdx.x * NB, nbj = min(NB, D - j0), c = threadIdx.x;
+    for (int e = threadIdx.x; e < NB * NB; e += NB) {
+        const int r = e % NB, cc = e / NB;
+        Ls[cc * 65 + r] = (r < nbj && cc < nbj && r >= cc) ? L[(int64_t)(j0 + cc) * ld + j0 + r] : (r == cc ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    // thread c solves L x = e_c by forward substitution; x lives in registers (loops fully unrolled)
+    double x[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        double acc = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) acc = fma(-Ls[k * 65 + i], x[k], acc);  // x[k] == 0 for k < c
+        x[i] = (i >= c) ? acc / Ls[i * 65 + i] : 0.0;
+    }
+    __syncthreads();
+    // stage through shared memory (reusing Ls) so the global store is coalesced over rows
+#pragma unroll
+    for (int i = 0; i < NB; ++i) Ls[c * 65 + i] = x[i];
+    __syncthreads();
+    for (int e = threadIdx.x; e < NB * NB; e += NB) {
+        const int r = e % NB, cc = e / NB;
+        if (r < nbj && cc < nbj) W[(int64_t)(j0 + cc) * ld + j0 + r] = Ls[cc * 65 + r];
+    }
+}
+
+__global__ void __launch_bounds__(bg::THREADS) trtri_offdiag_kernel(const double* __restrict__ L, int64_t ld, int D,
+                                                                    double* W, int dist) {
+    __shared__ double smA[bg::SMEM_A], smB[bg::SMEM_B];
+    const int bj = blockIdx.x, bi = bj + dist;
+    const int r0 = bi * NB, c0 = bj * NB;
+    double acc[4][4][2];
+    acc_zero(acc);
+    for (int bk = bj; bk < bi; ++bk) {
+        const int k0 = bk * NB;
+        // A (m, k) = L[r0 + m, k0 + k];  B (k, n) = W[k0 + k, c0 + n]  (k contiguous)
+        cta_gemm64<true>(acc, L + (int64_t)k0 * ld + r0, ld, D - r0, W + (int64_t)c0 * ld + k0, ld, D - c0, NB, smA, smB);
+    }
+    // park the intermediate sum C in the destination block (this CTA is its only reader and writer)
+    acc_foreach(acc, [&](int row, int col, double& v) {
+        const int gr = r0 + row, gc = c0 + col;
+        if (gr < D && gc < D) W[(int64_t)gc * ld + gr] = v;
+    });
+    __threadfence_block();
+    __syncthreads();
+    // W_ij = -W_ii * C.   A (m, k) = W[r0 + m, r0 + k];  B (k, n) = C[k, n] = W[r0 + k, c0 + n] (k contiguous)
+    acc_zero(acc);
+    cta_gemm64<true>(acc, W + (int64_t)r0 * ld + r0, ld, D - r0, W + (int64_t)c0 * ld + r0, ld, D - c0, min(NB, D - r0),
+                     smA, smB);
+    __syncthreads();
+    acc_foreach(acc, [&](int row, int col, double& v) {
+        const int gr = r0 + row, gc = c0 + col;
+        if (gr < D && gc < D) W[(int64_t)gc * ld + gr] = -v;
+    });
+}
+
+int trtri_lower(blr_ctx* ctx, const double* L, double* W, int64_t D64) {
+    const int D = (int)D64, nblk = (D + NB - 1) / NB;
+    cudaStream_t sm = ctx->stream;
+    BLR_CUDA_OK(ctx, cudaMemsetAsync(W, 0, (size_t)D64 * D64 * sizeof(double), sm));
+    trtri_diag_kernel<<<nblk, NB, 0, sm>>>(L, D64, D, W);
+    BLR_CHECK_LAUNCH(ctx, "trtri_diag_kernel");
+    for (int dist = 1; dist < nblk; ++dist) {
+        trtri_offdiag_kernel<<<nblk - dist, bg::THREADS, 0, sm>>>(L, D64, D, W, dist);
+        BLR_CHECK_LAUNCH(ctx, "trtri_offdiag_kernel");
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Posterior assembly
+__global__ void add_inplace_kernel(double* __restrict__ A, const double* __restrict__ G, int64_t n) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+        A[e] += G[e];
+}
+__global__ void set_diag_kernel(double* __restrict__ A, const double* __restrict__ d, int D) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D; i += gridDim.x * blockDim.x) A[(int64_t)i * D + i] = d[i];
+}
+__global__ void transpose_square_kernel(const double* __restrict__ A, double* __restrict__ At, int D) {
+    __shared__ double tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = bx + threadIdx.x, c = by + j;
+        tile[j][threadIdx.x] = (r < D && c < D) ? A[(int64_t)c * D + r] : 0.0;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = by + threadIdx.x, c = bx + j;  // At[r, c] = A[c, r]
+        if (r < D && c < D) At[(int64_t)c * D + r] = tile[threadIdx.x][j];
+    }
+}
+// z'z (block reduce), m' = mw + u, logpdf
+__global__ void __launch_bounds__(256) dot_self_kernel(const double* __restrict__ z, int D, double* __restrict__ out) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < D; i += 256) acc = fma(z[i], z[i], acc);
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) out[0] = acc;
+}
+__global__ void finalize_kernel(const double* __restrict__ scal /* q, ℓ, n */, const double* __restrict__ sc,
+                                const double* __restrict__ mw, const double* __restrict__ u, int D,
+                                double* __restrict__ m_post, double* __restrict__ logpdf) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D; i += gridDim.x * blockDim.x) m_post[i] = mw[i] + u[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const double LOG2PI = 1.8378770664093454835606594728112;
+        const double q = scal[0], l = scal[1], n = scal[2];
+        // sc[0] = logdet Λw, sc[1] = logdet Λ', sc[2] = z'z
+        logpdf[0] = -0.5 * (n * LOG2PI + l + q + (sc[1] - sc[0]) - sc[2]);
+    }
+}
+
+void post_release(blr_post* p) {
+    if (!p) return;
+    cudaFree(p->mw);
+    cudaFree(p->L);
+    cudaFree(p->W);
+    cudaFree(p->Lam);
+    delete p;
+}
+
+static int alloc_post(blr_ctx* ctx, int64_t D, blr_post** out) {
+    blr_post* p = new blr_post();
+    p->D = D;
+    cudaError_t e = cudaMalloc(&p->mw, (size_t)D * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&p->L, (size_t)D * D * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&p->Lam, (size_t)D * D * sizeof(double));
+    if (e != cudaSuccess) {
+        post_release(p);
+        return cuda_fail(ctx, e, "cudaMalloc(post)");
+    }
+    *out = p;
+    return 0;
+}
+
+// Upload the prior precision as a dense column-major D x D device matrix.  For a Diagonal prior the
+// log-determinant and positivity check are done on the host (D numbers); returns info > 0 on failure.
+static int upload_prior_precision(blr_ctx* ctx, const blr_prior* prior, int64_t D, double* Lam_dev, double* logdet_host,
+                                  bool* have_logdet) {
+    cudaStream_t sm = ctx->stream;
+    *have_logdet = false;
+    if (prior->lambda_kind == BLR_LAMBDA_DIAGONAL) {
+        double ld = 0.0;
+        for (int64_t i = 0; i < D; ++i) {
+            if (!(prior->lambda[i] > 0.0)) return (int)(i + 1);
+            ld += log(prior->lambda[i]);
+        }
+        *logdet_host = ld;
+        *have_logdet = true;
+        double* dtmp = ctx->small + SMALL_DTMP;
+        BLR_CUDA_OK(ctx, cudaMemsetAsync(Lam_dev, 0, (size_t)D * D * sizeof(double), sm));
+        BLR_CUDA_OK(ctx, cudaMemcpyAsync(dtmp, prior->lambda, (size_t)D * sizeof(double), cudaMemcpyHostToDevice, sm));
+        set_diag_kernel<<<(int)((D + 255) / 256), 256, 0, sm>>>(Lam_dev, dtmp, (int)D);
+        BLR_CHECK_LAUNCH(ctx, "set_diag_kernel");
+        BLR_CUDA_OK(ctx, cudaStreamSynchronize(sm));  // dtmp / host buffer reuse
+        return 0;
+    }
+    if (prior->lambda_kind == BLR_LAMBDA_DENSE) {
+        const int64_t ld = prior->ld > 0 ? prior->ld : D;
+        if (ld < D) return set_err(ctx, BLR_E_INVALID, "prior.ld < D");
+        BLR_CUDA_OK(ctx, cudaMemcpy2DAsync(Lam_dev, (size_t)D * sizeof(double), prior->lambda, (size_t)ld * sizeof(double),
+                                           (size_t)D * sizeof(double), (size_t)D, cudaMemcpyHostToDevice, sm));
+        BLR_CUDA_OK(ctx, cudaStreamSynchronize(sm));
+        return 0;
+    }
+    return set_err(ctx, BLR_E_INVALID, "unknown lambda_kind");
+}
+
+static int read_info(blr_ctx* ctx, int* info_host) {
+    BLR_CUDA_OK(ctx, cudaMemcpyAsync(info_host, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    BLR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int post_from_prior(blr_ctx* ctx, const blr_prior* prior, int64_t D, blr_post** out) {
+    blr_post* p = nullptr;
+    BLR_TRY(alloc_post(ctx, D, &p));
+    cudaStream_t sm = ctx->stream;
+    double ldh;
+    bool have;
+    int r = upload_prior_precision(ctx, prior, D, p->Lam, &ldh, &have);
+    if (r != 0) {
+        post_release(p);
+        return r;
+    }
+    cudaError_t e = cudaMemcpyAsync(p->mw, prior->mw, (size_t)D * sizeof(double), cudaMemcpyHostToDevice, sm);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(p->L, p->Lam, (size_t)D * D * sizeof(double), cudaMemcpyDeviceToDevice, sm);
+    if (e != cudaSuccess) {
+        post_release(p);
+        return cuda_fail(ctx, e, "post upload");
+    }
+    r = potrf_lower(ctx, p->L, D, ctx->d_info);
+    int info = 0;
+    if (r == 0) r = read_info(ctx, &info);
+    if (r == 0 && info != 0) r = info;
+    if (r != 0) {
+        post_release(p);
+        return r;
+    }
+    *out = p;
+    return 0;
+}
+
+int post_ensure_W(blr_ctx* ctx, blr_post* p) {
+    if (p->has_W) return 0;
+    if (!p->W) BLR_CUDA_OK(ctx, cudaMalloc(&p->W, (size_t)p->D * p->D * sizeof(double)));
+    BLR_TRY(trtri_lower(ctx, p->L, p->W, p->D));
+    p->has_W = true;
+    return 0;
+}
+
+int infer_solve(blr_ctx* ctx, const blr_prior* prior, const blr_stats* st, double* logpdf_out, double* m_post,
+                double* T_post, double* L_post, blr_post** post_out) {
+    const int64_t D = st->D;
+    cudaStream_t sm = ctx->stream;
+    BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[4], sm));
+    blr_post* p = nullptr;
+    BLR_TRY(alloc_post(ctx, D, &p));
+    // scratch scalars live behind the prep partials in ctx->small
+    double* sc = ctx->small + SMALL_SC;    // [0] logdet Λw  [1] logdet Λ'  [2] z'z  [3] logpdf
+    double* rhs = ctx->small + SMALL_RHS;  // D doubles
+    double* mwd = ctx->small + SMALL_MW;
+    int rc = 0, info = 0;
+    double ldh = 0.0;
+    bool have = false;
+    auto fail = [&](int code) {
+        post_release(p);
+        return code;
+    };
+    if (D > SMALL_VEC) return fail(set_err(ctx, BLR_E_INVALID, "D > 16384 not supported"));
+
+    // logdet Λw (and PosDef check of the prior): Diagonal on host, dense via a device Cholesky of a copy in p->L.
+    rc = upload_prior_precision(ctx, prior, D, p->Lam, &ldh, &have);
+    if (rc != 0) return fail(rc);
+    if (!have) {
+        BLR_CUDA_OK(ctx, cudaMemcpyAsync(p->L, p->Lam, (size_t)D * D * sizeof(double), cudaMemcpyDeviceToDevice, sm));
+        rc = potrf_lower(ctx, p->L, D, ctx->d_info);
+        if (rc == 0) rc = logdet_from_chol(ctx, p->L, D, sc + 0);
+        if (rc == 0) rc = read_info(ctx, &info);
+        if (rc != 0) return fail(rc);
+        if (info != 0) return fail(info);
+    } else {
+        BLR_CUDA_OK(ctx, cudaMemcpyAsync(sc + 0, &ldh, sizeof(double), cudaMemcpyHostToDevice, sm));
+    }
+    BLR_CUDA_OK(ctx, cudaMemcpyAsync(mwd, prior->mw, (size_t)D * sizeof(double), cudaMemcpyHostToDevice, sm));
+
+    // Λ' = Λw + G  (kept in p->Lam), factor a copy
+    const int64_t n2 = D * D;
+    add_inplace_kernel<<<(int)std::min<int64_t>((n2 + 255) / 256, ctx->sm_count * 8), 256, 0, sm>>>(p->Lam, st->G(), n2);
+    BLR_CHECK_LAUNCH(ctx, "add_inplace_kernel");
+    BLR_CUDA_OK(ctx, cudaMemcpyAsync(p->L, p->Lam, (size_t)n2 * sizeof(double), cudaMemcpyDeviceToDevice, sm));
+    rc = potrf_lower(ctx, p->L, D, ctx->d_info);
+    if (rc != 0) return fail(rc);
+    // z = L'^-1 r ; z'z ; u = L'^-T z ; m' = mw + u
+    BLR_CUDA_OK(ctx, cudaMemcpyAsync(rhs, st->r(), (size_t)D * sizeof(double), cudaMemcpyDeviceToDevice, sm));
+    rc = trsv_lower_forward(ctx, p->L, D, rhs);
+    if (rc != 0) return fail(rc);
+    dot_self_kernel<<<1, 256, 0, sm>>>(rhs, (int)D, sc + 2);
+    BLR_CHECK_LAUNCH(ctx, "dot_self_kernel");
+    rc = trsv_lower_backward(ctx, p->L, D, rhs);
+    if (rc == 0) rc = logdet_from_chol(ctx, p->L, D, sc + 1);
+    if (rc != 0) return fail(rc);
+    finalize_kernel<<<(int)std::min<int64_t>((D + 255) / 256, 64), 256, 0, sm>>>(st->scal(), sc, mwd, rhs, (int)D, p->mw,
+                                                                              sc + 3);
+    BLR_CHECK_LAUNCH(ctx, "finalize_kernel");
+    BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[5], sm));
+    ctx->ev_valid[3] = true;
+
+    rc = read_info(ctx, &info);
+    if (rc != 0) return fail(rc);
+    if (info != 0) return fail(info);
+
+    if (logpdf_out) BLR_CUDA_OK(ctx, cudaMemcpyAsync(logpdf_out, sc + 3, sizeof(double), cudaMemcpyDeviceToHost, sm));
+    if (m_post) BLR_CUDA_OK(ctx, cudaMemcpyAsync(m_post, p->mw, (size_t)D * sizeof(double), cudaMemcpyDeviceToHost, sm));
+    if (L_post) BLR_CUDA_OK(ctx, cudaMemcpyAsync(L_post, p->Lam, (size_t)n2 * sizeof(double), cudaMemcpyDeviceToHost, sm));
+    if (T_post) {
+        // T = L'^T (upper).  Transpose into the (not yet built) W buffer, then download.
+        if (!p->W) BLR_CUDA_OK(ctx, cudaMalloc(&p->W, (size_t)n2 * sizeof(double)));
+        dim3 grid((unsigned)((D + 31) / 32), (unsigned)((D + 31) / 32)), block(32, 8);
+        transpose_square_kernel<<<grid, block, 0, sm>>>(p->L, p->W, (int)D);
+        BLR_CHECK_LAUNCH(ctx, "transpose_square_kernel");
+        BLR_CUDA_OK(ctx, cudaMemcpyAsync(T_post, p->W, (size_t)n2 * sizeof(double), cudaMemcpyDeviceToHost, sm));
+    }
+    BLR_CUDA_OK(ctx, cudaStreamSynchronize(sm));
+    if (post_out)
+        *post_out = p;
+    else
+        post_release(p);
+    return 0;
+}
+
+}  // namespace blr

@@ -1,0 +1,479 @@
+// K0/K1: fused noise-scale + SYRK Gram accumulation
+//
+//     G = X S X'   r = X S δ   q = δ'Sδ   ℓ = Σ log σ²_n        S = diag(1/σ²),  δ = y - X'mw
+//
+// These are the O(N D²) statistics behind `__compute_inference_quantities`
+// (reference src/bayesian_linear_regression.jl:72-89: Bt = Uy^-T X' Uw^-1 at :81, δy at :82,
+// logdet Σy + |δy|² at :84, Bt'Bt at :86, Bt'δy at :57/:64) written in closed form so that the two
+// N x D temporaries of the reference never exist.
+//
+// Data layout in HBM: X is the D x N column-major ColVecs matrix (one observation = D contiguous
+// doubles); s_n = 1/σ²_n and t_n = s_n δ_n are N-vectors produced by the prep kernel.
+//
+// Fast path (gram_tma_kernel): the lower triangle of G is cut into 128 x 128 tiles; a CTA owns one
+// tile and one contiguous range of observations (split-N), keeps the tile in registers as fp64
+// tensor-core accumulators (DMMA.8x8x4), and streams its two 128-row panels of X through a 4-stage
+// shared-memory ring filled by TMA bulk copies (cp.async.bulk + mbarrier) issued by a dedicated
+// producer warp.  Partial tiles go to a workspace and are summed in a FIXED order by
+// gram_reduce_kernel, so results are bit-reproducible run to run.
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace blr {
+
+// ====================================================================== K0: per-observation prep
+// s_n = 1/σ²_n, t_n = s_n δ_n, block partials of q = Σ s δ² and ℓ = Σ log σ².
+// LAYOUT 0 = ColVecs, 1 = RowVecs.  HAS_MEAN = prior mean is non-zero (δ needs a pass over X).
+constexpr int PREP_THREADS = 256;
+
+template <int LAYOUT, bool HAS_MEAN>
+__global__ void __launch_bounds__(PREP_THREADS) prep_kernel(const double* __restrict__ X, int64_t ld, int D, int64_t N,
+                                                            int64_t npad, const double* __restrict__ y,
+                                                            const double* __restrict__ sigma2, double sigma2_scalar,
+                                                            const double* __restrict__ mw, double* __restrict__ s,
+                                                            double* __restrict__ t, double* __restrict__ partial) {
+    __shared__ double red[32];
+    double q = 0.0, l = 0.0;
+    if (HAS_MEAN && LAYOUT == BLR_COLVECS) {
+        // one warp per observation: the column is contiguous, lanes stride over features.
+        const int lane = threadIdx.x & 31;
+        const int64_t warps = (int64_t)gridDim.x * (PREP_THREADS / 32);
+        for (int64_t n = (int64_t)blockIdx.x * (PREP_THREADS / 32) + (threadIdx.x >> 5); n < npad; n += warps) {
+            if (n < N) {
+                const double* col = X + n * ld;
+                double dot = 0.0;
+                for (int d = lane; d < D; d += 32) dot = fma(col[d], __ldg(mw + d), dot);
+                dot = warp_sum(dot);
+                if (lane == 0) {
+                    const double v = sigma2 ? sigma2[n] : sigma2_scalar;
+                    const double sn = 1.0 / v, dl = y[n] - dot;
+                    s[n] = sn;
+                    t[n] = sn * dl;
+                    q += sn * dl * dl;
+                    l += log(v);
+                }
+            } else if (lane == 0) {
+                s[n] = 0.0;
+                t[n] = 0.0;
+            }
+        }
+    } else {
+        const int64_t stride = (int64_t)gridDim.x * PREP_THREADS;
+        for (int64_t n = (int64_t)blockIdx.x * PREP_THREADS + threadIdx.x; n < npad; n += stride) {
+            if (n < N) {
+                double dot = 0.0;
+                if (HAS_MEAN) {  // RowVecs: feature-contiguous, threads of a warp read consecutive n
+                    for (int d = 0; d < D; ++d) dot = fma(X[(int64_t)d * ld + n], __ldg(mw + d), dot);
+                }
+                const double v = sigma2 ? sigma2[n] : sigma2_scalar;
+                const double sn = 1.0 / v, dl = y[n] - dot;
+                s[n] = sn;
+                t[n] = sn * dl;
+                q += sn * dl * dl;
+                l += log(v);
+            } else {
+                s[n] = 0.0;
+                t[n] = 0.0;
+            }
+        }
+    }
+    q = block_sum(q, red);
+    l = block_sum(l, red);
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = q;
+        partial[2 * blockIdx.x + 1] = l;
+    }
+}
+
+// ====================================================================== K1 fast path
+namespace gk {
+constexpr int TM = 128;                   // tile edge (rows of G per panel)
+constexpr int KT = 16;                    // observations per pipeline stage
+constexpr int LDT = TM + 4;               // padded smem row: stride == 4 (mod 16) doubles -> conflict-free LDS.64
+constexpr int STAGES = 4;
+constexpr int CONSUMER_WARPS = 8;         // 2 (m) x 4 (n) warps, warp tile 64 x 32
+constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+struct __align__(16) Stage {
+    double a[KT * LDT];  // panel I rows  [k][m]
+    double b[KT * LDT];  // panel J rows  [k][n]  (unused on diagonal tiles)
+    double s[KT];        // 1/σ²
+    double t[KT];        // δ/σ²
+};
+struct Smem {
+    Stage st[STAGES];
+    double rred[TM];
+    unsigned long long full[STAGES];
+    unsigned long long empty[STAGES];
+};
+}  // namespace gk
+
+struct GramParams {
+    const double* X;
+    int64_t ld;
+    int D;
+    int64_t N;
+    const double* s;
+    const double* t;
+    double* P;   // [nsplit][ntiles][TM*TM]
+    double* Pr;  // [nsplit][nt][TM]
+    int nt;      // tiles per dimension
+    int ntiles;  // nt (nt + 1) / 2
+    int64_t chunk;  // observations per split (multiple of KT)
+};
+
+__device__ __forceinline__ void tile_from_index(int idx, int& ti, int& tj) {
+    int i = 0;
+    while ((i + 1) * (i + 2) / 2 <= idx) ++i;
+    ti = i;
+    tj = idx - i * (i + 1) / 2;
+}
+
+__global__ void __launch_bounds__(gk::THREADS, 1) gram_tma_kernel(const GramParams p) {
+    using namespace gk;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int ti, tj;
+    tile_from_index(blockIdx.x, ti, tj);
+    const bool diag = (ti == tj);
+    const int split = blockIdx.y;
+    const int i0 = ti * TM, j0 = tj * TM;
+    const int rowsA = min(TM, p.D - i0), rowsB = min(TM, p.D - j0);
+    const int64_t n0 = (int64_t)split * p.chunk;
+    const int64_t n1 = min(p.N, n0 + p.chunk);
+    const int niter = (n1 > n0) ? (int)((n1 - n0 + KT - 1) / KT) : 0;
+
+    // zero the ring once: rows past D (tail tile) and observations past N (tail stage) must read as 0.
+    {
+        double* z = reinterpret_cast<double*>(sm.st);
+        const int nz = (int)(sizeof(Stage) * STAGES / sizeof(double));
+        for (int i = tid; i < nz; i += THREADS) z[i] = 0.0;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(smem_u32(&sm.full[i]), 1);
+            mbar_init(smem_u32(&sm.empty[i]), CONSUMER_WARPS);
+        }
+        mbar_fence_init();
+    }
+    fence_proxy_async();  // order the generic-proxy zero fill before the async-proxy (TMA) writes
+    __syncthreads();
+
+    if (warp == CONSUMER_WARPS) {
+        // ------------------------------------------------------------ producer warp (TMA)
+        for (int it = 0; it < niter; ++it) {
+            const int stg = it % STAGES;
+            const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+            mbar_wait(smem_u32(&sm.empty[stg]), ph ^ 1u);
+            const int64_t k0 = n0 + (int64_t)it * KT;
+            const int kc = (int)min((int64_t)KT, n1 - k0);
+            Stage& S = sm.st[stg];
+            const uint32_t bar = smem_u32(&sm.full[stg]);
+            if (lane == 0) {
+                const uint32_t bytes = (uint32_t)kc * (uint32_t)(rowsA + (diag ? 0 : rowsB)) * 8u + 2u * KT * 8u;
+                mbar_arrive_expect_tx(bar, bytes);
+            }
+            __syncwarp();
+            if (lane < KT) {
+                if (lane < kc)
+                    bulk_g2s(smem_u32(&S.a[lane * LDT]), p.X + (k0 + lane) * p.ld + i0, (uint32_t)rowsA * 8u, bar);
+            } else {
+                const int l = lane - KT;
+                if (!diag && l < kc)
+                    bulk_g2s(smem_u32(&S.b[l * LDT]), p.X + (k0 + l) * p.ld + j0, (uint32_t)rowsB * 8u, bar);
+            }
+            if (lane == 0) {
+                bulk_g2s(smem_u32(S.s), p.s + k0, KT * 8u, bar);
+                bulk_g2s(smem_u32(S.t), p.t + k0, KT * 8u, bar);
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------- consumer warps (DMMA)
+    const int wm = warp >> 2, wn = warp & 3;
+    const int g = lane >> 2, kq = lane & 3;
+    double acc[8][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    double racc = 0.0;
+    const int rm = tid & (TM - 1), rhalf = tid >> 7;
+
+    for (int it = 0; it < niter; ++it) {
+        const int stg = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(smem_u32(&sm.full[stg]), ph);
+        const Stage& S = sm.st[stg];
+        const double* Ap = S.a + wm * 64 + g;
+        const double* Bp = (diag ? S.a : S.b) + wn * 32 + g;
+#pragma unroll
+        for (int kk = 0; kk < KT / 4; ++kk) {
+            const int kl = kk * 4 + kq;
+            const double sk = S.s[kl];
+            double a[8], b[4];
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi) a[mi] = Ap[kl * LDT + mi * 8];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) b[ni] = Bp[kl * LDT + ni * 8] * sk;
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
+        }
+        if (diag) {  // r block of this row panel: r[m] += Σ_k X[m,k] t_k
+#pragma unroll
+            for (int k = 0; k < KT / 2; ++k) {
+                const int kl = rhalf * (KT / 2) + k;
+                racc = fma(S.a[kl * LDT + rm], S.t[kl], racc);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sm.empty[stg]));
+    }
+
+    // ---------------------------------------------------------------- epilogue: partial tile -> workspace
+    double* Pt = p.P + ((int64_t)split * p.ntiles + blockIdx.x) * (TM * TM);
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi) {
+        const int row = wm * 64 + mi * 8 + g;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            const int col = wn * 32 + ni * 8 + kq * 2;
+            *reinterpret_cast<double2*>(Pt + row * TM + col) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+        }
+    }
+    if (diag) {
+        if (rhalf == 1) sm.rred[rm] = racc;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (rhalf == 0) p.Pr[((int64_t)split * p.nt + ti) * TM + rm] = racc + sm.rred[rm];
+    }
+}
+
+// ====================================================================== K1 generic path
+// Any D, any leading dimension, either layout (element (d, n) at d*sd + n*sn).  32 x 32 tiles of the
+// lower triangle, 2 x 2 outputs per thread, plain DFMA.  Used for small / odd shapes (README toy D = 2,
+// the reference's D = 3..7 test problems); not a throughput path.
+namespace gg {
+constexpr int TS = 32, KC = 32, LDS_ = 33, THREADS = 256;
+}
+
+__global__ void __launch_bounds__(gg::THREADS) gram_generic_kernel(const double* __restrict__ X, int64_t sd, int64_t sn,
+                                                                   int coalesce_n, int D, int64_t N,
+                                                                   const double* __restrict__ s,
+                                                                   const double* __restrict__ t, double* __restrict__ P,
+                                                                   double* __restrict__ Pr, int nt, int ntiles,
+                                                                   int64_t chunk) {
+    using namespace gg;
+    __shared__ double Xi[KC * LDS_], Xj[KC * LDS_], ss[KC], tt[KC];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    int ti, tj;
+    tile_from_index(blockIdx.x, ti, tj);
+    const bool diag = (ti == tj);
+    const int split = blockIdx.y;
+    const int64_t n0 = (int64_t)split * chunk, n1 = min(N, n0 + chunk);
+    double c00 = 0, c01 = 0, c10 = 0, c11 = 0, racc = 0;
+    for (int64_t k0 = n0; k0 < n1; k0 += KC) {
+        __syncthreads();
+        for (int e = tid; e < TS * KC; e += THREADS) {
+            const int dl = coalesce_n ? e / KC : e % TS;
+            const int k = coalesce_n ? e % KC : e / TS;
+            const int64_t n = k0 + k;
+            const int di = ti * TS + dl, dj = tj * TS + dl;
+            Xi[k * LDS_ + dl] = (di < D && n < n1) ? X[(int64_t)di * sd + n * sn] : 0.0;
+            Xj[k * LDS_ + dl] = (dj < D && n < n1) ? X[(int64_t)dj * sd + n * sn] : 0.0;
+        }
+        if (tid < KC) {
+            const int64_t n = k0 + tid;
+            ss[tid] = (n < n1) ? s[n] : 0.0;
+            tt[tid] = (n < n1) ? t[n] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < KC; ++k) {
+            const double a0 = Xi[k * LDS_ + ty * 2], a1 = Xi[k * LDS_ + ty * 2 + 1];
+            const double sk = ss[k];
+            const double b0 = Xj[k * LDS_ + tx * 2] * sk, b1 = Xj[k * LDS_ + tx * 2 + 1] * sk;
+            c00 = fma(a0, b0, c00);
+            c01 = fma(a0, b1, c01);
+            c10 = fma(a1, b0, c10);
+            c11 = fma(a1, b1, c11);
+        }
+        if (diag && tid < TS) {
+            for (int k = 0; k < KC; ++k) racc = fma(Xi[k * LDS_ + tid], tt[k], racc);
+        }
+    }
+    double* Pt = P + ((int64_t)split * ntiles + blockIdx.x) * (TS * TS);
+    Pt[(ty * 2) * TS + tx * 2] = c00;
+    Pt[(ty * 2) * TS + tx * 2 + 1] = c01;
+    Pt[(ty * 2 + 1) * TS + tx * 2] = c10;
+    Pt[(ty * 2 + 1) * TS + tx * 2 + 1] = c11;
+    if (diag && tid < TS) Pr[((int64_t)split * nt + ti) * TS + tid] = racc;
+}
+
+// ====================================================================== fixed-order split reduction
+// stats.G += Σ_split P (lower tiles mirrored to both triangles), stats.r += Σ_split Pr,
+// stats.{q, ℓ, n} += prep partials.  One CTA per tile; the sum over splits runs in index order.
+__global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restrict__ P, const double* __restrict__ Pr,
+                                                          int TS, int nt, int ntiles, int nsplit, int D,
+                                                          double* __restrict__ G, double* __restrict__ r,
+                                                          double* __restrict__ scal,
+                                                          const double* __restrict__ prep_partial, int prep_blocks,
+                                                          double n_obs) {
+    __shared__ double red[32];
+    int ti, tj;
+    tile_from_index(blockIdx.x, ti, tj);
+    const int tsz = TS * TS;
+    for (int e = threadIdx.x; e < tsz; e += blockDim.x) {
+        const int row = e / TS, col = e % TS;
+        const int gi = ti * TS + row, gj = tj * TS + col;
+        if (gi < D && gj < D && gi >= gj) {
+            double v = 0.0;
+            for (int sp = 0; sp < nsplit; ++sp) v += P[((int64_t)sp * ntiles + blockIdx.x) * tsz + e];
+            const double nv = G[(int64_t)gj * D + gi] + v;
+            G[(int64_t)gj * D + gi] = nv;
+            if (gi != gj) G[(int64_t)gi * D + gj] = nv;
+        }
+    }
+    if (ti == tj) {
+        for (int m = threadIdx.x; m < TS; m += blockDim.x) {
+            const int gi = ti * TS + m;
+            if (gi < D) {
+                double v = 0.0;
+                for (int sp = 0; sp < nsplit; ++sp) v += Pr[((int64_t)sp * nt + ti) * TS + m];
+                r[gi] += v;
+            }
+        }
+    }
+    if (blockIdx.x == 0) {
+        double q = 0.0, l = 0.0;
+        for (int b = threadIdx.x; b < prep_blocks; b += blockDim.x) {
+            q += prep_partial[2 * b];
+            l += prep_partial[2 * b + 1];
+        }
+        q = block_sum(q, red);
+        l = block_sum(l, red);
+        if (threadIdx.x == 0) {
+            scal[0] += q;
+            scal[1] += l;
+            scal[2] += n_obs;
+        }
+    }
+}
+
+// ====================================================================== host orchestration
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_is_zero, const blr_x* x,
+                    const double* y, const double* sigma2, double sigma2_scalar) {
+    const int64_t N = x->N;
+    const int D = (int)x->D;
+    if (N == 0) return 0;
+    cudaStream_t sm = ctx->stream;
+    BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], sm));
+
+    // ---- K0: prep
+    const int64_t npad = round_up(N, gk::KT) + gk::KT;
+    BLR_TRY(ensure_nbuf(ctx, (size_t)(2 * npad) * sizeof(double)));
+    double* s = ctx->nbuf;
+    double* t = ctx->nbuf + npad;
+    const int max_blocks = ctx->sm_count * 8;
+    int prep_blocks;
+    const bool warp_per_obs = (!mw_is_zero && x->layout == BLR_COLVECS);
+    {
+        const int64_t per_block = warp_per_obs ? PREP_THREADS / 32 : PREP_THREADS;
+        prep_blocks = (int)std::min<int64_t>((npad + per_block - 1) / per_block, max_blocks);
+    }
+    double* prep_partial = ctx->small;  // 2 * prep_blocks doubles (small buffer holds >= 2 * 8 * sm_count)
+    if (mw_is_zero) {
+        prep_kernel<BLR_COLVECS, false><<<prep_blocks, PREP_THREADS, 0, sm>>>(x->p, x->ld, D, N, npad, y, sigma2,
+                                                                              sigma2_scalar, mw_dev, s, t, prep_partial);
+    } else if (x->layout == BLR_COLVECS) {
+        prep_kernel<BLR_COLVECS, true><<<prep_blocks, PREP_THREADS, 0, sm>>>(x->p, x->ld, D, N, npad, y, sigma2,
+                                                                             sigma2_scalar, mw_dev, s, t, prep_partial);
+    } else {
+        prep_kernel<BLR_ROWVECS, true><<<prep_blocks, PREP_THREADS, 0, sm>>>(x->p, x->ld, D, N, npad, y, sigma2,
+                                                                             sigma2_scalar, mw_dev, s, t, prep_partial);
+    }
+    BLR_CHECK_LAUNCH(ctx, "prep_kernel");
+    BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[1], sm));
+
+    // ---- K1
+    const double* Xc = x->p;
+    int64_t ldc = x->ld;
+    double* xt = nullptr;  // transposed copy for a large RowVecs input
+    bool fast = (D >= 64) && (D % 2 == 0);
+    if (fast && x->layout == BLR_ROWVECS) {
+        const int64_t ldt = round_up(D, 2);
+        BLR_CUDA_OK(ctx, cudaMallocAsync(&xt, (size_t)ldt * N * sizeof(double), sm));
+        BLR_TRY(transpose_to_colvecs(ctx, x, xt, ldt));
+        Xc = xt;
+        ldc = ldt;
+    }
+    if (fast && ((ldc % 2) != 0 || (reinterpret_cast<uintptr_t>(Xc) & 15) != 0)) fast = false;
+
+    int TS, nt, ntiles, nsplit;
+    int64_t chunk;
+    if (fast) {
+        TS = gk::TM;
+        nt = (D + TS - 1) / TS;
+        ntiles = nt * (nt + 1) / 2;
+        nsplit = std::max(1, ctx->sm_count / ntiles);
+        chunk = round_up((N + nsplit - 1) / nsplit, gk::KT);
+        nsplit = (int)((N + chunk - 1) / chunk);
+    } else {
+        TS = gg::TS;
+        nt = (D + TS - 1) / TS;
+        ntiles = nt * (nt + 1) / 2;
+        nsplit = std::max(1, (ctx->sm_count * 4) / ntiles);
+        chunk = round_up((N + nsplit - 1) / nsplit, gg::KC);
+        nsplit = (int)((N + chunk - 1) / chunk);
+    }
+    const size_t p_elems = (size_t)nsplit * ntiles * TS * TS;
+    const size_t pr_elems = (size_t)nsplit * nt * TS;
+    BLR_TRY(ensure_ws(ctx, (p_elems + pr_elems) * sizeof(double)));
+    double* P = ctx->ws;
+    double* Pr = ctx->ws + p_elems;
+
+    if (fast) {
+        GramParams gp;
+        gp.X = Xc;
+        gp.ld = ldc;
+        gp.D = D;
+        gp.N = N;
+        gp.s = s;
+        gp.t = t;
+        gp.P = P;
+        gp.Pr = Pr;
+        gp.nt = nt;
+        gp.ntiles = ntiles;
+        gp.chunk = chunk;
+        BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)sizeof(gk::Smem)));
+        gram_tma_kernel<<<dim3(ntiles, nsplit), gk::THREADS, sizeof(gk::Smem), sm>>>(gp);
+        BLR_CHECK_LAUNCH(ctx, "gram_tma_kernel");
+    } else {
+        const bool colv = (x->layout == BLR_COLVECS);
+        const int64_t sd = colv ? 1 : x->ld, sn = colv ? x->ld : 1;
+        gram_generic_kernel<<<dim3(ntiles, nsplit), gg::THREADS, 0, sm>>>(x->p, sd, sn, colv ? 0 : 1, D, N, s, t, P, Pr,
+                                                                          nt, ntiles, chunk);
+        BLR_CHECK_LAUNCH(ctx, "gram_generic_kernel");
+    }
+    BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], sm));
+
+    gram_reduce_kernel<<<ntiles, 256, 0, sm>>>(P, Pr, TS, nt, ntiles, nsplit, D, st->G(), st->r(), st->scal(),
+                                               prep_partial, prep_blocks, (double)N);
+    BLR_CHECK_LAUNCH(ctx, "gram_reduce_kernel");
+    BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], sm));
+    ctx->ev_valid[0] = ctx->ev_valid[1] = ctx->ev_valid[2] = true;
+    if (xt) BLR_CUDA_OK(ctx, cudaFreeAsync(xt, sm));
+    return 0;
+}
+
+}  // namespace blr

@@ -1,0 +1,144 @@
+// Internal declarations shared by the translation units of libblr_cuda.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/blr_cuda.h"
+
+struct blr_x {
+    double* p = nullptr;
+    int64_t D = 0, N = 0, ld = 0;
+    int layout = BLR_COLVECS;
+    bool owned = false;
+};
+struct blr_vec {
+    double* p = nullptr;
+    int64_t n = 0;
+    bool owned = false;
+};
+// packed statistics: G (D*D, column-major, full symmetric) | r (D) | q | ℓ | n   -> D*D + D + 3 doubles
+struct blr_stats {
+    double* p = nullptr;
+    int64_t D = 0;
+    int64_t len() const { return D * D + D + 3; }
+    double* G() const { return p; }
+    double* r() const { return p + D * D; }
+    double* scal() const { return p + D * D + D; }  // q, ℓ, n
+};
+// device-resident regressor (prior or posterior)
+struct blr_post {
+    int64_t D = 0;
+    double* mw = nullptr;    // D
+    double* L = nullptr;     // D x D lower Cholesky factor of Λw (Λw = L L'), column-major; upper part zero
+    double* W = nullptr;     // D x D lower, W = inv(L); built lazily for var / rand
+    double* Lam = nullptr;   // D x D precision (kept for download)
+    bool has_W = false;
+};
+
+struct blr_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    // scratch
+    double* ws = nullptr;  // gram partial workspace
+    size_t ws_bytes = 0;
+    double* nbuf = nullptr;  // per-observation scratch (s, t = sδ), 2 * npad doubles
+    size_t nbuf_bytes = 0;
+    double* small = nullptr;  // small device scratch (scalars, block partial sums)
+    size_t small_bytes = 0;
+    int* d_info = nullptr;
+    cudaEvent_t ev[8] = {};
+    bool ev_valid[4] = {};
+    // host-streaming path (blr_stats_accumulate_host): copy stream, two staging slots
+    cudaStream_t copy_stream = nullptr;
+    double* stage[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    cudaEvent_t ev_copied[2] = {}, ev_consumed[2] = {};
+    // NCCL (dlopen'ed)
+    void* nccl_comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+namespace blr {
+
+// layout of blr_ctx::small (doubles)
+constexpr int SMALL_PREP = 0;        // prep-kernel block partials (2 per block, <= 4096)
+constexpr int SMALL_SC = 4096;       // scalars
+constexpr int SMALL_VEC = 16384;     // capacity of each D-vector slot (max supported D)
+constexpr int SMALL_RHS = 8192;
+constexpr int SMALL_MW = SMALL_RHS + SMALL_VEC;
+constexpr int SMALL_DTMP = SMALL_MW + SMALL_VEC;
+constexpr int SMALL_TOTAL = SMALL_DTMP + SMALL_VEC;
+
+int set_err(blr_ctx* ctx, int code, const std::string& msg);
+int cuda_fail(blr_ctx* ctx, cudaError_t e, const char* what);
+int ensure_ws(blr_ctx* ctx, size_t bytes);
+int ensure_nbuf(blr_ctx* ctx, size_t bytes);
+
+#define BLR_CUDA_OK(ctx, call)                                           \
+    do {                                                                 \
+        cudaError_t _e = (call);                                         \
+        if (_e != cudaSuccess) return ::blr::cuda_fail(ctx, _e, #call);  \
+    } while (0)
+#define BLR_CHECK_LAUNCH(ctx, name)                                             \
+    do {                                                                        \
+        (ctx)->launches++;                                                      \
+        cudaError_t _e = cudaGetLastError();                                    \
+        if (_e != cudaSuccess) return ::blr::cuda_fail(ctx, _e, "launch " name); \
+    } while (0)
+#define BLR_TRY(call)          \
+    do {                       \
+        int _r = (call);       \
+        if (_r != 0) return _r; \
+    } while (0)
+
+// ---- gram.cu
+// stats += local shard statistics.  s_noise: scalar σ² when sigma2 == nullptr.
+int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_is_zero, const blr_x* x,
+                    const double* y, const double* sigma2, double sigma2_scalar);
+
+// ---- chol.cu
+// In-place lower Cholesky of the column-major D x D matrix A (only the lower triangle is read);
+// strictly-upper part is zeroed.  *info_dev (device int) receives 0 or the 1-based failing order.
+int potrf_lower(blr_ctx* ctx, double* A, int64_t D, int* info_dev);
+// W = inv(L) (lower triangular, column-major), strictly-upper part zeroed.
+int trtri_lower(blr_ctx* ctx, const double* L, double* W, int64_t D);
+// Solve L z = b (forward) then optionally L' u = z (backward); b overwritten.  zz_out (device) = z'z.
+int trsv_lower_forward(blr_ctx* ctx, const double* L, int64_t D, double* b);
+int trsv_lower_backward(blr_ctx* ctx, const double* L, int64_t D, double* b);
+// out[0] = 2 * sum log diag(L)
+int logdet_from_chol(blr_ctx* ctx, const double* L, int64_t D, double* out_dev);
+int infer_solve(blr_ctx* ctx, const blr_prior* prior, const blr_stats* st, double* logpdf_out, double* m_post,
+                double* T_post, double* L_post, blr_post** post_out);
+int post_from_prior(blr_ctx* ctx, const blr_prior* prior, int64_t D, blr_post** out);
+int post_ensure_W(blr_ctx* ctx, blr_post* p);
+void post_release(blr_post* p);
+
+// ---- predict.cu
+int predict_mean_var(blr_ctx* ctx, blr_post* p, const blr_x* x, const double* sigma2, double sigma2_scalar,
+                     double* mean_dev, double* var_dev);
+int predict_cov(blr_ctx* ctx, blr_post* p, const blr_x* x, const double* sigma2, double sigma2_scalar, double* C_dev);
+int sample_weights(blr_ctx* ctx, blr_post* p, int64_t S, const double* Z_dev, double* W_dev);
+int sample_finite(blr_ctx* ctx, const blr_x* x, const double* Wsamp_dev, int64_t S, const double* sigma2,
+                  double sigma2_scalar, const double* Zy_dev, uint64_t seed, double* Y_dev);
+int apply_weights(blr_ctx* ctx, const blr_x* x, const double* w_dev, double* out_dev);
+
+// ---- synth.cu
+int synth_normal(blr_ctx* ctx, double* out, int64_t rows, int64_t cols, int64_t ld, uint64_t seed, uint64_t stream_id,
+                 int64_t col_offset);
+int synth_noise(blr_ctx* ctx, double* sigma2, int64_t n, uint64_t seed, int64_t n_offset);
+int synth_targets(blr_ctx* ctx, const blr_x* x, const double* sigma2, uint64_t seed, int64_t n_offset, double* y);
+int rff_features(blr_ctx* ctx, const blr_x* xin, const double* W_dev, const double* b_dev, int64_t D, double* out,
+                 int64_t ldo);
+int transpose_to_colvecs(blr_ctx* ctx, const blr_x* x, double* out, int64_t ldo);
+
+// ---- calib.cu
+int calib_dmma(blr_ctx* ctx, double* tflops);
+int calib_dfma(blr_ctx* ctx, double* tflops);
+int calib_hbm(blr_ctx* ctx, double* gbs);
+
+}  // namespace blr

@@ -1,0 +1,271 @@
+// K6/K7: prediction-side kernels -- mean, marginal variances, covariance, sampling.
+//
+// Reference work replaced (src/bayesian_linear_regression.jl):
+//   mean  :33      X' mw
+//   var   :40-43   α = Uw' \ X ; sum(abs2, α; dims=1) .+ diag(Σy)      (Uw' = L, lower factor of Λw)
+//   cov   :35-38   α'α + Σy
+//   rand  :49-53   X'(mw .+ Uw \ Zw) .+ Uy' Zy
+// and src/sampling_functions.jl:29,35,44 (weight draws), :17-19 (BLRFunctionSample call).
+//
+// The triangular solve against N columns is recast as a triangular GEMM with the explicit inverse factor
+// W = inv(L) (built once per regressor, cached on the device): α = W X, var_n = |W x_n|² + σ²_n.  α is never
+// written to HBM: each CTA owns a tile of test points, sweeps the row blocks of W and folds the squares into
+// per-point sums held in registers (shuffle reduction across the fragment rows).
+#include <math.h>
+
+#include <algorithm>
+
+#include "blockgemm.cuh"
+#include "common.cuh"
+#include "internal.h"
+#include "philox.cuh"
+
+namespace blr {
+
+// ---------------------------------------------------------------------------------------------
+// out_n = x_n' w   (mean :33, BLRFunctionSample call)
+template <int LAYOUT>
+__global__ void __launch_bounds__(256) apply_weights_kernel(const double* __restrict__ X, int64_t ld, int D, int64_t N,
+                                                            const double* __restrict__ w, double* __restrict__ out) {
+    if (LAYOUT == BLR_COLVECS) {
+        const int lane = threadIdx.x & 31;
+        const int64_t warps = (int64_t)gridDim.x * 8;
+        for (int64_t n = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); n < N; n += warps) {
+            const double* col = X + n * ld;
+            double dot = 0.0;
+            for (int d = lane; d < D; d += 32) dot = fma(col[d], __ldg(w + d), dot);
+            dot = warp_sum(dot);
+            if (lane == 0) out[n] = dot;
+        }
+    } else {
+        const int64_t stride = (int64_t)gridDim.x * 256;
+        for (int64_t n = (int64_t)blockIdx.x * 256 + threadIdx.x; n < N; n += stride) {
+            double dot = 0.0;
+            for (int d = 0; d < D; ++d) dot = fma(X[(int64_t)d * ld + n], __ldg(w + d), dot);
+            out[n] = dot;
+        }
+    }
+}
+
+int apply_weights(blr_ctx* ctx, const blr_x* x, const double* w_dev, double* out_dev) {
+    if (x->N == 0) return 0;
+    const int D = (int)x->D;
+    if (x->layout == BLR_COLVECS) {
+        const int grid = (int)std::min<int64_t>((x->N + 7) / 8, (int64_t)ctx->sm_count * 16);
+        apply_weights_kernel<BLR_COLVECS><<<grid, 256, 0, ctx->stream>>>(x->p, x->ld, D, x->N, w_dev, out_dev);
+    } else {
+        const int grid = (int)std::min<int64_t>((x->N + 255) / 256, (int64_t)ctx->sm_count * 16);
+        apply_weights_kernel<BLR_ROWVECS><<<grid, 256, 0, ctx->stream>>>(x->p, x->ld, D, x->N, w_dev, out_dev);
+    }
+    BLR_CHECK_LAUNCH(ctx, "apply_weights_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// var_n = |W x_n|² + σ²_n for a tile of 64 test points per CTA (DMMA block GEMMs, α stays on chip).
+template <int LAYOUT>
+__global__ void __launch_bounds__(bg::THREADS) var_kernel(const double* __restrict__ W, int D,
+                                                          const double* __restrict__ X, int64_t ld, int64_t N,
+                                                          const double* __restrict__ sigma2, double sigma2_scalar,
+                                                          double* __restrict__ var) {
+    __shared__ double smA[bg::SMEM_A], smB[bg::SMEM_B];
+    __shared__ double colsum[2][bg::BS];
+    const int64_t p0 = (int64_t)blockIdx.x * bg::BS;
+    const int pvalid = (int)min((int64_t)bg::BS, N - p0);
+    const int nblk = (D + bg::BS - 1) / bg::BS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp >> 1, wn = warp & 1;
+    double csum[4][2];
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) csum[ni][0] = csum[ni][1] = 0.0;
+
+    for (int ib = 0; ib < nblk; ++ib) {
+        double acc[4][4][2];
+        acc_zero(acc);
+        const int r0 = ib * bg::BS;
+        for (int kb = 0; kb <= ib; ++kb) {
+            const int k0 = kb * bg::BS;
+            const int kc = min(bg::BS, D - k0);
+            // A (m, k) = W[r0 + m, k0 + k] ; B (k, n) = X[k0 + k, p0 + n]
+            if (LAYOUT == BLR_COLVECS)
+                cta_gemm64<true>(acc, W + (int64_t)k0 * D + r0, D, D - r0, X + p0 * ld + k0, ld, pvalid, kc, smA, smB);
+            else
+                cta_gemm64<false>(acc, W + (int64_t)k0 * D + r0, D, D - r0, X + (int64_t)k0 * ld + p0, ld, pvalid, kc, smA,
+                                  smB);
+        }
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                csum[ni][0] = fma(acc[mi][ni][0], acc[mi][ni][0], csum[ni][0]);
+                csum[ni][1] = fma(acc[mi][ni][1], acc[mi][ni][1], csum[ni][1]);
+            }
+    }
+    // fold the 8 fragment rows (lane >> 2) of each column, then the two row-warps
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            double v = csum[ni][c];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if ((lane >> 2) == 0) colsum[wm][wn * 32 + ni * 8 + (lane & 3) * 2 + c] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < pvalid) {
+        const int64_t n = p0 + threadIdx.x;
+        var[n] = (colsum[0][threadIdx.x] + colsum[1][threadIdx.x]) + (sigma2 ? sigma2[n] : sigma2_scalar);
+    }
+}
+
+int predict_mean_var(blr_ctx* ctx, blr_post* p, const blr_x* x, const double* sigma2, double sigma2_scalar,
+                     double* mean_dev, double* var_dev) {
+    if (x->N == 0) return 0;
+    if (mean_dev) BLR_TRY(apply_weights(ctx, x, p->mw, mean_dev));
+    if (var_dev) {
+        BLR_TRY(post_ensure_W(ctx, p));
+        const int64_t grid = (x->N + bg::BS - 1) / bg::BS;
+        if (grid > 0x7fffffff) return set_err(ctx, BLR_E_INVALID, "too many test points for one launch");
+        if (x->layout == BLR_COLVECS)
+            var_kernel<BLR_COLVECS><<<(int)grid, bg::THREADS, 0, ctx->stream>>>(p->W, (int)p->D, x->p, x->ld, x->N, sigma2,
+                                                                              sigma2_scalar, var_dev);
+        else
+            var_kernel<BLR_ROWVECS><<<(int)grid, bg::THREADS, 0, ctx->stream>>>(p->W, (int)p->D, x->p, x->ld, x->N, sigma2,
+                                                                              sigma2_scalar, var_dev);
+        BLR_CHECK_LAUNCH(ctx, "var_kernel");
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic strided GEMM (plain DFMA, 32 x 32 tiles): C[m, n] = beta * C + Σ_k A[m, k] B[k, n].
+// Used for the small-N "next" rows (cov) and the first version of rand; not a throughput path.
+__global__ void __launch_bounds__(256) gemm_generic_kernel(int64_t M, int64_t Nn, int64_t K, const double* __restrict__ A,
+                                                           int64_t as_m, int64_t as_k, const double* __restrict__ B,
+                                                           int64_t bs_k, int64_t bs_n, double* __restrict__ C,
+                                                           int64_t cs_m, int64_t cs_n, double beta) {
+    __shared__ double As[32][33], Bs[32][33];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int64_t m0 = (int64_t)blockIdx.x * 32, n0 = (int64_t)blockIdx.y * 32;
+    double c00 = 0, c01 = 0, c10 = 0, c11 = 0;
+    for (int64_t k0 = 0; k0 < K; k0 += 32) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < 1024; e += 256) {
+            // pick the thread -> element map that walks the unit-stride direction of each operand
+            const int a_m = (as_m <= as_k) ? e % 32 : e / 32, a_k = (as_m <= as_k) ? e / 32 : e % 32;
+            As[a_k][a_m] = (m0 + a_m < M && k0 + a_k < K) ? A[(m0 + a_m) * as_m + (k0 + a_k) * as_k] : 0.0;
+            const int b_n = (bs_n <= bs_k) ? e % 32 : e / 32, b_k = (bs_n <= bs_k) ? e / 32 : e % 32;
+            Bs[b_k][b_n] = (n0 + b_n < Nn && k0 + b_k < K) ? B[(k0 + b_k) * bs_k + (n0 + b_n) * bs_n] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const double a0 = As[k][ty * 2], a1 = As[k][ty * 2 + 1], b0 = Bs[k][tx * 2], b1 = Bs[k][tx * 2 + 1];
+            c00 = fma(a0, b0, c00);
+            c01 = fma(a0, b1, c01);
+            c10 = fma(a1, b0, c10);
+            c11 = fma(a1, b1, c11);
+        }
+    }
+    const double cc[2][2] = {{c00, c01}, {c10, c11}};
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) {
+            const int64_t m = m0 + ty * 2 + i, n = n0 + tx * 2 + j;
+            if (m < M && n < Nn) {
+                double* dst = C + m * cs_m + n * cs_n;
+                *dst = (beta == 0.0) ? cc[i][j] : beta * (*dst) + cc[i][j];
+            }
+        }
+}
+
+static int gemm_generic(blr_ctx* ctx, int64_t M, int64_t Nn, int64_t K, const double* A, int64_t as_m, int64_t as_k,
+                        const double* B, int64_t bs_k, int64_t bs_n, double* C, int64_t cs_m, int64_t cs_n, double beta) {
+    if (M == 0 || Nn == 0) return 0;
+    const int64_t gx = (M + 31) / 32, gy = (Nn + 31) / 32;
+    if (gy > 65535) return set_err(ctx, BLR_E_INVALID, "gemm_generic: too many column tiles");
+    gemm_generic_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, ctx->stream>>>(M, Nn, K, A, as_m, as_k, B, bs_k, bs_n, C,
+                                                                                  cs_m, cs_n, beta);
+    BLR_CHECK_LAUNCH(ctx, "gemm_generic_kernel");
+    return 0;
+}
+
+__global__ void add_diag_noise_kernel(double* __restrict__ C, int64_t N, const double* __restrict__ sigma2,
+                                      double sigma2_scalar) {
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x)
+        C[n * N + n] += sigma2 ? sigma2[n] : sigma2_scalar;
+}
+
+// cov = α'α + Σy, α = W X  (N x N output: small-N path, "next" row of SURVEY.md section 8f)
+int predict_cov(blr_ctx* ctx, blr_post* p, const blr_x* x, const double* sigma2, double sigma2_scalar, double* C_dev) {
+    const int64_t D = p->D, N = x->N;
+    if (N == 0) return 0;
+    BLR_TRY(post_ensure_W(ctx, p));
+    double* alpha = nullptr;
+    BLR_CUDA_OK(ctx, cudaMallocAsync(&alpha, (size_t)D * N * sizeof(double), ctx->stream));
+    const bool colv = x->layout == BLR_COLVECS;
+    // α (D x N, column-major) = W (D x D, column-major) * X
+    int rc = gemm_generic(ctx, D, N, D, p->W, 1, D, x->p, colv ? 1 : x->ld, colv ? x->ld : 1, alpha, 1, D, 0.0);
+    // C = α'α
+    if (rc == 0) rc = gemm_generic(ctx, N, N, D, alpha, D, 1, alpha, 1, D, C_dev, 1, N, 0.0);
+    if (rc == 0) {
+        add_diag_noise_kernel<<<(int)std::min<int64_t>((N + 255) / 256, 1024), 256, 0, ctx->stream>>>(C_dev, N, sigma2,
+                                                                                                   sigma2_scalar);
+        ctx->launches++;
+    }
+    cudaFreeAsync(alpha, ctx->stream);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight draws: Wsamp (D x S) = mw .+ Uw \ Z = mw .+ L^-T Z = mw .+ W' Z
+__global__ void add_col_vector_kernel(double* __restrict__ A, int64_t D, int64_t S, const double* __restrict__ v) {
+    const int64_t total = D * S;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+        A[e] += v[e % D];
+}
+
+int sample_weights(blr_ctx* ctx, blr_post* p, int64_t S, const double* Z_dev, double* W_dev) {
+    const int64_t D = p->D;
+    if (S == 0) return 0;
+    BLR_TRY(post_ensure_W(ctx, p));
+    // (W' Z)[d, s] = Σ_k W[k, d] Z[k, s]
+    BLR_TRY(gemm_generic(ctx, D, S, D, p->W, D, 1, Z_dev, 1, D, W_dev, 1, D, 0.0));
+    add_col_vector_kernel<<<(int)std::min<int64_t>((D * S + 255) / 256, (int64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(
+        W_dev, D, S, p->mw);
+    BLR_CHECK_LAUNCH(ctx, "add_col_vector_kernel");
+    return 0;
+}
+
+// Y[n, s] += sqrt(σ²_n) * z,  z = Zy[n, s] when supplied, else Philox normal (stream 7, element n + s * n_total)
+__global__ void add_obs_noise_kernel(double* __restrict__ Y, int64_t N, int64_t S, const double* __restrict__ sigma2,
+                                     double sigma2_scalar, const double* __restrict__ Zy, uint64_t seed) {
+    const int64_t total = N * S;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = e % N;
+        const double sd = sqrt(sigma2 ? sigma2[n] : sigma2_scalar);
+        double z;
+        if (Zy) {
+            z = Zy[e];
+        } else {
+            double z0, z1;
+            philox_normal_pair(seed, 7, (uint64_t)e, z0, z1);
+            z = z0;
+        }
+        Y[e] = fma(sd, z, Y[e]);
+    }
+}
+
+int sample_finite(blr_ctx* ctx, const blr_x* x, const double* Wsamp_dev, int64_t S, const double* sigma2,
+                  double sigma2_scalar, const double* Zy_dev, uint64_t seed, double* Y_dev) {
+    const int64_t N = x->N, D = x->D;
+    if (N == 0 || S == 0) return 0;
+    const bool colv = x->layout == BLR_COLVECS;
+    // Y (N x S) = X' Wsamp : A[m = n, k = d] = X[d, n]
+    BLR_TRY(gemm_generic(ctx, N, S, D, x->p, colv ? x->ld : 1, colv ? 1 : x->ld, Wsamp_dev, 1, D, Y_dev, 1, N, 0.0));
+    add_obs_noise_kernel<<<(int)std::min<int64_t>((N * S + 255) / 256, (int64_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(
+        Y_dev, N, S, sigma2, sigma2_scalar, Zy_dev, seed);
+    BLR_CHECK_LAUNCH(ctx, "add_obs_noise_kernel");
+    return 0;
+}
+
+}  // namespace blr

@@ -1,0 +1,186 @@
+/* libblr_cuda -- C ABI of the B200-native FiniteBLR inference path.
+ *
+ * This is the drop-in boundary for BayesianLinearRegressors.jl's hot path.  The reference has
+ * no FFI of its own (its boundary is Julia method dispatch); each entry
+ * point below names the reference method body (file:line under the reference repo) whose work
+ * it replaces.  The Julia glue (`julia/src/`) and the Python host mirror
+ * (`bayesianlinearregressors.jl_b200/`) bind exactly these symbols; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; every matrix is Float64, column-major (Julia / LAPACK order);
+ *   - status return: 0 ok; >0 = LAPACK-style `info` of a failed Cholesky (leading minor of
+ *     that order is not positive definite -> LinearAlgebra.PosDefException(info));
+ *     <0 = BLR_E_* argument / CUDA / NCCL error, text via blr_last_error(ctx);
+ *   - one context drives one GPU (one process per GPU under torchrun, or several contexts in
+ *     one Julia process); a context is not re-entrant; every call sets its own device;
+ *   - host pointers are borrowed for the duration of the call only (`GC.@preserve`);
+ *   - "dev" pointers are device addresses on the context's GPU, borrowed while the handle lives;
+ *   - there is NO CPU fallback: without a usable sm_100 device blr_ctx_create fails.
+ */
+#ifndef BLR_CUDA_H
+#define BLR_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLR_VERSION 100 /* 0.1.0 */
+
+/* error codes (negative) */
+#define BLR_E_INVALID (-1)   /* bad argument (shape, null pointer, unknown kind) */
+#define BLR_E_CUDA (-2)      /* CUDA runtime error */
+#define BLR_E_NCCL (-3)      /* NCCL error / NCCL not loadable */
+#define BLR_E_DIM (-4)       /* length(y) != size(X, 2)  (src/bayesian_linear_regression.jl:74) */
+#define BLR_E_NODEVICE (-5)  /* no sm_100 device: the product path refuses to run */
+#define BLR_E_NOMEM (-6)
+
+/* input layouts: x_as_colvecs, src/bayesian_linear_regression.jl:20-31 */
+#define BLR_COLVECS 0 /* D x N column-major: observation contiguous, element (d,n) at n*ld + d */
+#define BLR_ROWVECS 1 /* N x D column-major: feature contiguous,     element (n,d) at d*ld + n */
+
+/* precision-matrix kinds of BayesianLinearRegressor.Λw (src/bayesian_linear_regression.jl:11-14) */
+#define BLR_LAMBDA_DIAGONAL 0 /* `lambda` = D diagonal entries (LinearAlgebra.Diagonal) */
+#define BLR_LAMBDA_DENSE 1    /* `lambda` = D x D symmetric, column-major, leading dim ld (Matrix / Symmetric / PDMat.mat) */
+
+/* observation-noise kinds of FiniteGP.Σy */
+#define BLR_NOISE_SCALAR 0 /* Diagonal(Fill(σ², N)) : f(X, 0.1) */
+#define BLR_NOISE_VECTOR 1 /* Diagonal(v)           : f(X, Diagonal(v)) */
+
+typedef struct blr_ctx blr_ctx;
+typedef struct blr_x blr_x;         /* device design matrix (this rank's N-shard) */
+typedef struct blr_vec blr_vec;     /* device N-vector (targets y, noise variances σ²) */
+typedef struct blr_stats blr_stats; /* packed sufficient statistics [G(DxD) | r(D) | q | ℓ | n] on device */
+typedef struct blr_post blr_post;   /* device-resident regressor: mw, chol(Λw) (+ inverse factor), cached for predict */
+
+typedef struct blr_prior {
+    const double* mw;     /* host, D */
+    int lambda_kind;      /* BLR_LAMBDA_* */
+    const double* lambda; /* host */
+    int64_t ld;           /* leading dimension for DENSE (>= D); ignored for DIAGONAL */
+} blr_prior;
+
+typedef struct blr_noise {
+    int kind;           /* BLR_NOISE_* */
+    double scalar;      /* σ² when kind == SCALAR */
+    const blr_vec* vec; /* σ²_n when kind == VECTOR (same N partition as X) */
+} blr_noise;
+
+/* ------------------------------------------------------------------ context */
+int blr_version(void);
+int blr_ctx_create(blr_ctx** out, int device);
+int blr_ctx_destroy(blr_ctx* ctx);
+const char* blr_last_error(const blr_ctx* ctx);
+int blr_ctx_sync(blr_ctx* ctx);
+/* cudaStream_t all kernels of this context are launched on (for CUDA-event timing by the host). */
+int blr_ctx_stream(blr_ctx* ctx, void** stream_out);
+/* number of libblr_cuda kernels launched by this context so far. */
+int64_t blr_launch_count(const blr_ctx* ctx);
+/* Device-event timings (ms) of the last blr_stats_accumulate / blr_infer* call:
+ * out[0]=prep (δ, 1/σ²), out[1]=Gram kernel, out[2]=split reduce, out[3]=factorise+solve, out[4..7]=0. */
+int blr_last_timings(blr_ctx* ctx, double* out8);
+
+/* ------------------------------------------------------------------ multi-GPU (N-sharded observations)
+ * One rank per GPU; the only exchange of the path is one sum-allreduce of the packed statistics
+ * (SURVEY.md section 8e).  NCCL is dlopen'ed on first use. */
+int blr_nccl_unique_id(void* out128);
+int blr_comm_init_rank(blr_ctx* ctx, const void* id128, int nranks, int rank);
+int blr_comm_destroy(blr_ctx* ctx);
+
+/* ------------------------------------------------------------------ data handles */
+int blr_x_upload(blr_ctx* ctx, const double* host, int64_t D, int64_t N, int64_t ld, int layout, blr_x** out);
+int blr_x_wrap_device(blr_ctx* ctx, const double* dev, int64_t D, int64_t N, int64_t ld, int layout, blr_x** out);
+int blr_x_alloc(blr_ctx* ctx, int64_t D, int64_t N, int layout, blr_x** out);
+int blr_x_device_ptr(blr_ctx* ctx, const blr_x* x, double** dev_out, int64_t* ld_out);
+int blr_x_free(blr_ctx* ctx, blr_x* x);
+int blr_vec_upload(blr_ctx* ctx, const double* host, int64_t n, blr_vec** out);
+int blr_vec_wrap_device(blr_ctx* ctx, const double* dev, int64_t n, blr_vec** out);
+int blr_vec_alloc(blr_ctx* ctx, int64_t n, blr_vec** out);
+int blr_vec_device_ptr(blr_ctx* ctx, const blr_vec* v, double** dev_out);
+int blr_vec_download(blr_ctx* ctx, const blr_vec* v, double* host);
+int blr_vec_free(blr_ctx* ctx, blr_vec* v);
+
+/* bench-only synthetic generators (counter-based Philox4x32-10):
+ *   X ~ N(0,1) iid;  σ²_n = exp(z_n);  y = X' w* + σ_n ε_n  with w* ~ N(0, I_D). */
+int blr_x_synth(blr_ctx* ctx, blr_x* x, uint64_t seed, int64_t n_offset);
+int blr_vec_synth_noise(blr_ctx* ctx, blr_vec* sigma2, uint64_t seed, int64_t n_offset);
+int blr_vec_synth_targets(blr_ctx* ctx, const blr_x* x, const blr_vec* sigma2, uint64_t seed, int64_t n_offset,
+                          blr_vec* y);
+
+/* device-resident random Fourier features for BasisFunctionRegressor
+ * (replaces ϕ(x) of src/basis_function_regression.jl:41 for ϕ(x) = sqrt(2/D) cos(W x + b)):
+ * xin: d_in x N ColVecs; W host D x d_in column-major; b host D; out: new D x N ColVecs handle. */
+int blr_x_rff(blr_ctx* ctx, const blr_x* xin, const double* W, const double* b, int64_t D, blr_x** out);
+
+/* ------------------------------------------------------------------ inference
+ * replaces __compute_inference_quantities / logpdf / posterior,
+ * src/bayesian_linear_regression.jl:55-89 */
+int blr_stats_create(blr_ctx* ctx, int64_t D, blr_stats** out);
+int blr_stats_free(blr_ctx* ctx, blr_stats* s);
+int blr_stats_zero(blr_ctx* ctx, blr_stats* s);
+/* stats += [X S X', X S δ, δ'Sδ, Σ log σ², N] of this shard, δ = y - X'mw, S = diag(1/σ²)
+ * (the O(N D²) part of :81-:86 in closed form).  May be called repeatedly (chunked / streamed data). */
+int blr_stats_accumulate(blr_ctx* ctx, blr_stats* s, const double* mw_host, const blr_x* x, const blr_vec* y,
+                         const blr_noise* noise);
+/* Same, from HOST arrays (what a Julia caller holds): the observations are streamed to the device in chunks of
+ * `chunk` observations through two staging buffers, copies on a second stream overlapped with the Gram kernel
+ * of the previous chunk.  X: D x N (COLVECS) or N x D (ROWVECS) column-major with leading dimension ld;
+ * sigma2_host: N noise variances when noise_kind == BLR_NOISE_VECTOR, else ignored.  Pinned host memory
+ * gives full PCIe overlap; pageable memory works (staged by the driver). */
+int blr_stats_accumulate_host(blr_ctx* ctx, blr_stats* s, const double* mw_host, const double* X, int64_t D, int64_t N,
+                              int64_t ld, int layout, const double* y, int noise_kind, double noise_scalar,
+                              const double* sigma2_host, int64_t chunk);
+/* in-place NCCL sum over ranks; no-op without a communicator. */
+int blr_stats_allreduce(blr_ctx* ctx, blr_stats* s);
+int blr_stats_device_ptr(blr_ctx* ctx, const blr_stats* s, double** dev_out, int64_t* len_out);
+int blr_stats_download(blr_ctx* ctx, const blr_stats* s, double* host);
+int blr_stats_upload(blr_ctx* ctx, blr_stats* s, const double* host);
+/* posterior + logpdf from reduced statistics (replicated on every rank).  Any output may be NULL.
+ *   logpdf_out : 1      log marginal likelihood                                     (:57)
+ *   m_post     : D      posterior mean                                              (:68)
+ *   T_post     : D x D  upper-triangular factor, T'T = posterior precision, ld = D  (:67)
+ *   L_post     : D x D  posterior precision Λw + X S X' (symmetric), ld = D         (:92)
+ *   post_out   : device-resident posterior regressor for mean/var/rand              */
+int blr_infer_from_stats(blr_ctx* ctx, const blr_prior* prior, const blr_stats* s, double* logpdf_out, double* m_post,
+                         double* T_post, double* L_post, blr_post** post_out);
+/* zero + accumulate + allreduce + infer_from_stats in one call. */
+int blr_infer(blr_ctx* ctx, const blr_prior* prior, const blr_x* x, const blr_vec* y, const blr_noise* noise,
+              double* logpdf_out, double* m_post, double* T_post, double* L_post, blr_post** post_out);
+
+/* ------------------------------------------------------------------ prediction / sampling
+ * replaces mean / var / mean_and_var / rand, src/bayesian_linear_regression.jl:33-53,
+ * and the weight draw of src/sampling_functions.jl:29,35,44 */
+int blr_post_create(blr_ctx* ctx, const blr_prior* prior, int64_t D, blr_post** out); /* factorises Λw once */
+int blr_post_free(blr_ctx* ctx, blr_post* p);
+int blr_post_dim(const blr_post* p, int64_t* D_out);
+/* mean_n = x_n'mw,  var_n = |Uw^-T x_n|² + σ²_n; outputs are host (or device if *_dev) N-vectors; either may be NULL. */
+int blr_mean_var(blr_ctx* ctx, blr_post* p, const blr_x* x, const blr_noise* noise, double* mean_host,
+                 double* var_host);
+int blr_mean_var_dev(blr_ctx* ctx, blr_post* p, const blr_x* x, const blr_noise* noise, double* mean_dev,
+                     double* var_dev);
+/* N x N covariance α'α + Σy (cov, :35-38); C host column-major ld = N. */
+int blr_cov(blr_ctx* ctx, blr_post* p, const blr_x* x, const blr_noise* noise, double* C_host);
+/* Y (N x S, column-major) = X'(mw + Uw^-1 Zw) + sqrt(σ²) .* Zy  (:51-52).
+ * Zw (D x S) / Zy (N x S) host standard-normal draws in the reference's order, or NULL to draw on
+ * device (Philox, `seed`). */
+int blr_rand_finite(blr_ctx* ctx, blr_post* p, const blr_x* x, const blr_noise* noise, int64_t S, const double* Zw,
+                    const double* Zy, uint64_t seed, double* Y_host);
+int blr_rand_finite_dev(blr_ctx* ctx, blr_post* p, const blr_x* x, const blr_noise* noise, int64_t S,
+                        const double* Zw_host, const double* Zy_dev, uint64_t seed, double* Y_dev);
+/* W (D x S) = mw .+ Uw \ Z */
+int blr_rand_weights(blr_ctx* ctx, blr_post* p, int64_t S, const double* Z, uint64_t seed, double* W_host);
+/* out_n = x_n'w for one weight sample (BLRFunctionSample call, src/sampling_functions.jl:17-19) */
+int blr_apply_weights(blr_ctx* ctx, const blr_x* x, const double* w_host, double* out_host);
+
+/* ------------------------------------------------------------------ on-box calibration of the fp64 roofline
+ * ("fp64 peak must be calibrated on-box").  Pure DMMA.8x8x4 issue loop over all SMs and a
+ * device-to-device copy; results in TFLOP/s (2 flop per FMA) and GB/s (read + write bytes). */
+int blr_calibrate_dmma(blr_ctx* ctx, double* tflops_out);
+int blr_calibrate_dfma(blr_ctx* ctx, double* tflops_out);
+int blr_calibrate_hbm(blr_ctx* ctx, double* gbs_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLR_CUDA_H */

@@ -1,0 +1,40 @@
+#!/bin/bash
+# One gpurun call = one session: run the requested stages, never abort on a failed stage, log under gpurun_out/.
+# usage: tools/gpu_session.sh <tag> stage [stage ...]      stages: tests smoke calib bench_small bench ncu_list ncu_full
+set -u
+TAG=$1; shift
+OUT=gpurun_out/$TAG
+mkdir -p "$OUT"
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm,clocks.sm,power.limit --format=csv > "$OUT/gpu.csv" 2>&1
+nproc > "$OUT/nproc.txt"; free -g >> "$OUT/nproc.txt"
+for stage in "$@"; do
+  echo "=== stage $stage $(date +%T)"
+  case $stage in
+    tests)
+      timeout 1500 python -m pytest tests -m gpu -q -x --timeout 600 > "$OUT/tests.log" 2>&1; echo "tests exit $?"; tail -15 "$OUT/tests.log";;
+    tests_all)
+      timeout 1500 python -m pytest tests -m gpu -q --timeout 600 > "$OUT/tests.log" 2>&1; echo "tests exit $?"; tail -40 "$OUT/tests.log";;
+    smoke)
+      timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > "$OUT/smoke.log" 2>&1; echo "smoke exit $?"; tail -5 "$OUT/smoke.log";;
+    calib)
+      timeout 300 python -c "
+import blr_b200 as b, json
+c = b.Context(0)
+print(json.dumps(c.calibrate()))
+" > "$OUT/calib.log" 2>&1; echo "calib exit $?"; tail -3 "$OUT/calib.log";;
+    bench_small)
+      timeout 600 python bench.py --n-obs 1048576 --dim 256 --steps 5 --warmup 3 --e2e-obs 262144 --cpu-sample 65536 > "$OUT/bench_small.json" 2> "$OUT/bench_small.err"; echo "bench_small exit $?"; tail -c 3000 "$OUT/bench_small.json"; tail -5 "$OUT/bench_small.err";;
+    bench)
+      timeout 1200 python bench.py --steps 3 --warmup 3 > "$OUT/bench.json" 2> "$OUT/bench.err"; echo "bench exit $?"; tail -c 3000 "$OUT/bench.json"; tail -5 "$OUT/bench.err";;
+    bench_ref)
+      timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > "$OUT/bench_ref.json" 2> "$OUT/bench_ref.err"; echo "bench_ref exit $?"; tail -c 1500 "$OUT/bench_ref.json";;
+    ncu_list)
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches.csv" \
+        python bench.py --n-obs 2097152 --steps 1 --warmup 1 --no-cpu --no-calibrate --e2e-obs 65536 > "$OUT/ncu_list.log" 2>&1; echo "ncu_list exit $?";;
+    ncu_full)
+      timeout 1200 ncu --set full --clock-control none --import-source on -k regex:gram_tma -s 1 -c 1 -o "$OUT/prof_gram" -f \
+        python bench.py --n-obs 2097152 --steps 1 --warmup 1 --no-cpu --no-calibrate --e2e-obs 65536 > "$OUT/ncu_full.log" 2>&1; echo "ncu_full exit $?";;
+    *) echo "unknown stage $stage";;
+  esac
+done
+echo "=== done $(date +%T)"
