@@ -1,0 +1,76 @@
+# Drop-in replacement for the method bodies of BayesianLinearRegressors.jl/src/bayesian_linear_regression.jl:33-93.
+# The struct, the FiniteBLR alias, x_as_colvecs and every signature are unchanged; only the bodies dispatch to
+# libblr_cuda.  UNEXECUTED (no Julia in the build image) -- see INTEGRATION.md.
+using .LibBLR: LibBLR
+
+# layout + device upload of whatever x_as_colvecs accepts (:20-31); errors for unknown vectors are preserved.
+_device_x(ctx, x::ColVecs) = LibBLR.upload_x(ctx, x.X, LibBLR.COLVECS)
+_device_x(ctx, x::RowVecs) = LibBLR.upload_x(ctx, x.X, LibBLR.ROWVECS)      # feature-major read in place: no transpose copy
+_device_x(ctx, x::AbstractVector) = x_as_colvecs(x)                           # -> the reference's ErrorException
+
+# Λw kinds (:11-14): Diagonal is sent as its diagonal, everything else as the dense symmetric matrix.
+_prior(f::BayesianLinearRegressor{<:Any,<:Diagonal}) =
+    (mw = collect(Float64, f.mw); λ = collect(Float64, f.Λw.diag);
+     (LibBLR.Prior(pointer(mw), LibBLR.LAMBDA_DIAGONAL, pointer(λ), length(mw)), (mw, λ)))
+_prior(f::BayesianLinearRegressor) =
+    (mw = collect(Float64, f.mw); Λ = Matrix{Float64}(f.Λw);
+     (LibBLR.Prior(pointer(mw), LibBLR.LAMBDA_DENSE, pointer(Λ), size(Λ, 1)), (mw, Λ)))
+
+# Σy kinds of FiniteGP: Diagonal(Fill) -> scalar, Diagonal(v) -> device vector.  Dense Σy keeps the reference path.
+_noise(ctx, Σy::Diagonal{<:Real,<:FillArrays.Fill}) = (LibBLR.Noise(LibBLR.NOISE_SCALAR, first(Σy.diag), C_NULL), nothing)
+function _noise(ctx, Σy::Diagonal)
+    v = LibBLR.upload_vec(ctx, collect(Float64, Σy.diag))
+    return LibBLR.Noise(LibBLR.NOISE_VECTOR, 0.0, v.ptr), v
+end
+
+function _infer(fx::FiniteBLR, y::AbstractVector{<:Real}; want_T::Bool)
+    ctx = LibBLR.default_context()
+    length(y) == length(fx.x) || throw(error("length(y) != size(fx.x.X, 2)"))            # :74
+    x = _device_x(ctx, fx.x)
+    yv = LibBLR.upload_vec(ctx, collect(Float64, y))
+    prior, keep1 = _prior(fx.f)
+    noise, keep2 = _noise(ctx, fx.Σy)
+    GC.@preserve keep1 keep2 x yv LibBLR.infer(ctx, prior, x, yv, noise; want_T=want_T)
+end
+
+AbstractGPs.logpdf(fx::FiniteBLR, y::AbstractVector{<:Real}) = _infer(fx, y; want_T=false)[1]     # :55-58
+
+function AbstractGPs.posterior(fx::FiniteBLR, y::AbstractVector{<:Real})                           # :60-69
+    _, m′, Λ′, T, _ = _infer(fx, y; want_T=fx.f.Λw isa AbstractPDMat)
+    return BayesianLinearRegressor(m′, __build_Λ(typeof(fx.f.Λw), Λ′, T))
+end
+__build_Λ(_, Λ′, _) = Symmetric(Λ′)                                                                # :92
+__build_Λ(::Type{<:AbstractPDMat}, Λ′, T) = PDMat(Λ′, Cholesky(UpperTriangular(T)))                 # :93
+
+function _predict(fx::FiniteBLR; mean::Bool, var::Bool)
+    ctx = LibBLR.default_context()
+    x = _device_x(ctx, fx.x)
+    prior, keep1 = _prior(fx.f)
+    noise, keep2 = _noise(ctx, fx.Σy)
+    GC.@preserve keep1 keep2 begin
+        p = LibBLR.post_create(ctx, prior, length(fx.f.mw))
+        LibBLR.mean_var(ctx, p, x, noise; mean=mean, var=var)
+    end
+end
+AbstractGPs.mean(fx::FiniteBLR) = _predict(fx; mean=true, var=false)[1]                            # :33
+AbstractGPs.var(fx::FiniteBLR) = _predict(fx; mean=false, var=true)[2]                             # :40-43
+AbstractGPs.mean_and_var(fx::FiniteBLR) = _predict(fx; mean=true, var=true)                        # :47
+
+function AbstractGPs.cov(fx::FiniteBLR)                                                            # :35-38
+    ctx = LibBLR.default_context()
+    x = _device_x(ctx, fx.x)
+    prior, keep1 = _prior(fx.f)
+    noise, keep2 = _noise(ctx, fx.Σy)
+    GC.@preserve keep1 keep2 Symmetric(LibBLR.cov(ctx, LibBLR.post_create(ctx, prior, length(fx.f.mw)), x, noise))
+end
+AbstractGPs.mean_and_cov(fx::FiniteBLR) = (mean(fx), cov(fx))                                      # :45
+
+function AbstractGPs.rand(rng::AbstractRNG, fx::FiniteBLR, samples::Int)                           # :49-53
+    ctx = LibBLR.default_context()
+    x = _device_x(ctx, fx.x)
+    Zw = randn(rng, length(fx.f.mw), samples)          # drawn FIRST (:51)
+    Zy = randn(rng, length(fx.x), samples)             # drawn SECOND (:52)
+    prior, keep1 = _prior(fx.f)
+    noise, keep2 = _noise(ctx, fx.Σy)
+    GC.@preserve keep1 keep2 LibBLR.rand_finite(ctx, LibBLR.post_create(ctx, prior, length(fx.f.mw)), x, noise, Zw, Zy)
+end

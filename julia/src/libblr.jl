@@ -1,0 +1,153 @@
+# Low-level ccall bindings of libblr_cuda (include/blr_cuda.h).
+#
+# UNEXECUTED: there is no Julia toolchain in the build image or on the GPU box (SURVEY.md section 8c); this file
+# documents the binding a maintainer adds to BayesianLinearRegressors.jl.  The same symbols are exercised end
+# to end through the Python ctypes binding (bayesianlinearregressors.jl_b200/_lib.py).
+module LibBLR
+
+using LinearAlgebra: PosDefException
+
+const libblr = get(ENV, "LIBBLR_CUDA", "libblr_cuda")
+
+const COLVECS, ROWVECS = Cint(0), Cint(1)
+const LAMBDA_DIAGONAL, LAMBDA_DENSE = Cint(0), Cint(1)
+const NOISE_SCALAR, NOISE_VECTOR = Cint(0), Cint(1)
+const E_DIM = Cint(-4)
+
+struct Prior
+    mw::Ptr{Float64}
+    lambda_kind::Cint
+    lambda::Ptr{Float64}
+    ld::Int64
+end
+
+struct Noise
+    kind::Cint
+    scalar::Float64
+    vec::Ptr{Cvoid}
+end
+
+mutable struct Context
+    ptr::Ptr{Cvoid}
+    function Context(device::Integer=0)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:blr_ctx_create, libblr), Cint, (Ref{Ptr{Cvoid}}, Cint), r, device)
+        rc == 0 || error("blr_ctx_create failed with code $rc (no sm_100 device? libblr_cuda has no CPU fallback)")
+        ctx = new(r[])
+        finalizer(c -> ccall((:blr_ctx_destroy, libblr), Cint, (Ptr{Cvoid},), c.ptr), ctx)
+        return ctx
+    end
+end
+
+const _ctx = Ref{Union{Nothing,Context}}(nothing)
+default_context() = something(_ctx[], (_ctx[] = Context(); _ctx[]))
+
+# status -> Julia exception, preserving the reference's error behaviour
+function check(ctx::Context, rc::Cint)
+    rc == 0 && return nothing
+    rc > 0 && throw(PosDefException(Int(rc)))                    # LAPACK-style info from the device Cholesky
+    msg = unsafe_string(ccall((:blr_last_error, libblr), Cstring, (Ptr{Cvoid},), ctx.ptr))
+    error(rc == E_DIM ? "length(y) != size(fx.x.X, 2)" : "libblr_cuda error $rc: $msg")   # ErrorException
+end
+
+# ---- device handles with finalizers ---------------------------------------------------------------
+mutable struct DeviceX
+    ptr::Ptr{Cvoid}
+    ctx::Context
+    D::Int
+    N::Int
+end
+function upload_x(ctx::Context, X::StridedMatrix{Float64}, layout::Cint)
+    D, N = layout == COLVECS ? size(X) : reverse(size(X))
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve X check(ctx, ccall((:blr_x_upload, libblr), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Cint, Ref{Ptr{Cvoid}}),
+        ctx.ptr, pointer(X), D, N, stride(X, 2), layout, r))
+    x = DeviceX(r[], ctx, D, N)
+    finalizer(h -> ccall((:blr_x_free, libblr), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), h.ctx.ptr, h.ptr), x)
+    return x
+end
+
+mutable struct DeviceVec
+    ptr::Ptr{Cvoid}
+    ctx::Context
+end
+function upload_vec(ctx::Context, v::StridedVector{Float64})
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve v check(ctx, ccall((:blr_vec_upload, libblr), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ref{Ptr{Cvoid}}), ctx.ptr, pointer(v), length(v), r))
+    h = DeviceVec(r[], ctx)
+    finalizer(h -> ccall((:blr_vec_free, libblr), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), h.ctx.ptr, h.ptr), h)
+    return h
+end
+
+mutable struct DevicePost
+    ptr::Ptr{Cvoid}
+    ctx::Context
+end
+_post(ctx, p) = (h = DevicePost(p, ctx);
+    finalizer(h -> ccall((:blr_post_free, libblr), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), h.ctx.ptr, h.ptr), h); h)
+
+# fused posterior + logpdf  (replaces src/bayesian_linear_regression.jl:55-89)
+function infer(ctx::Context, prior::Prior, x::DeviceX, y::DeviceVec, noise::Noise;
+               want_T::Bool=false, want_post::Bool=true)
+    D = x.D
+    lp = Ref{Float64}(NaN)
+    m = Vector{Float64}(undef, D)
+    Λ = Matrix{Float64}(undef, D, D)
+    T = want_T ? Matrix{Float64}(undef, D, D) : nothing
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx, ccall((:blr_infer, libblr), Cint,
+        (Ptr{Cvoid}, Ref{Prior}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Noise}, Ref{Float64}, Ptr{Float64}, Ptr{Float64},
+         Ptr{Float64}, Ref{Ptr{Cvoid}}),
+        ctx.ptr, prior, x.ptr, y.ptr, noise, lp, m, want_T ? T : C_NULL, Λ, h))
+    return lp[], m, Λ, T, _post(ctx, h[])
+end
+
+function post_create(ctx::Context, prior::Prior, D::Integer)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx, ccall((:blr_post_create, libblr), Cint, (Ptr{Cvoid}, Ref{Prior}, Int64, Ref{Ptr{Cvoid}}),
+        ctx.ptr, prior, D, h))
+    return _post(ctx, h[])
+end
+
+function mean_var(ctx::Context, p::DevicePost, x::DeviceX, noise::Noise; mean::Bool=true, var::Bool=true)
+    m = mean ? Vector{Float64}(undef, x.N) : nothing
+    v = var ? Vector{Float64}(undef, x.N) : nothing
+    check(ctx, ccall((:blr_mean_var, libblr), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Noise}, Ptr{Float64}, Ptr{Float64}),
+        ctx.ptr, p.ptr, x.ptr, noise, mean ? m : C_NULL, var ? v : C_NULL))
+    return m, v
+end
+
+function cov(ctx::Context, p::DevicePost, x::DeviceX, noise::Noise)
+    C = Matrix{Float64}(undef, x.N, x.N)
+    check(ctx, ccall((:blr_cov, libblr), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Noise}, Ptr{Float64}),
+        ctx.ptr, p.ptr, x.ptr, noise, C))
+    return C
+end
+
+function rand_finite(ctx::Context, p::DevicePost, x::DeviceX, noise::Noise, Zw::Matrix{Float64}, Zy::Matrix{Float64})
+    S = size(Zw, 2)
+    Y = Matrix{Float64}(undef, x.N, S)
+    check(ctx, ccall((:blr_rand_finite, libblr), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Noise}, Int64, Ptr{Float64}, Ptr{Float64}, UInt64, Ptr{Float64}),
+        ctx.ptr, p.ptr, x.ptr, noise, S, Zw, Zy, 0, Y))
+    return Y
+end
+
+function rand_weights(ctx::Context, p::DevicePost, Z::Matrix{Float64})
+    W = similar(Z)
+    check(ctx, ccall((:blr_rand_weights, libblr), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Float64}, UInt64, Ptr{Float64}), ctx.ptr, p.ptr, size(Z, 2), Z, 0, W))
+    return W
+end
+
+function apply_weights(ctx::Context, x::DeviceX, w::Vector{Float64})
+    out = Vector{Float64}(undef, x.N)
+    check(ctx, ccall((:blr_apply_weights, libblr), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+        ctx.ptr, x.ptr, w, out))
+    return out
+end
+
+end # module
