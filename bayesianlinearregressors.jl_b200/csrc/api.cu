@@ -2,6 +2,7 @@
 // glue / Python host mirror bind.  No torch types, no exceptions across the boundary, no CPU fallback.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -133,6 +134,10 @@ int blr_ctx_create(blr_ctx** out, int device) {
         return BLR_E_CUDA;
     }
     ctx->small_bytes = (size_t)SMALL_TOTAL * sizeof(double);
+    if (const char* w = getenv("BLR_DIAG_WEIGHT")) {
+        const int v = atoi(w);
+        if (v >= 8 && v <= 128) ctx->diag_weight = v;
+    }
     *out = ctx;
     return 0;
 }
@@ -146,6 +151,7 @@ int blr_ctx_destroy(blr_ctx* ctx) {
     cudaFree(ctx->nbuf);
     cudaFree(ctx->small);
     cudaFree(ctx->d_info);
+    cudaFree(ctx->sched);
     cudaFree(ctx->stage[0]);
     cudaFree(ctx->stage[1]);
     for (int i = 0; i < 2; ++i) {
@@ -520,7 +526,10 @@ int blr_stats_accumulate_host(blr_ctx* ctx, blr_stats* s, const double* mw_host,
         double* ys = xs + x_elems;
         double* ss = ys + chunk;
         if (it >= 2) BLR_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[b], 0));
-        if (layout == BLR_COLVECS)
+        if (layout == BLR_COLVECS && ld == D && ldx == D)  // contiguous block of columns: one linear copy
+            BLR_CUDA_OK(ctx, cudaMemcpyAsync(xs, X + a * ld, (size_t)D * nb * sizeof(double), cudaMemcpyHostToDevice,
+                                             ctx->copy_stream));
+        else if (layout == BLR_COLVECS)
             BLR_CUDA_OK(ctx, cudaMemcpy2DAsync(xs, (size_t)ldx * sizeof(double), X + a * ld, (size_t)ld * sizeof(double),
                                                (size_t)D * sizeof(double), (size_t)nb, cudaMemcpyHostToDevice,
                                                ctx->copy_stream));
@@ -777,6 +786,11 @@ int blr_calibrate_dmma(blr_ctx* ctx, double* tflops_out) {
     CTX_ENTER(ctx);
     if (!tflops_out) return BLR_E_INVALID;
     return calib_dmma(ctx, tflops_out);
+}
+int blr_calibrate_dmma_cfg(blr_ctx* ctx, int warps_per_sm, int n_acc, double* tflops_out) {
+    CTX_ENTER(ctx);
+    if (!tflops_out) return BLR_E_INVALID;
+    return calib_dmma_cfg(ctx, warps_per_sm, n_acc, tflops_out);
 }
 int blr_calibrate_dfma(blr_ctx* ctx, double* tflops_out) {
     CTX_ENTER(ctx);

@@ -78,6 +78,47 @@ int calib_dmma(blr_ctx* ctx, double* tflops) {
     return 0;
 }
 
+// DMMA issue-rate probe: `warps` warps per SM (one CTA per SM), NACC independent accumulators per warp.
+template <int NACC>
+__global__ void calib_dmma_cfg_kernel(double* __restrict__ out, int iters, double seed) {
+    double c[NACC][2];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) c[i][0] = c[i][1] = 0.0;
+    const double a = seed + threadIdx.x * 1e-9, b = seed * 0.5;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) dmma884(c[i], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) s += c[i][0] + c[i][1];
+    out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+int calib_dmma_cfg(blr_ctx* ctx, int warps, int nacc, double* tflops) {
+    if (warps < 1 || warps > 32) return set_err(ctx, BLR_E_INVALID, "warps per SM must be 1..32");
+    const int blocks = ctx->sm_count, threads = warps * 32;
+    const int iters = 400000 / nacc;
+    BLR_TRY(ensure_ws(ctx, (size_t)blocks * threads * sizeof(double)));
+    float ms;
+    auto launch = [&] {
+        switch (nacc) {
+            case 1: calib_dmma_cfg_kernel<1><<<blocks, threads, 0, ctx->stream>>>(ctx->ws, iters, 1.0); break;
+            case 2: calib_dmma_cfg_kernel<2><<<blocks, threads, 0, ctx->stream>>>(ctx->ws, iters, 1.0); break;
+            case 4: calib_dmma_cfg_kernel<4><<<blocks, threads, 0, ctx->stream>>>(ctx->ws, iters, 1.0); break;
+            case 8: calib_dmma_cfg_kernel<8><<<blocks, threads, 0, ctx->stream>>>(ctx->ws, iters, 1.0); break;
+            case 16: calib_dmma_cfg_kernel<16><<<blocks, threads, 0, ctx->stream>>>(ctx->ws, iters, 1.0); break;
+            default: calib_dmma_cfg_kernel<32><<<blocks, threads, 0, ctx->stream>>>(ctx->ws, iters, 1.0); break;
+        }
+    };
+    if (nacc != 1 && nacc != 2 && nacc != 4 && nacc != 8 && nacc != 16 && nacc != 32)
+        return set_err(ctx, BLR_E_INVALID, "nacc must be 1, 2, 4, 8, 16 or 32");
+    BLR_TRY(time_best(ctx, 3, launch, &ms));
+    const double flop = (double)blocks * warps * (double)iters * nacc * 512.0;
+    *tflops = flop / (ms * 1e-3) / 1e12;
+    return 0;
+}
+
 int calib_dfma(blr_ctx* ctx, double* tflops) {
     const int blocks = ctx->sm_count * 2, iters = 20000;
     BLR_TRY(ensure_ws(ctx, (size_t)blocks * CAL_THREADS * sizeof(double)));

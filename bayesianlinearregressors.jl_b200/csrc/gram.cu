@@ -10,18 +10,21 @@
 // Data layout in HBM: X is the D x N column-major ColVecs matrix (one observation = D contiguous
 // doubles); s_n = 1/σ²_n and t_n = s_n δ_n are N-vectors produced by the prep kernel.
 //
-// Fast path (gram_tma_kernel): the lower triangle of G is cut into 128 x 128 tiles; a CTA owns one
-// tile and one contiguous range of observations (split-N), keeps the tile in registers as fp64
-// tensor-core accumulators (DMMA.8x8x4), and streams its two 128-row panels of X through a 4-stage
-// shared-memory ring filled by TMA bulk copies (cp.async.bulk + mbarrier) issued by a dedicated
-// producer warp.  Partial tiles go to a workspace and are summed in a FIXED order by
-// gram_reduce_kernel, so results are bit-reproducible run to run.
+// Fast path (gram_tma_kernel): the lower triangle of G is cut into 128 x 128 tiles.  One persistent CTA per SM
+// owns an equal share of the (tile, observation) work space (stream-K: a few segments = tile x observation
+// range), keeps the current tile in registers as fp64 tensor-core accumulators (DMMA.8x8x4), and streams the
+// tile's two 128-row panels of X through a 4-stage shared-memory ring filled by TMA bulk copies
+// (cp.async.bulk + mbarrier) issued by a dedicated producer warp.  Diagonal tiles skip the 8 x 8 sub-tiles above
+// the diagonal.  Each segment's partial tile goes to its own workspace slot; gram_reduce_kernel sums the slots of
+// a tile in a FIXED order, so results are bit-reproducible run to run.
 #include <math.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 #include "internal.h"
+#include "schedule.h"
 
 namespace blr {
 
@@ -97,6 +100,7 @@ constexpr int LDT = TM + 4;               // padded smem row: stride == 4 (mod 1
 constexpr int STAGES = 4;
 constexpr int CONSUMER_WARPS = 8;         // 2 (m) x 4 (n) warps, warp tile 64 x 32
 constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+constexpr int W_OFF = 64;                 // schedule weight of one stage of an off-diagonal tile
 struct __align__(16) Stage {
     double a[KT * LDT];  // panel I rows  [k][m]
     double b[KT * LDT];  // panel J rows  [k][n]  (unused on diagonal tiles)
@@ -111,6 +115,10 @@ struct Smem {
 };
 }  // namespace gk
 
+// Stream-K schedule (built on the host, see build_schedule): the (tile, stage) work space is linearised
+// tile-major with per-tile weights (diagonal tiles skip their strictly-upper 8 x 8 sub-tiles and are cheaper), cut
+// into one equal share per CTA; a CTA therefore owns a few SEGMENTS (tile, stage range), each flushed to its own
+// partial slot.  Segments of one tile are contiguous in the global segment list, so the reduction order is fixed.
 struct GramParams {
     const double* X;
     int64_t ld;
@@ -118,11 +126,12 @@ struct GramParams {
     int64_t N;
     const double* s;
     const double* t;
-    double* P;   // [nsplit][ntiles][TM*TM]
-    double* Pr;  // [nsplit][nt][TM]
-    int nt;      // tiles per dimension
-    int ntiles;  // nt (nt + 1) / 2
-    int64_t chunk;  // observations per split (multiple of KT)
+    double* P;    // [nseg][TM*TM]
+    double* Pr;   // [nseg][TM]
+    const int* cta_seg_begin;  // [grid + 1]
+    const int* seg_tile;       // [nseg]
+    const int* seg_g0;         // [nseg] first stage (16 observations each)
+    const int* seg_g1;         // [nseg] one past the last stage
 };
 
 __device__ __forceinline__ void tile_from_index(int idx, int& ti, int& tj) {
@@ -132,21 +141,70 @@ __device__ __forceinline__ void tile_from_index(int idx, int& ti, int& tj) {
     tj = idx - i * (i + 1) / 2;
 }
 
+// One pipeline stage of a consumer warp.  THR is a compile-time threshold: sub-tile (mi, ni) is computed only when
+// mi - ni >= THR (diagonal tiles skip the 8 x 8 sub-tiles above the diagonal; (wm*8 + mi) >= (wn*4 + ni) <=>
+// mi - ni >= wn*4 - wm*8).  Compile-time, because predicating an mma.sync at run time makes ptxas wrap every DMMA in
+// WARPSYNC.ALL, which serialises the tensor pipe (measured: no speed-up at all from run-time skipping).
+//   THR = -8: all 32 sub-tiles;  THR = 0: 26;  THR = 4: 10.
+template <bool DIAG, int THR>
+__device__ __forceinline__ void consume_stage(double (&acc)[8][4][2], const gk::Stage& S, int wm, int wn, int g, int kq) {
+    using namespace gk;
+    const double* Ap = S.a + wm * 64 + g;
+    const double* Bp = (DIAG ? S.a : S.b) + wn * 32 + g;
+#pragma unroll
+    for (int kk = 0; kk < KT / 4; ++kk) {
+        const int kl = kk * 4 + kq;
+        const double sk = S.s[kl];
+        double a[8], b[4];
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi)
+            if (mi - 0 >= THR) a[mi] = Ap[kl * LDT + mi * 8];  // row block mi is used by some ni iff mi >= THR
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+            if (7 - ni >= THR) b[ni] = Bp[kl * LDT + ni * 8] * sk;
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                if ((mi - ni) >= THR) dmma884(acc[mi][ni], a[mi], b[ni]);
+            }
+    }
+}
+
+// All stages of one segment for one consumer warp.  MODE: 0 off-diagonal; 1..3 diagonal with THR -8 / 0 / 4;
+// 4 diagonal, warp entirely above the diagonal (only helps with the r block).
+template <int MODE>
+__device__ __forceinline__ void run_segment(double (&acc)[8][4][2], double& racc, gk::Smem& sm, int& it, int nst, int wm,
+                                            int wn, int g, int kq, int rm, int rhalf, int lane) {
+    using namespace gk;
+    for (int i = 0; i < nst; ++i, ++it) {
+        const int stg = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(smem_u32(&sm.full[stg]), ph);
+        const Stage& S = sm.st[stg];
+        if (MODE == 0) consume_stage<false, -8>(acc, S, wm, wn, g, kq);
+        if (MODE == 1) consume_stage<true, -8>(acc, S, wm, wn, g, kq);
+        if (MODE == 2) consume_stage<true, 0>(acc, S, wm, wn, g, kq);
+        if (MODE == 3) consume_stage<true, 4>(acc, S, wm, wn, g, kq);
+        if (MODE != 0) {
+#pragma unroll
+            for (int k = 0; k < KT / 2; ++k) {  // r block of this row panel: r[m] += Σ_k X[m,k] t_k
+                const int kl = rhalf * (KT / 2) + k;
+                racc = fma(S.a[kl * LDT + rm], S.t[kl], racc);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sm.empty[stg]));
+    }
+}
+
 __global__ void __launch_bounds__(gk::THREADS, 1) gram_tma_kernel(const GramParams p) {
     using namespace gk;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    int ti, tj;
-    tile_from_index(blockIdx.x, ti, tj);
-    const bool diag = (ti == tj);
-    const int split = blockIdx.y;
-    const int i0 = ti * TM, j0 = tj * TM;
-    const int rowsA = min(TM, p.D - i0), rowsB = min(TM, p.D - j0);
-    const int64_t n0 = (int64_t)split * p.chunk;
-    const int64_t n1 = min(p.N, n0 + p.chunk);
-    const int niter = (n1 > n0) ? (int)((n1 - n0 + KT - 1) / KT) : 0;
+    const int seg_begin = p.cta_seg_begin[blockIdx.x], seg_end = p.cta_seg_begin[blockIdx.x + 1];
 
     // zero the ring once: rows past D (tail tile) and observations past N (tail stage) must read as 0.
     {
@@ -166,93 +224,100 @@ __global__ void __launch_bounds__(gk::THREADS, 1) gram_tma_kernel(const GramPara
 
     if (warp == CONSUMER_WARPS) {
         // ------------------------------------------------------------ producer warp (TMA)
-        for (int it = 0; it < niter; ++it) {
-            const int stg = it % STAGES;
-            const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-            mbar_wait(smem_u32(&sm.empty[stg]), ph ^ 1u);
-            const int64_t k0 = n0 + (int64_t)it * KT;
-            const int kc = (int)min((int64_t)KT, n1 - k0);
-            Stage& S = sm.st[stg];
-            const uint32_t bar = smem_u32(&sm.full[stg]);
-            if (lane == 0) {
-                const uint32_t bytes = (uint32_t)kc * (uint32_t)(rowsA + (diag ? 0 : rowsB)) * 8u + 2u * KT * 8u;
-                mbar_arrive_expect_tx(bar, bytes);
-            }
-            __syncwarp();
-            if (lane < KT) {
-                if (lane < kc)
-                    bulk_g2s(smem_u32(&S.a[lane * LDT]), p.X + (k0 + lane) * p.ld + i0, (uint32_t)rowsA * 8u, bar);
-            } else {
-                const int l = lane - KT;
-                if (!diag && l < kc)
-                    bulk_g2s(smem_u32(&S.b[l * LDT]), p.X + (k0 + l) * p.ld + j0, (uint32_t)rowsB * 8u, bar);
-            }
-            if (lane == 0) {
-                bulk_g2s(smem_u32(S.s), p.s + k0, KT * 8u, bar);
-                bulk_g2s(smem_u32(S.t), p.t + k0, KT * 8u, bar);
+        int it = 0;  // running stage counter of this CTA: ring slot and phase continue across segments
+        for (int sg = seg_begin; sg < seg_end; ++sg) {
+            int ti, tj;
+            tile_from_index(p.seg_tile[sg], ti, tj);
+            const bool diag = (ti == tj);
+            const int i0 = ti * TM, j0 = tj * TM;
+            const int rowsA = min(TM, p.D - i0), rowsB = min(TM, p.D - j0);
+            const int g0 = p.seg_g0[sg], g1 = p.seg_g1[sg];
+            // a tail tile has fewer rows than the previous tenant of the ring slot: stale rows would be read as data
+            const bool narrow = (rowsA < TM) || (!diag && rowsB < TM);
+            for (int gi = g0; gi < g1; ++gi, ++it) {
+                const int stg = it % STAGES;
+                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                mbar_wait(smem_u32(&sm.empty[stg]), ph ^ 1u);
+                const int64_t k0 = (int64_t)gi * KT;
+                const int kc = (int)min((int64_t)KT, p.N - k0);
+                Stage& S = sm.st[stg];
+                const uint32_t bar = smem_u32(&sm.full[stg]);
+                if (narrow) {  // rare (only tiles in the last block row when D % 128 != 0): clear the slot first
+                    double* z = reinterpret_cast<double*>(&S);
+                    for (int i = lane; i < 2 * KT * LDT; i += 32) z[i] = 0.0;
+                    fence_proxy_async();
+                    __syncwarp();
+                }
+                if (lane == 0) {
+                    const uint32_t bytes = (uint32_t)kc * (uint32_t)(rowsA + (diag ? 0 : rowsB)) * 8u + 2u * KT * 8u;
+                    mbar_arrive_expect_tx(bar, bytes);
+                }
+                __syncwarp();
+                if (lane < KT) {
+                    if (lane < kc)
+                        bulk_g2s(smem_u32(&S.a[lane * LDT]), p.X + (k0 + lane) * p.ld + i0, (uint32_t)rowsA * 8u, bar);
+                } else {
+                    const int l = lane - KT;
+                    if (!diag && l < kc)
+                        bulk_g2s(smem_u32(&S.b[l * LDT]), p.X + (k0 + l) * p.ld + j0, (uint32_t)rowsB * 8u, bar);
+                }
+                if (lane == 0) {
+                    bulk_g2s(smem_u32(S.s), p.s + k0, KT * 8u, bar);
+                    bulk_g2s(smem_u32(S.t), p.t + k0, KT * 8u, bar);
+                }
             }
         }
         return;
     }
 
     // ---------------------------------------------------------------- consumer warps (DMMA)
-    const int wm = warp >> 2, wn = warp & 3;
     const int g = lane >> 2, kq = lane & 3;
-    double acc[8][4][2];
-#pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-    double racc = 0.0;
     const int rm = tid & (TM - 1), rhalf = tid >> 7;
+    // off-diagonal tiles: warp -> (wm, wn) row-major.  Diagonal tiles: remapped so that the surviving sub-tile counts
+    // {26, 10, 0, 0, 32, 32, 26, 10} pair up evenly over the four SM sub-partitions (warp % 4): 32, 32, 36, 36.
+    const int wm_off = warp >> 2, wn_off = warp & 3;
+    const int dmap = (0x7132'6054 >> (4 * warp)) & 0xf;  // warp 0..7 -> (1,0) (1,1) (0,0) (1,2) (0,2) (0,3) (0,1) (1,3)
+    const int wm_dg = dmap >> 2, wn_dg = dmap & 3;
+    int it = 0;
+    for (int sg = seg_begin; sg < seg_end; ++sg) {
+        int ti, tj;
+        tile_from_index(p.seg_tile[sg], ti, tj);
+        const bool diag = (ti == tj);
+        const int nst = p.seg_g1[sg] - p.seg_g0[sg];
+        const int wm = diag ? wm_dg : wm_off, wn = diag ? wn_dg : wn_off;
+        const int thr = wn * 4 - wm * 8;  // sub-tile (mi, ni) needed iff mi - ni >= thr
+        double acc[8][4][2];
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        double racc = 0.0;
 
-    for (int it = 0; it < niter; ++it) {
-        const int stg = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(smem_u32(&sm.full[stg]), ph);
-        const Stage& S = sm.st[stg];
-        const double* Ap = S.a + wm * 64 + g;
-        const double* Bp = (diag ? S.a : S.b) + wn * 32 + g;
+        // warp-uniform dispatch to a fully unrolled, unpredicated instruction stream
+        if (!diag) run_segment<0>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
+        else if (thr <= -3) run_segment<1>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
+        else if (thr == 0) run_segment<2>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
+        else if (thr == 4) run_segment<3>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
+        else run_segment<4>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
+
+        // ------------------------------------------------------------ segment epilogue: partial tile -> its slot
+        double* Pt = p.P + (int64_t)sg * (TM * TM);
 #pragma unroll
-        for (int kk = 0; kk < KT / 4; ++kk) {
-            const int kl = kk * 4 + kq;
-            const double sk = S.s[kl];
-            double a[8], b[4];
+        for (int mi = 0; mi < 8; ++mi) {
+            const int row = wm * 64 + mi * 8 + g;
 #pragma unroll
-            for (int mi = 0; mi < 8; ++mi) a[mi] = Ap[kl * LDT + mi * 8];
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) b[ni] = Bp[kl * LDT + ni * 8] * sk;
-#pragma unroll
-            for (int mi = 0; mi < 8; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
-        }
-        if (diag) {  // r block of this row panel: r[m] += Σ_k X[m,k] t_k
-#pragma unroll
-            for (int k = 0; k < KT / 2; ++k) {
-                const int kl = rhalf * (KT / 2) + k;
-                racc = fma(S.a[kl * LDT + rm], S.t[kl], racc);
+            for (int ni = 0; ni < 4; ++ni) {
+                const int col = wn * 32 + ni * 8 + kq * 2;
+                if (!diag || (mi - ni) >= thr)
+                    *reinterpret_cast<double2*>(Pt + row * TM + col) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&sm.empty[stg]));
-    }
-
-    // ---------------------------------------------------------------- epilogue: partial tile -> workspace
-    double* Pt = p.P + ((int64_t)split * p.ntiles + blockIdx.x) * (TM * TM);
-#pragma unroll
-    for (int mi = 0; mi < 8; ++mi) {
-        const int row = wm * 64 + mi * 8 + g;
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-            const int col = wn * 32 + ni * 8 + kq * 2;
-            *reinterpret_cast<double2*>(Pt + row * TM + col) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+        if (diag) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // rred may still be read by the previous segment
+            if (rhalf == 1) sm.rred[rm] = racc;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (rhalf == 0) p.Pr[(int64_t)sg * TM + rm] = racc + sm.rred[rm];
         }
-    }
-    if (diag) {
-        if (rhalf == 1) sm.rred[rm] = racc;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (rhalf == 0) p.Pr[((int64_t)split * p.nt + ti) * TM + rm] = racc + sm.rred[rm];
     }
 }
 
@@ -268,8 +333,7 @@ __global__ void __launch_bounds__(gg::THREADS) gram_generic_kernel(const double*
                                                                    int coalesce_n, int D, int64_t N,
                                                                    const double* __restrict__ s,
                                                                    const double* __restrict__ t, double* __restrict__ P,
-                                                                   double* __restrict__ Pr, int nt, int ntiles,
-                                                                   int64_t chunk) {
+                                                                   double* __restrict__ Pr, int nsplit, int64_t chunk) {
     using namespace gg;
     __shared__ double Xi[KC * LDS_], Xj[KC * LDS_], ss[KC], tt[KC];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -309,20 +373,22 @@ __global__ void __launch_bounds__(gg::THREADS) gram_generic_kernel(const double*
             for (int k = 0; k < KC; ++k) racc = fma(Xi[k * LDS_ + tid], tt[k], racc);
         }
     }
-    double* Pt = P + ((int64_t)split * ntiles + blockIdx.x) * (TS * TS);
+    const int64_t slot = (int64_t)blockIdx.x * nsplit + split;
+    double* Pt = P + slot * (TS * TS);
     Pt[(ty * 2) * TS + tx * 2] = c00;
     Pt[(ty * 2) * TS + tx * 2 + 1] = c01;
     Pt[(ty * 2 + 1) * TS + tx * 2] = c10;
     Pt[(ty * 2 + 1) * TS + tx * 2 + 1] = c11;
-    if (diag && tid < TS) Pr[((int64_t)split * nt + ti) * TS + tid] = racc;
+    if (diag && tid < TS) Pr[slot * TS + tid] = racc;
 }
 
-// ====================================================================== fixed-order split reduction
-// stats.G += Σ_split P (lower tiles mirrored to both triangles), stats.r += Σ_split Pr,
-// stats.{q, ℓ, n} += prep partials.  One CTA per tile; the sum over splits runs in index order.
+// ====================================================================== fixed-order partial reduction
+// stats.G += Σ_slots P (lower tiles mirrored to both triangles), stats.r += Σ_slots Pr,
+// stats.{q, ℓ, n} += prep partials.  One CTA per tile; the slots of a tile are visited in index order, so the
+// result does not depend on timing.  tile_slot_begin == nullptr: uniform layout, slots [t * nsplit, (t+1) * nsplit).
 __global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restrict__ P, const double* __restrict__ Pr,
-                                                          int TS, int nt, int ntiles, int nsplit, int D,
-                                                          double* __restrict__ G, double* __restrict__ r,
+                                                          int TS, const int* __restrict__ tile_slot_begin, int nsplit,
+                                                          int D, double* __restrict__ G, double* __restrict__ r,
                                                           double* __restrict__ scal,
                                                           const double* __restrict__ prep_partial, int prep_blocks,
                                                           double n_obs) {
@@ -330,12 +396,15 @@ __global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restri
     int ti, tj;
     tile_from_index(blockIdx.x, ti, tj);
     const int tsz = TS * TS;
+    const int s0 = tile_slot_begin ? tile_slot_begin[blockIdx.x] : blockIdx.x * nsplit;
+    const int s1 = tile_slot_begin ? tile_slot_begin[blockIdx.x + 1] : (blockIdx.x + 1) * nsplit;
     for (int e = threadIdx.x; e < tsz; e += blockDim.x) {
         const int row = e / TS, col = e % TS;
         const int gi = ti * TS + row, gj = tj * TS + col;
+        // diagonal tiles of the fast path only hold sub-tiles whose 8-row block is not above their 8-col block
         if (gi < D && gj < D && gi >= gj) {
             double v = 0.0;
-            for (int sp = 0; sp < nsplit; ++sp) v += P[((int64_t)sp * ntiles + blockIdx.x) * tsz + e];
+            for (int sl = s0; sl < s1; ++sl) v += P[(int64_t)sl * tsz + e];
             const double nv = G[(int64_t)gj * D + gi] + v;
             G[(int64_t)gj * D + gi] = nv;
             if (gi != gj) G[(int64_t)gi * D + gj] = nv;
@@ -346,7 +415,7 @@ __global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restri
             const int gi = ti * TS + m;
             if (gi < D) {
                 double v = 0.0;
-                for (int sp = 0; sp < nsplit; ++sp) v += Pr[((int64_t)sp * nt + ti) * TS + m];
+                for (int sl = s0; sl < s1; ++sl) v += Pr[(int64_t)sl * TS + m];
                 r[gi] += v;
             }
         }
@@ -390,7 +459,7 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
         const int64_t per_block = warp_per_obs ? PREP_THREADS / 32 : PREP_THREADS;
         prep_blocks = (int)std::min<int64_t>((npad + per_block - 1) / per_block, max_blocks);
     }
-    double* prep_partial = ctx->small;  // 2 * prep_blocks doubles (small buffer holds >= 2 * 8 * sm_count)
+    double* prep_partial = ctx->small + SMALL_PREP;
     if (mw_is_zero) {
         prep_kernel<BLR_COLVECS, false><<<prep_blocks, PREP_THREADS, 0, sm>>>(x->p, x->ld, D, N, npad, y, sigma2,
                                                                               sigma2_scalar, mw_dev, s, t, prep_partial);
@@ -418,30 +487,36 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
     }
     if (fast && ((ldc % 2) != 0 || (reinterpret_cast<uintptr_t>(Xc) & 15) != 0)) fast = false;
 
-    int TS, nt, ntiles, nsplit;
-    int64_t chunk;
     if (fast) {
-        TS = gk::TM;
-        nt = (D + TS - 1) / TS;
-        ntiles = nt * (nt + 1) / 2;
-        nsplit = std::max(1, ctx->sm_count / ntiles);
-        chunk = round_up((N + nsplit - 1) / nsplit, gk::KT);
-        nsplit = (int)((N + chunk - 1) / chunk);
-    } else {
-        TS = gg::TS;
-        nt = (D + TS - 1) / TS;
-        ntiles = nt * (nt + 1) / 2;
-        nsplit = std::max(1, (ctx->sm_count * 4) / ntiles);
-        chunk = round_up((N + nsplit - 1) / nsplit, gg::KC);
-        nsplit = (int)((N + chunk - 1) / chunk);
-    }
-    const size_t p_elems = (size_t)nsplit * ntiles * TS * TS;
-    const size_t pr_elems = (size_t)nsplit * nt * TS;
-    BLR_TRY(ensure_ws(ctx, (p_elems + pr_elems) * sizeof(double)));
-    double* P = ctx->ws;
-    double* Pr = ctx->ws + p_elems;
-
-    if (fast) {
+        const int TS = gk::TM;
+        const int nt = (D + TS - 1) / TS;
+        const int64_t n_stages = (N + gk::KT - 1) / gk::KT;
+        const int G = ctx->sm_count;
+        if (ctx->sched_key[0] != nt || ctx->sched_key[1] != n_stages || ctx->sched_key[2] != G ||
+            ctx->sched_key[3] != ctx->diag_weight) {
+            Schedule sc;
+            build_schedule(sc, nt, n_stages, G, ctx->diag_weight);
+            const size_t bytes = sc.table.size() * sizeof(int);
+            if (ctx->sched_bytes < bytes) {
+                BLR_CUDA_OK(ctx, cudaStreamSynchronize(sm));
+                if (ctx->sched) BLR_CUDA_OK(ctx, cudaFree(ctx->sched));
+                ctx->sched = nullptr;
+                ctx->sched_bytes = 0;
+                BLR_CUDA_OK(ctx, cudaMalloc(&ctx->sched, bytes * 2));
+                ctx->sched_bytes = bytes * 2;
+            }
+            BLR_CUDA_OK(ctx, cudaMemcpyAsync(ctx->sched, sc.table.data(), bytes, cudaMemcpyHostToDevice, sm));
+            BLR_CUDA_OK(ctx, cudaStreamSynchronize(sm));  // the host vector dies at the end of this scope
+            ctx->sched_key[0] = nt;
+            ctx->sched_key[1] = n_stages;
+            ctx->sched_key[2] = G;
+            ctx->sched_key[3] = ctx->diag_weight;
+            ctx->sched_T = sc.T;
+            ctx->sched_nseg = sc.nseg;
+        }
+        const int T = ctx->sched_T, nseg = ctx->sched_nseg;
+        const size_t p_elems = (size_t)nseg * TS * TS, pr_elems = (size_t)nseg * TS;
+        BLR_TRY(ensure_ws(ctx, (p_elems + pr_elems) * sizeof(double)));
         GramParams gp;
         gp.X = Xc;
         gp.ld = ldc;
@@ -449,27 +524,41 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
         gp.N = N;
         gp.s = s;
         gp.t = t;
-        gp.P = P;
-        gp.Pr = Pr;
-        gp.nt = nt;
-        gp.ntiles = ntiles;
-        gp.chunk = chunk;
+        gp.P = ctx->ws;
+        gp.Pr = ctx->ws + p_elems;
+        gp.cta_seg_begin = ctx->sched;
+        const int* tile_slot_begin = ctx->sched + (G + 1);
+        gp.seg_tile = tile_slot_begin + (T + 1);
+        gp.seg_g0 = gp.seg_tile + nseg;
+        gp.seg_g1 = gp.seg_g0 + nseg;
         BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)sizeof(gk::Smem)));
-        gram_tma_kernel<<<dim3(ntiles, nsplit), gk::THREADS, sizeof(gk::Smem), sm>>>(gp);
+        gram_tma_kernel<<<G, gk::THREADS, sizeof(gk::Smem), sm>>>(gp);
         BLR_CHECK_LAUNCH(ctx, "gram_tma_kernel");
+        BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], sm));
+        gram_reduce_kernel<<<T, 256, 0, sm>>>(gp.P, gp.Pr, TS, tile_slot_begin, 0, D, st->G(), st->r(), st->scal(),
+                                              prep_partial, prep_blocks, (double)N);
+        BLR_CHECK_LAUNCH(ctx, "gram_reduce_kernel");
     } else {
+        const int TS = gg::TS;
+        const int nt = (D + TS - 1) / TS, ntiles = nt * (nt + 1) / 2;
+        int nsplit = std::max(1, (ctx->sm_count * 4) / ntiles);
+        const int64_t chunk = round_up((N + nsplit - 1) / nsplit, gg::KC);
+        nsplit = (int)((N + chunk - 1) / chunk);
+        const size_t p_elems = (size_t)nsplit * ntiles * TS * TS, pr_elems = (size_t)nsplit * ntiles * TS;
+        BLR_TRY(ensure_ws(ctx, (p_elems + pr_elems) * sizeof(double)));
+        double* P = ctx->ws;
+        double* Pr = ctx->ws + p_elems;
         const bool colv = (x->layout == BLR_COLVECS);
         const int64_t sd = colv ? 1 : x->ld, sn = colv ? x->ld : 1;
         gram_generic_kernel<<<dim3(ntiles, nsplit), gg::THREADS, 0, sm>>>(x->p, sd, sn, colv ? 0 : 1, D, N, s, t, P, Pr,
-                                                                          nt, ntiles, chunk);
+                                                                          nsplit, chunk);
         BLR_CHECK_LAUNCH(ctx, "gram_generic_kernel");
+        BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], sm));
+        gram_reduce_kernel<<<ntiles, 256, 0, sm>>>(P, Pr, TS, nullptr, nsplit, D, st->G(), st->r(), st->scal(),
+                                                   prep_partial, prep_blocks, (double)N);
+        BLR_CHECK_LAUNCH(ctx, "gram_reduce_kernel");
     }
-    BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], sm));
-
-    gram_reduce_kernel<<<ntiles, 256, 0, sm>>>(P, Pr, TS, nt, ntiles, nsplit, D, st->G(), st->r(), st->scal(),
-                                               prep_partial, prep_blocks, (double)N);
-    BLR_CHECK_LAUNCH(ctx, "gram_reduce_kernel");
     BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], sm));
     ctx->ev_valid[0] = ctx->ev_valid[1] = ctx->ev_valid[2] = true;
     if (xt) BLR_CUDA_OK(ctx, cudaFreeAsync(xt, sm));

@@ -53,6 +53,12 @@ struct blr_ctx {
     int* d_info = nullptr;
     cudaEvent_t ev[8] = {};
     bool ev_valid[4] = {};
+    // stream-K schedule of the Gram fast path (cached by shape)
+    int* sched = nullptr;
+    size_t sched_bytes = 0;
+    int64_t sched_key[4] = {-1, -1, -1, -1};
+    int sched_T = 0, sched_nseg = 0;
+    int diag_weight = 40;  // cost of a diagonal-tile stage relative to W_OFF = 64 (BLR_DIAG_WEIGHT overrides)
     // host-streaming path (blr_stats_accumulate_host): copy stream, two staging slots
     cudaStream_t copy_stream = nullptr;
     double* stage[2] = {nullptr, nullptr};
@@ -139,6 +145,7 @@ int transpose_to_colvecs(blr_ctx* ctx, const blr_x* x, double* out, int64_t ldo)
 // ---- calib.cu
 int calib_dmma(blr_ctx* ctx, double* tflops);
 int calib_dfma(blr_ctx* ctx, double* tflops);
+int calib_dmma_cfg(blr_ctx* ctx, int warps, int nacc, double* tflops);
 int calib_hbm(blr_ctx* ctx, double* gbs);
 
 }  // namespace blr

@@ -253,7 +253,7 @@ def run_ours(args):
         }
 
     # ---- e2e: same metric through the public API with HOST buffers (H2D of every chunk + D2H of results timed)
-    if rank == 0 or world > 1:
+    if (rank == 0 or world > 1) and not args.no_e2e:
         e2e = run_e2e(args, ctx, blr, torch, rank, world)
         if out is not None:
             out["e2e"] = e2e
@@ -343,6 +343,7 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=1 << 16)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-calibrate", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

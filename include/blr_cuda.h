@@ -177,6 +177,8 @@ int blr_apply_weights(blr_ctx* ctx, const blr_x* x, const double* w_host, double
  * ("fp64 peak must be calibrated on-box").  Pure DMMA.8x8x4 issue loop over all SMs and a
  * device-to-device copy; results in TFLOP/s (2 flop per FMA) and GB/s (read + write bytes). */
 int blr_calibrate_dmma(blr_ctx* ctx, double* tflops_out);
+/* issue-rate probe: `warps_per_sm` warps on every SM, each with `n_acc` (1..32, power of two) independent DMMA chains */
+int blr_calibrate_dmma_cfg(blr_ctx* ctx, int warps_per_sm, int n_acc, double* tflops_out);
 int blr_calibrate_dfma(blr_ctx* ctx, double* tflops_out);
 int blr_calibrate_hbm(blr_ctx* ctx, double* gbs_out);
 

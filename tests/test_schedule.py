@@ -1,0 +1,35 @@
+"""CPU: the stream-K schedule of the Gram kernel (host logic, csrc/schedule.h) covers every (tile, stage) exactly
+once, keeps the segments of a tile contiguous (fixed reduction order) and balances weighted work across CTAs."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "bayesianlinearregressors.jl_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def exe(tmp_path_factory):
+    out = tmp_path_factory.mktemp("sched") / "schedule_test"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", CSRC, os.path.join(ROOT, "tests", "cpp", "schedule_test.cpp"), "-o", str(out)],
+                   check=True)
+    return str(out)
+
+
+@pytest.mark.parametrize("nt,n_stages,G,wd", [
+    (8, 1 << 20, 148, 40),   # cfg3: D=1024, N=2^24
+    (2, 65536, 148, 40),     # cfg2: D=256, N=2^20
+    (32, 262144, 148, 36),   # cfg5: D=4096, N=2^22
+    (1, 1, 148, 40), (1, 7, 148, 40), (3, 5, 148, 64), (2, 1000, 1, 40), (5, 999, 7, 50), (8, 131072, 132, 44),
+])
+def test_schedule_properties(exe, nt, n_stages, G, wd):
+    res = subprocess.run([exe, str(nt), str(n_stages), str(G), str(wd)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout
+    tag, nseg, mx, mn = res.stdout.split()
+    assert tag == "ok"
+    T = nt * (nt + 1) // 2
+    assert int(nseg) <= G + T
+    total = n_stages * (nt * wd + (T - nt) * 64)
+    # no CTA carries more than its fair share plus one stage of the heaviest tile per segment boundary
+    assert int(mx) <= total // G + 2 * 64 + 1

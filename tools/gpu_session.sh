@@ -34,6 +34,24 @@ print(json.dumps(c.calibrate()))
     ncu_full)
       timeout 1200 ncu --set full --clock-control none --import-source on -k regex:gram_tma -s 1 -c 1 -o "$OUT/prof_gram" -f \
         python bench.py --n-obs 2097152 --steps 1 --warmup 1 --no-cpu --no-calibrate --e2e-obs 65536 > "$OUT/ncu_full.log" 2>&1; echo "ncu_full exit $?";;
+    dmma_probe)
+      timeout 300 python -c "
+import blr_b200 as b, ctypes as C
+c = b.Context(0)
+for w in (1,2,3,4,8,12,16):
+    row=[]
+    for na in (1,2,4,8,16,32):
+        v=C.c_double(); c.check(c.lib.blr_calibrate_dmma_cfg(c.handle, w, na, C.byref(v))); row.append(round(v.value,2))
+    print('warps/SM', w, 'n_acc 1,2,4,8,16,32 ->', row)
+" > "$OUT/dmma_probe.log" 2>&1; echo "dmma_probe exit $?"; cat "$OUT/dmma_probe.log";;
+    sweep_diag)
+      for w in 36 38 40 42; do
+        for cfg in "--n-obs 1048576 --dim 256" "--n-obs 4194304 --dim 1024"; do
+          echo "diag_weight=$w cfg=$cfg"
+          BLR_DIAG_WEIGHT=$w timeout 600 python bench.py $cfg --steps 5 --warmup 3 --no-cpu --no-e2e --no-calibrate 2>> "$OUT/sweep.err" \
+            | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['achieved'])"
+        done
+      done 2>&1 | tee "$OUT/sweep_diag.log";;
     *) echo "unknown stage $stage";;
   esac
 done
