@@ -34,6 +34,12 @@ static int grow(blr_ctx* ctx, double** buf, size_t* cap, size_t bytes) {
     *cap = bytes;
     return 0;
 }
+cudaError_t dev_alloc(blr_ctx* ctx, double** p, size_t bytes) {
+    return cudaMallocAsync(reinterpret_cast<void**>(p), std::max<size_t>(bytes, 16), ctx->stream);
+}
+void dev_free(cudaStream_t stream, void* p) {
+    if (p) cudaFreeAsync(p, stream);
+}
 int ensure_ws(blr_ctx* ctx, size_t bytes) { return grow(ctx, &ctx->ws, &ctx->ws_bytes, bytes); }
 int ensure_nbuf(blr_ctx* ctx, size_t bytes) { return grow(ctx, &ctx->nbuf, &ctx->nbuf_bytes, bytes); }
 
@@ -126,6 +132,13 @@ int blr_ctx_create(blr_ctx** out, int device) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    {   // keep freed blocks in the device's default pool: steady-state calls never hit cudaMalloc / cudaFree
+        cudaMemPool_t pool;
+        if (e == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->small, (size_t)SMALL_TOTAL * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_info, sizeof(int));
@@ -429,10 +442,10 @@ int blr_stats_create(blr_ctx* ctx, int64_t D, blr_stats** out) {
     if (!out || D < 1 || D > SMALL_VEC) return set_err(ctx, BLR_E_INVALID, "bad D (1 <= D <= 16384)");
     blr_stats* s = new blr_stats();
     s->D = D;
-    cudaError_t e = cudaMalloc(&s->p, (size_t)s->len() * sizeof(double));
+    cudaError_t e = dev_alloc(ctx, &s->p, (size_t)s->len() * sizeof(double));
     if (e != cudaSuccess) {
         delete s;
-        return cuda_fail(ctx, e, "cudaMalloc(stats)");
+        return cuda_fail(ctx, e, "cudaMallocAsync(stats)");
     }
     *out = s;
     return blr_stats_zero(ctx, s);
@@ -441,9 +454,10 @@ int blr_stats_free(blr_ctx* ctx, blr_stats* s) {
     if (!s) return 0;
     if (ctx) {
         cudaSetDevice(ctx->device);
-        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        dev_free(ctx->stream, s->p);
+    } else {
+        cudaFree(s->p);
     }
-    cudaFree(s->p);
     delete s;
     return 0;
 }
@@ -615,10 +629,7 @@ int blr_post_create(blr_ctx* ctx, const blr_prior* prior, int64_t D, blr_post** 
 }
 int blr_post_free(blr_ctx* ctx, blr_post* p) {
     if (!p) return 0;
-    if (ctx) {
-        cudaSetDevice(ctx->device);
-        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    }
+    if (ctx) cudaSetDevice(ctx->device);
     post_release(p);
     return 0;
 }
@@ -646,7 +657,7 @@ int blr_mean_var(blr_ctx* ctx, blr_post* p, const blr_x* x, const blr_noise* noi
     const int64_t N = x->N;
     if (N == 0) return 0;
     double* buf = nullptr;
-    BLR_CUDA_OK(ctx, cudaMalloc(&buf, (size_t)2 * N * sizeof(double)));
+    BLR_CUDA_OK(ctx, dev_alloc(ctx, &buf, (size_t)2 * N * sizeof(double)));
     int rc = blr_mean_var_dev(ctx, p, x, noise, mean_host ? buf : nullptr, var_host ? buf + N : nullptr);
     cudaError_t e = cudaSuccess;
     if (rc == 0 && mean_host)
@@ -654,7 +665,7 @@ int blr_mean_var(blr_ctx* ctx, blr_post* p, const blr_x* x, const blr_noise* noi
     if (rc == 0 && e == cudaSuccess && var_host)
         e = cudaMemcpyAsync(var_host, buf + N, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-    cudaFree(buf);
+    dev_free(ctx->stream, buf);
     if (rc != 0) return rc;
     if (e != cudaSuccess) return cuda_fail(ctx, e, "download mean/var");
     if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "mean_var sync");
@@ -671,12 +682,12 @@ int blr_cov(blr_ctx* ctx, blr_post* p, const blr_x* x, const blr_noise* noise, d
     double sig_scalar = 0.0;
     BLR_TRY(noise_args(ctx, noise, N, &sig, &sig_scalar));
     double* C = nullptr;
-    BLR_CUDA_OK(ctx, cudaMalloc(&C, (size_t)N * N * sizeof(double)));
+    BLR_CUDA_OK(ctx, dev_alloc(ctx, &C, (size_t)N * N * sizeof(double)));
     int rc = predict_cov(ctx, p, x, sig, sig_scalar, C);
     cudaError_t e = cudaSuccess;
     if (rc == 0) e = cudaMemcpyAsync(C_host, C, (size_t)N * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-    cudaFree(C);
+    dev_free(ctx->stream, C);
     if (rc != 0) return rc;
     if (e != cudaSuccess) return cuda_fail(ctx, e, "download cov");
     if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "cov sync");
@@ -689,7 +700,7 @@ int blr_rand_weights(blr_ctx* ctx, blr_post* p, int64_t S, const double* Z, uint
     if (S == 0) return 0;
     const int64_t D = p->D;
     double* buf = nullptr;
-    BLR_CUDA_OK(ctx, cudaMalloc(&buf, (size_t)2 * (D + 1) * S * sizeof(double)));
+    BLR_CUDA_OK(ctx, dev_alloc(ctx, &buf, (size_t)2 * (D + 1) * S * sizeof(double)));
     double *Zd = buf, *Wd = buf + (D + 1) * S;
     int rc = 0;
     cudaError_t e = cudaSuccess;
@@ -701,7 +712,7 @@ int blr_rand_weights(blr_ctx* ctx, blr_post* p, int64_t S, const double* Z, uint
     if (rc == 0 && e == cudaSuccess)
         e = cudaMemcpyAsync(W_host, Wd, (size_t)D * S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-    cudaFree(buf);
+    dev_free(ctx->stream, buf);
     if (rc != 0) return rc;
     if (e != cudaSuccess) return cuda_fail(ctx, e, "rand_weights copy");
     if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "rand_weights sync");
@@ -719,7 +730,7 @@ int blr_rand_finite_dev(blr_ctx* ctx, blr_post* p, const blr_x* x, const blr_noi
     double sig_scalar = 0.0;
     BLR_TRY(noise_args(ctx, noise, x->N, &sig, &sig_scalar));
     double* buf = nullptr;
-    BLR_CUDA_OK(ctx, cudaMalloc(&buf, (size_t)2 * (D + 1) * S * sizeof(double)));
+    BLR_CUDA_OK(ctx, dev_alloc(ctx, &buf, (size_t)2 * (D + 1) * S * sizeof(double)));
     double *Zd = buf, *Wd = buf + (D + 1) * S;
     int rc = 0;
     cudaError_t e = cudaSuccess;
@@ -730,7 +741,7 @@ int blr_rand_finite_dev(blr_ctx* ctx, blr_post* p, const blr_x* x, const blr_noi
     if (rc == 0 && e == cudaSuccess) rc = sample_weights(ctx, p, S, Zd, Wd);
     if (rc == 0 && e == cudaSuccess) rc = sample_finite(ctx, x, Wd, S, sig, sig_scalar, Zy_dev, seed, Y_dev);
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-    cudaFree(buf);
+    dev_free(ctx->stream, buf);
     if (rc != 0) return rc;
     if (e != cudaSuccess) return cuda_fail(ctx, e, "rand_finite copy");
     if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "rand_finite sync");
@@ -744,10 +755,10 @@ int blr_rand_finite(blr_ctx* ctx, blr_post* p, const blr_x* x, const blr_noise* 
     const int64_t N = x->N;
     if (S == 0 || N == 0) return 0;
     double *Yd = nullptr, *Zyd = nullptr;
-    BLR_CUDA_OK(ctx, cudaMalloc(&Yd, (size_t)N * S * sizeof(double)));
+    BLR_CUDA_OK(ctx, dev_alloc(ctx, &Yd, (size_t)N * S * sizeof(double)));
     cudaError_t e = cudaSuccess;
     if (Zy) {
-        e = cudaMalloc(&Zyd, (size_t)N * S * sizeof(double));
+        e = dev_alloc(ctx, &Zyd, (size_t)N * S * sizeof(double));
         if (e == cudaSuccess)
             e = cudaMemcpyAsync(Zyd, Zy, (size_t)N * S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
     }
@@ -755,8 +766,8 @@ int blr_rand_finite(blr_ctx* ctx, blr_post* p, const blr_x* x, const blr_noise* 
     if (rc == 0 && e == cudaSuccess)
         e = cudaMemcpyAsync(Y_host, Yd, (size_t)N * S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-    cudaFree(Yd);
-    cudaFree(Zyd);
+    dev_free(ctx->stream, Yd);
+    dev_free(ctx->stream, Zyd);
     if (rc != 0) return rc;
     if (e != cudaSuccess) return cuda_fail(ctx, e, "rand_finite copy");
     if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "rand_finite sync");
@@ -768,13 +779,13 @@ int blr_apply_weights(blr_ctx* ctx, const blr_x* x, const double* w_host, double
     if (!x || !w_host || !out_host) return set_err(ctx, BLR_E_INVALID, "null argument");
     if (x->N == 0) return 0;
     double* buf = nullptr;
-    BLR_CUDA_OK(ctx, cudaMalloc(&buf, (size_t)(x->N + x->D) * sizeof(double)));
+    BLR_CUDA_OK(ctx, dev_alloc(ctx, &buf, (size_t)(x->N + x->D) * sizeof(double)));
     cudaError_t e = cudaMemcpyAsync(buf + x->N, w_host, (size_t)x->D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
     int rc = (e == cudaSuccess) ? apply_weights(ctx, x, buf + x->N, buf) : 0;
     if (rc == 0 && e == cudaSuccess)
         e = cudaMemcpyAsync(out_host, buf, (size_t)x->N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-    cudaFree(buf);
+    dev_free(ctx->stream, buf);
     if (rc != 0) return rc;
     if (e != cudaSuccess) return cuda_fail(ctx, e, "apply_weights copy");
     if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "apply_weights sync");

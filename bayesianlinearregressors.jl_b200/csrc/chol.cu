@@ -371,19 +371,20 @@ __global__ void finalize_kernel(const double* __restrict__ scal /* q, ℓ, n */,
 
 void post_release(blr_post* p) {
     if (!p) return;
-    cudaFree(p->mw);
-    cudaFree(p->L);
-    cudaFree(p->W);
-    cudaFree(p->Lam);
+    dev_free(p->stream, p->mw);
+    dev_free(p->stream, p->L);
+    dev_free(p->stream, p->W);
+    dev_free(p->stream, p->Lam);
     delete p;
 }
 
 static int alloc_post(blr_ctx* ctx, int64_t D, blr_post** out) {
     blr_post* p = new blr_post();
     p->D = D;
-    cudaError_t e = cudaMalloc(&p->mw, (size_t)D * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&p->L, (size_t)D * D * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&p->Lam, (size_t)D * D * sizeof(double));
+    p->stream = ctx->stream;
+    cudaError_t e = dev_alloc(ctx, &p->mw, (size_t)D * sizeof(double));
+    if (e == cudaSuccess) e = dev_alloc(ctx, &p->L, (size_t)D * D * sizeof(double));
+    if (e == cudaSuccess) e = dev_alloc(ctx, &p->Lam, (size_t)D * D * sizeof(double));
     if (e != cudaSuccess) {
         post_release(p);
         return cuda_fail(ctx, e, "cudaMalloc(post)");
@@ -411,15 +412,13 @@ static int upload_prior_precision(blr_ctx* ctx, const blr_prior* prior, int64_t 
         BLR_CUDA_OK(ctx, cudaMemcpyAsync(dtmp, prior->lambda, (size_t)D * sizeof(double), cudaMemcpyHostToDevice, sm));
         set_diag_kernel<<<(int)((D + 255) / 256), 256, 0, sm>>>(Lam_dev, dtmp, (int)D);
         BLR_CHECK_LAUNCH(ctx, "set_diag_kernel");
-        BLR_CUDA_OK(ctx, cudaStreamSynchronize(sm));  // dtmp / host buffer reuse
-        return 0;
+        return 0;  // no host sync: dtmp reuse is stream-ordered and pageable H2D copies are staged before returning
     }
     if (prior->lambda_kind == BLR_LAMBDA_DENSE) {
         const int64_t ld = prior->ld > 0 ? prior->ld : D;
         if (ld < D) return set_err(ctx, BLR_E_INVALID, "prior.ld < D");
         BLR_CUDA_OK(ctx, cudaMemcpy2DAsync(Lam_dev, (size_t)D * sizeof(double), prior->lambda, (size_t)ld * sizeof(double),
                                            (size_t)D * sizeof(double), (size_t)D, cudaMemcpyHostToDevice, sm));
-        BLR_CUDA_OK(ctx, cudaStreamSynchronize(sm));
         return 0;
     }
     return set_err(ctx, BLR_E_INVALID, "unknown lambda_kind");
@@ -462,7 +461,7 @@ int post_from_prior(blr_ctx* ctx, const blr_prior* prior, int64_t D, blr_post** 
 
 int post_ensure_W(blr_ctx* ctx, blr_post* p) {
     if (p->has_W) return 0;
-    if (!p->W) BLR_CUDA_OK(ctx, cudaMalloc(&p->W, (size_t)p->D * p->D * sizeof(double)));
+    if (!p->W) BLR_CUDA_OK(ctx, dev_alloc(ctx, &p->W, (size_t)p->D * p->D * sizeof(double)));
     BLR_TRY(trtri_lower(ctx, p->L, p->W, p->D));
     p->has_W = true;
     return 0;
@@ -534,7 +533,7 @@ int infer_solve(blr_ctx* ctx, const blr_prior* prior, const blr_stats* st, doubl
     if (L_post) BLR_CUDA_OK(ctx, cudaMemcpyAsync(L_post, p->Lam, (size_t)n2 * sizeof(double), cudaMemcpyDeviceToHost, sm));
     if (T_post) {
         // T = L'^T (upper).  Transpose into the (not yet built) W buffer, then download.
-        if (!p->W) BLR_CUDA_OK(ctx, cudaMalloc(&p->W, (size_t)n2 * sizeof(double)));
+        if (!p->W) BLR_CUDA_OK(ctx, dev_alloc(ctx, &p->W, (size_t)n2 * sizeof(double)));
         dim3 grid((unsigned)((D + 31) / 32), (unsigned)((D + 31) / 32)), block(32, 8);
         transpose_square_kernel<<<grid, block, 0, sm>>>(p->L, p->W, (int)D);
         BLR_CHECK_LAUNCH(ctx, "transpose_square_kernel");

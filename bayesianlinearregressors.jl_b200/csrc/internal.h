@@ -35,6 +35,7 @@ struct blr_post {
     double* W = nullptr;     // D x D lower, W = inv(L); built lazily for var / rand
     double* Lam = nullptr;   // D x D precision (kept for download)
     bool has_W = false;
+    cudaStream_t stream = nullptr;  // stream the buffers were allocated on (stream-ordered pool)
 };
 
 struct blr_ctx {
@@ -82,6 +83,9 @@ constexpr int SMALL_TOTAL = SMALL_DTMP + SMALL_VEC;
 
 int set_err(blr_ctx* ctx, int code, const std::string& msg);
 int cuda_fail(blr_ctx* ctx, cudaError_t e, const char* what);
+// stream-ordered allocations for per-call objects (no device-wide synchronisation, memory retained by the pool)
+cudaError_t dev_alloc(blr_ctx* ctx, double** p, size_t bytes);
+void dev_free(cudaStream_t stream, void* p);
 int ensure_ws(blr_ctx* ctx, size_t bytes);
 int ensure_nbuf(blr_ctx* ctx, size_t bytes);
 

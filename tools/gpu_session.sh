@@ -34,6 +34,21 @@ print(json.dumps(c.calibrate()))
     ncu_full)
       timeout 1200 ncu --set full --clock-control none --import-source on -k regex:gram_tma -s 1 -c 1 -o "$OUT/prof_gram" -f \
         python bench.py --n-obs 2097152 --steps 1 --warmup 1 --no-cpu --no-calibrate --e2e-obs 65536 > "$OUT/ncu_full.log" 2>&1; echo "ncu_full exit $?";;
+    multi_tests)
+      timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -x --timeout 600 > "$OUT/multi_tests.log" 2>&1; echo "multi_tests exit $?"; tail -15 "$OUT/multi_tests.log";;
+    bench_multi)
+      NG=$(nvidia-smi -L | wc -l)
+      for n in 1 2 4 8; do
+        if [ $n -le $NG ]; then
+          if [ $n -eq 1 ]; then
+            timeout 900 python bench.py --gpus 1 --steps 3 --warmup 3 --no-cpu --no-e2e > "$OUT/bench_g$n.json" 2> "$OUT/bench_g$n.err"
+          else
+            timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 \
+              bench.py --gpus $n --steps 3 --warmup 3 --no-cpu --no-e2e > "$OUT/bench_g$n.json" 2> "$OUT/bench_g$n.err"
+          fi
+          echo "bench_multi n=$n exit $?"; tail -c 1200 "$OUT/bench_g$n.json"; tail -3 "$OUT/bench_g$n.err"
+        fi
+      done;;
     dmma_probe)
       timeout 300 python -c "
 import blr_b200 as b, ctypes as C
