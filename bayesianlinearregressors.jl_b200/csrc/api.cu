@@ -42,6 +42,7 @@ void dev_free(cudaStream_t stream, void* p) {
 }
 int ensure_ws(blr_ctx* ctx, size_t bytes) { return grow(ctx, &ctx->ws, &ctx->ws_bytes, bytes); }
 int ensure_nbuf(blr_ctx* ctx, size_t bytes) { return grow(ctx, &ctx->nbuf, &ctx->nbuf_bytes, bytes); }
+int ensure_dinv(blr_ctx* ctx, size_t bytes) { return grow(ctx, &ctx->dinv, &ctx->dinv_bytes, bytes); }
 
 // ---------------------------------------------------------------------------------------------- NCCL via dlopen
 struct NcclApi {
@@ -142,6 +143,8 @@ int blr_ctx_create(blr_ctx** out, int device) {
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->small, (size_t)SMALL_TOTAL * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_info, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_flags, 512 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_flags, 0, 512 * sizeof(int));
     if (e != cudaSuccess || ctx->sm_count * 16 > SMALL_SC) {
         blr_ctx_destroy(ctx);
         return BLR_E_CUDA;
@@ -162,8 +165,10 @@ int blr_ctx_destroy(blr_ctx* ctx) {
     blr_comm_destroy(ctx);
     cudaFree(ctx->ws);
     cudaFree(ctx->nbuf);
+    cudaFree(ctx->dinv);
     cudaFree(ctx->small);
     cudaFree(ctx->d_info);
+    cudaFree(ctx->d_flags);
     cudaFree(ctx->sched);
     cudaFree(ctx->stage[0]);
     cudaFree(ctx->stage[1]);

@@ -20,40 +20,49 @@ namespace blr {
 constexpr int NB = 64;  // block size of the D x D phase
 
 // ---------------------------------------------------------------------------------------------
-// Factor a 64 x 64 diagonal block held in shared memory (Ls[c * 65 + r], lower part used).
-// Blocks smaller than 64 are padded with the identity by the caller.  Returns (to all threads) the
-// 1-based index of the first non-positive pivot, or 0.
-__device__ int factor_block_smem(double* Ls, int nthreads) {
+// Factor a 64 x 64 diagonal block held in shared memory: Ls[c * 65 + r] = element (r, c), lower part + diagonal
+// hold the (partially updated) matrix.  Right-looking, ONE barrier per column: the scaled column k of the factor
+// is written into the unused upper triangle at the transposed position (row k, col i) = Ls[i * 65 + k], so it never
+// races with the threads still reading the unscaled column.  On return  L[i][k] = Ls[i * 65 + k]  for i >= k
+// (i.e. the factor sits transposed in the upper triangle + diagonal) and rdiag[k] = 1 / L[k][k].
+// Blocks smaller than 64 are padded with the identity by the caller.  256 threads: tx = row, ty = column phase.
+// Returns (to all threads) the 1-based index of the first non-positive pivot, or 0.
+constexpr int PANEL_THREADS = 256;
+__device__ int factor_block_smem(double* Ls, double* rdiag) {
     __shared__ int fail;
+    const int i = threadIdx.x & 63, ty = threadIdx.x >> 6;
     if (threadIdx.x == 0) fail = 0;
     __syncthreads();
     for (int k = 0; k < NB; ++k) {
-        if (threadIdx.x == 0) {
-            const double d = Ls[k * 65 + k];
-            if (!(d > 0.0) && fail == 0) fail = k + 1;
-            Ls[k * 65 + k] = sqrt(d);
+        const double akk = Ls[k * 65 + k];
+        const double inv = 1.0 / akk, d = sqrt(akk), rd = 1.0 / d;
+        const double aik = Ls[k * 65 + i];  // element (i, k): still unscaled
+        if (i > k) {
+            for (int j = k + 1 + ty; j <= i; j += 4) Ls[j * 65 + i] -= aik * (Ls[k * 65 + j] * inv);
         }
-        __syncthreads();
-        const double inv = 1.0 / Ls[k * 65 + k];
-        for (int i = k + 1 + threadIdx.x; i < NB; i += nthreads) Ls[k * 65 + i] *= inv;
-        __syncthreads();
-        const int m = NB - k - 1;
-        for (int e = threadIdx.x; e < m * m; e += nthreads) {
-            const int j = k + 1 + e / m, i = k + 1 + e % m;
-            if (i >= j) Ls[j * 65 + i] -= Ls[k * 65 + i] * Ls[k * 65 + j];
+        __syncthreads();  // all reads of column k done; updates visible
+        if (ty == 0) {
+            if (i > k) Ls[i * 65 + k] = aik * rd;  // transposed slot (row k, col i)
+            if (i == k) {
+                Ls[k * 65 + k] = d;
+                rdiag[k] = rd;
+                if (!(akk > 0.0) && fail == 0) fail = k + 1;
+            }
         }
-        __syncthreads();
+        // no barrier needed here: the slots just written are in row k (upper part) / the diagonal element (k, k),
+        // which later iterations never read (they read columns k' > k at rows >= k').
     }
+    __syncthreads();
     return fail;
 }
 
 // Panel step j of the right-looking Cholesky: every CTA factors the diagonal block A[j0:j0+64, j0:j0+64]
 // redundantly in shared memory (saves a launch + a dependency), CTA 0 writes it back, and each CTA solves
-// 128 rows of the panel below:  L21 = A21 * L11^-T  (one thread per row, unrolled substitution in registers).
-constexpr int PANEL_THREADS = 128;
-__global__ void __launch_bounds__(PANEL_THREADS) potrf_panel_kernel(double* __restrict__ A, int64_t ld, int D, int j0,
-                                                                    int* __restrict__ info) {
+// 256 rows of the panel below:  L21 = A21 * L11^-T  (one thread per row, unrolled substitution in registers).
+__global__ void __launch_bounds__(PANEL_THREADS, 1) potrf_panel_kernel(double* __restrict__ A, int64_t ld, int D, int j0,
+                                                                       int* __restrict__ info) {
     __shared__ double Ls[NB * 65];
+    __shared__ double rdiag[NB];
     const int nbj = min(NB, D - j0);
     for (int e = threadIdx.x; e < NB * NB; e += PANEL_THREADS) {
         const int r = e % NB, c = e / NB;
@@ -62,11 +71,12 @@ __global__ void __launch_bounds__(PANEL_THREADS) potrf_panel_kernel(double* __re
         Ls[c * 65 + r] = v;
     }
     __syncthreads();
-    const int fail = factor_block_smem(Ls, PANEL_THREADS);
+    const int fail = factor_block_smem(Ls, rdiag);
+    // L[r][c] (r >= c) now lives at Ls[r * 65 + c]
     if (blockIdx.x == 0) {
         for (int e = threadIdx.x; e < NB * NB; e += PANEL_THREADS) {
             const int r = e % NB, c = e / NB;
-            if (r < nbj && c < nbj) A[(int64_t)(j0 + c) * ld + j0 + r] = (r >= c) ? Ls[c * 65 + r] : 0.0;
+            if (r < nbj && c < nbj) A[(int64_t)(j0 + c) * ld + j0 + r] = (r >= c) ? Ls[r * 65 + c] : 0.0;
         }
         if (threadIdx.x == 0 && fail != 0 && *info == 0) *info = j0 + fail;
     }
@@ -77,10 +87,10 @@ __global__ void __launch_bounds__(PANEL_THREADS) potrf_panel_kernel(double* __re
         for (int c = 0; c < NB; ++c) a[c] = A[(int64_t)(j0 + c) * ld + row];
 #pragma unroll
         for (int k = 0; k < NB; ++k) {
-            const double xk = a[k] / Ls[k * 65 + k];
+            const double xk = a[k] * rdiag[k];
             a[k] = xk;
 #pragma unroll
-            for (int c = k + 1; c < NB; ++c) a[c] = fma(-xk, Ls[k * 65 + c], a[c]);
+            for (int c = k + 1; c < NB; ++c) a[c] = fma(-xk, Ls[c * 65 + k], a[c]);  // L[c][k], broadcast read
         }
 #pragma unroll
         for (int c = 0; c < NB; ++c) A[(int64_t)(j0 + c) * ld + row] = a[c];
@@ -138,103 +148,137 @@ int potrf_lower(blr_ctx* ctx, double* A, int64_t D64, int* info_dev) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Triangular solves with a single right-hand side (single CTA; the D x D factor is streamed once).
-constexpr int TRSV_THREADS = 512;
+// Triangular solves with a single right-hand side, as a wavefront over 64-row blocks: one CTA per block row,
+//     x_j = inv(L_jj) (b_j - Σ_{k<j} L_jk x_k)            (forward;  backward is the transposed mirror image)
+// CTA j consumes x_k as soon as CTA k publishes it (flag = launch epoch, release/acquire through global memory),
+// so the D x D factor is streamed by D/64 SMs at once and the critical path is D/64 short steps instead of one
+// SM reading the whole matrix.  inv(L_jj) comes from trtri_diag_packed_kernel.  CTAs only wait on lower
+// blockIdx (dispatch order), so the grid cannot deadlock even if it were not fully resident.
+constexpr int TRSV_THREADS = 256;
 
-// L z = b
-__global__ void __launch_bounds__(TRSV_THREADS) trsv_forward_kernel(const double* __restrict__ L, int64_t ld, int D,
-                                                                    double* __restrict__ b) {
-    __shared__ double Ls[NB * 65];
-    __shared__ double zb[NB];
-    const int tid = threadIdx.x;
-    for (int j0 = 0; j0 < D; j0 += NB) {
-        const int nbj = min(NB, D - j0);
-        __syncthreads();
-        for (int e = tid; e < NB * NB; e += TRSV_THREADS) {
-            const int r = e % NB, c = e / NB;
-            Ls[c * 65 + r] = (r < nbj && c < nbj && r >= c) ? L[(int64_t)(j0 + c) * ld + j0 + r] : (r == c ? 1.0 : 0.0);
+__device__ __forceinline__ void wait_flag(const int* flag, int epoch) {
+    if (threadIdx.x == 0) {
+        while (*reinterpret_cast<const volatile int*>(flag) < epoch) {
         }
-        if (tid < NB) zb[tid] = (tid < nbj) ? b[j0 + tid] : 0.0;
-        __syncthreads();
-        if (tid < 32) {  // warp 0: substitution inside the block, lane owns rows lane and lane + 32
-            double x0 = zb[tid], x1 = zb[tid + 32];
-            for (int c = 0; c < NB; ++c) {
-                const double src = (c < 32) ? x0 : x1;
-                const double zc = __shfl_sync(0xffffffffu, src, c & 31) / Ls[c * 65 + c];
-                if (tid == (c & 31)) {
-                    if (c < 32) x0 = zc; else x1 = zc;
-                }
-                if (tid > c) x0 = fma(-zc, Ls[c * 65 + tid], x0);
-                if (tid + 32 > c) x1 = fma(-zc, Ls[c * 65 + tid + 32], x1);
-            }
-            zb[tid] = x0;
-            zb[tid + 32] = x1;
-        }
-        __syncthreads();
-        if (tid < nbj) b[j0 + tid] = zb[tid];
-        // rows below the block: b[i] -= Σ_c L[i, j0 + c] z_c   (column-major: coalesced over i)
-        for (int i = j0 + NB + tid; i < D; i += TRSV_THREADS) {
-            double acc = b[i];
-#pragma unroll 8
-            for (int c = 0; c < NB; ++c) acc = fma(-L[(int64_t)(j0 + c) * ld + i], zb[c], acc);
-            b[i] = acc;
-        }
+        __threadfence();
     }
+    __syncthreads();
 }
 
-// L' u = z
-__global__ void __launch_bounds__(TRSV_THREADS) trsv_backward_kernel(const double* __restrict__ L, int64_t ld, int D,
-                                                                     double* __restrict__ b) {
+// Dinv[b][c * 64 + r] = (inv(L_bb))[r][c]; identity padding for a partial last block
+__global__ void __launch_bounds__(NB) trtri_diag_packed_kernel(const double* __restrict__ L, int64_t ld, int D,
+                                                               double* __restrict__ Dinv) {
     __shared__ double Ls[NB * 65];
-    __shared__ double zb[NB];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int j0 = blockIdx.x * NB, nbj = min(NB, D - j0), c = threadIdx.x;
+    for (int e = threadIdx.x; e < NB * NB; e += NB) {
+        const int r = e % NB, cc = e / NB;
+        Ls[cc * 65 + r] = (r < nbj && cc < nbj && r >= cc) ? L[(int64_t)(j0 + cc) * ld + j0 + r] : (r == cc ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    double x[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        double acc = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) acc = fma(-Ls[k * 65 + i], x[k], acc);
+        x[i] = (i >= c) ? acc / Ls[i * 65 + i] : 0.0;
+    }
+    double* out = Dinv + (int64_t)blockIdx.x * NB * NB + c * NB;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) out[i] = x[i];
+}
+
+// TRANS == false: L z = b.  TRANS == true: L' u = b (block rows visited from the bottom; blockIdx 0 = last block).
+template <bool TRANS>
+__global__ void __launch_bounds__(TRSV_THREADS) trsv_wavefront_kernel(const double* __restrict__ L, int64_t ld, int D,
+                                                                      const double* __restrict__ Dinv, double* b,
+                                                                      int* flags, int epoch) {
+    __shared__ double xs[NB];
+    __shared__ double part[4][NB];
+    __shared__ double Ts[TRANS ? NB * 65 : 1];
     const int nblk = (D + NB - 1) / NB;
-    for (int jb = nblk - 1; jb >= 0; --jb) {
-        const int j0 = jb * NB;
-        const int nbj = min(NB, D - j0);
-        __syncthreads();
-        // z_c -= Σ_{k >= j0 + 64} L[k, j0 + c] u_k : one warp per column, lanes stride over k (contiguous)
-        for (int c = warp; c < nbj; c += TRSV_THREADS / 32) {
-            const double* col = L + (int64_t)(j0 + c) * ld;
-            double acc = 0.0;
-            for (int k = j0 + NB + lane; k < D; k += 32) acc = fma(col[k], b[k], acc);
-            acc = warp_sum(acc);
-            if (lane == 0) zb[c] = b[j0 + c] - acc;
-        }
-        for (int e = tid; e < NB * NB; e += TRSV_THREADS) {
-            const int r = e % NB, c = e / NB;
-            Ls[c * 65 + r] = (r < nbj && c < nbj && r >= c) ? L[(int64_t)(j0 + c) * ld + j0 + r] : (r == c ? 1.0 : 0.0);
-        }
-        if (tid >= nbj && tid < NB) zb[tid] = 0.0;
-        __syncthreads();
-        if (tid < 32) {  // solve the transposed 64 x 64 block from the bottom up
-            double x0 = zb[tid], x1 = zb[tid + 32];
-            for (int c = NB - 1; c >= 0; --c) {
-                const double src = (c < 32) ? x0 : x1;
-                const double uc = __shfl_sync(0xffffffffu, src, c & 31) / Ls[c * 65 + c];
-                if (tid == (c & 31)) {
-                    if (c < 32) x0 = uc; else x1 = uc;
-                }
-                // row i < c of L': (L')[i, c] = L[c, i]
-                if (tid < c) x0 = fma(-uc, Ls[tid * 65 + c], x0);
-                if (tid + 32 < c) x1 = fma(-uc, Ls[(tid + 32) * 65 + c], x1);
+    const int j = TRANS ? nblk - 1 - (int)blockIdx.x : (int)blockIdx.x;
+    const int j0 = j * NB;
+    const int r = threadIdx.x & 63, q = threadIdx.x >> 6;
+    double acc = 0.0;
+    const int nprev = TRANS ? nblk - 1 - j : j;
+    for (int s = 0; s < nprev; ++s) {
+        const int k = TRANS ? nblk - 1 - s : s;  // blocks become ready in this order
+        const int k0 = k * NB;
+        if (TRANS) {
+            // stage L[k0 + rr, j0 + cc] (coalesced over rr) before waiting: the factor itself is already final
+            for (int e = threadIdx.x; e < NB * NB; e += TRSV_THREADS) {
+                const int rr = e % NB, cc = e / NB;
+                Ts[cc * 65 + rr] = (k0 + rr < D && j0 + cc < D) ? L[(int64_t)(j0 + cc) * ld + k0 + rr] : 0.0;
             }
-            zb[tid] = x0;
-            zb[tid + 32] = x1;
+        }
+        double lv[16];
+        if (!TRANS) {
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                const int c = q * 16 + t;
+                lv[t] = (j0 + r < D && k0 + c < D) ? L[(int64_t)(k0 + c) * ld + j0 + r] : 0.0;
+            }
+        }
+        wait_flag(flags + k, epoch);
+        if (threadIdx.x < NB) xs[threadIdx.x] = (k0 + threadIdx.x < D) ? __ldcg(b + k0 + threadIdx.x) : 0.0;
+        __syncthreads();
+        if (TRANS) {
+            // column r of the staged block: Σ_rr L[k0 + rr, j0 + r] x_k[rr], rows rr split over the 4 phases q
+#pragma unroll
+            for (int t = 0; t < 16; ++t) acc = fma(Ts[r * 65 + q * 16 + t], xs[q * 16 + t], acc);
+        } else {
+#pragma unroll
+            for (int t = 0; t < 16; ++t) acc = fma(lv[t], xs[q * 16 + t], acc);
         }
         __syncthreads();
-        if (tid < nbj) b[j0 + tid] = zb[tid];
+    }
+    part[q][r] = acc;
+    __syncthreads();
+    if (threadIdx.x < NB) {
+        const double rhs = ((j0 + r < D) ? b[j0 + r] : 0.0) - (part[0][r] + part[1][r] + part[2][r] + part[3][r]);
+        xs[r] = rhs;
+    }
+    __syncthreads();
+    if (threadIdx.x < NB) {
+        // x_j = inv(L_jj) rhs   or   inv(L_jj)' rhs
+        const double* Dj = Dinv + (int64_t)j * NB * NB;
+        double v = 0.0;
+        if (TRANS) {
+            for (int c = r; c < NB; ++c) v = fma(Dj[r * NB + c], xs[c], v);  // (inv L)'[r][c] = (inv L)[c][r]
+        } else {
+            for (int c = 0; c <= r; ++c) v = fma(Dj[c * NB + r], xs[c], v);
+        }
+        if (j0 + r < D) b[j0 + r] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicExch(flags + j, epoch);
     }
 }
 
-int trsv_lower_forward(blr_ctx* ctx, const double* L, int64_t D, double* b) {
-    trsv_forward_kernel<<<1, TRSV_THREADS, 0, ctx->stream>>>(L, D, (int)D, b);
-    BLR_CHECK_LAUNCH(ctx, "trsv_forward_kernel");
+static int trsv_wavefront(blr_ctx* ctx, const double* L, int64_t D, const double* Dinv, double* b, bool trans) {
+    const int nblk = (int)((D + NB - 1) / NB);
+    const int epoch = ++ctx->flag_epoch;
+    if (trans)
+        trsv_wavefront_kernel<true><<<nblk, TRSV_THREADS, 0, ctx->stream>>>(L, D, (int)D, Dinv, b, ctx->d_flags, epoch);
+    else
+        trsv_wavefront_kernel<false><<<nblk, TRSV_THREADS, 0, ctx->stream>>>(L, D, (int)D, Dinv, b, ctx->d_flags, epoch);
+    BLR_CHECK_LAUNCH(ctx, "trsv_wavefront_kernel");
     return 0;
 }
-int trsv_lower_backward(blr_ctx* ctx, const double* L, int64_t D, double* b) {
-    trsv_backward_kernel<<<1, TRSV_THREADS, 0, ctx->stream>>>(L, D, (int)D, b);
-    BLR_CHECK_LAUNCH(ctx, "trsv_backward_kernel");
+int trsv_lower_forward(blr_ctx* ctx, const double* L, int64_t D, const double* Dinv, double* b) {
+    return trsv_wavefront(ctx, L, D, Dinv, b, false);
+}
+int trsv_lower_backward(blr_ctx* ctx, const double* L, int64_t D, const double* Dinv, double* b) {
+    return trsv_wavefront(ctx, L, D, Dinv, b, true);
+}
+int trtri_diag_packed(blr_ctx* ctx, const double* L, int64_t D, double* Dinv) {
+    const int nblk = (int)((D + NB - 1) / NB);
+    trtri_diag_packed_kernel<<<nblk, NB, 0, ctx->stream>>>(L, D, (int)D, Dinv);
+    BLR_CHECK_LAUNCH(ctx, "trtri_diag_packed_kernel");
     return 0;
 }
 
@@ -511,11 +555,17 @@ int infer_solve(blr_ctx* ctx, const blr_prior* prior, const blr_stats* st, doubl
     if (rc != 0) return fail(rc);
     // z = L'^-1 r ; z'z ; u = L'^-T z ; m' = mw + u
     BLR_CUDA_OK(ctx, cudaMemcpyAsync(rhs, st->r(), (size_t)D * sizeof(double), cudaMemcpyDeviceToDevice, sm));
-    rc = trsv_lower_forward(ctx, p->L, D, rhs);
+    // inverse diagonal blocks for the wavefront solves
+    const int64_t nblk = (D + NB - 1) / NB;
+    rc = ensure_dinv(ctx, (size_t)nblk * NB * NB * sizeof(double));
+    if (rc != 0) return fail(rc);
+    double* Dinv = ctx->dinv;
+    rc = trtri_diag_packed(ctx, p->L, D, Dinv);
+    if (rc == 0) rc = trsv_lower_forward(ctx, p->L, D, Dinv, rhs);
     if (rc != 0) return fail(rc);
     dot_self_kernel<<<1, 256, 0, sm>>>(rhs, (int)D, sc + 2);
     BLR_CHECK_LAUNCH(ctx, "dot_self_kernel");
-    rc = trsv_lower_backward(ctx, p->L, D, rhs);
+    rc = trsv_lower_backward(ctx, p->L, D, Dinv, rhs);
     if (rc == 0) rc = logdet_from_chol(ctx, p->L, D, sc + 1);
     if (rc != 0) return fail(rc);
     finalize_kernel<<<(int)std::min<int64_t>((D + 255) / 256, 64), 256, 0, sm>>>(st->scal(), sc, mwd, rhs, (int)D, p->mw,

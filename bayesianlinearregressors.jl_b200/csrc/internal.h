@@ -49,9 +49,13 @@ struct blr_ctx {
     size_t ws_bytes = 0;
     double* nbuf = nullptr;  // per-observation scratch (s, t = sδ), 2 * npad doubles
     size_t nbuf_bytes = 0;
+    double* dinv = nullptr;  // packed inverse diagonal blocks for the wavefront solves
+    size_t dinv_bytes = 0;
     double* small = nullptr;  // small device scratch (scalars, block partial sums)
     size_t small_bytes = 0;
     int* d_info = nullptr;
+    int* d_flags = nullptr;  // wavefront-solve ready flags (one per 64-row block), compared against flag_epoch
+    int flag_epoch = 0;
     cudaEvent_t ev[8] = {};
     bool ev_valid[4] = {};
     // stream-K schedule of the Gram fast path (cached by shape)
@@ -88,6 +92,7 @@ cudaError_t dev_alloc(blr_ctx* ctx, double** p, size_t bytes);
 void dev_free(cudaStream_t stream, void* p);
 int ensure_ws(blr_ctx* ctx, size_t bytes);
 int ensure_nbuf(blr_ctx* ctx, size_t bytes);
+int ensure_dinv(blr_ctx* ctx, size_t bytes);
 
 #define BLR_CUDA_OK(ctx, call)                                           \
     do {                                                                 \
@@ -118,8 +123,9 @@ int potrf_lower(blr_ctx* ctx, double* A, int64_t D, int* info_dev);
 // W = inv(L) (lower triangular, column-major), strictly-upper part zeroed.
 int trtri_lower(blr_ctx* ctx, const double* L, double* W, int64_t D);
 // Solve L z = b (forward) then optionally L' u = z (backward); b overwritten.  zz_out (device) = z'z.
-int trsv_lower_forward(blr_ctx* ctx, const double* L, int64_t D, double* b);
-int trsv_lower_backward(blr_ctx* ctx, const double* L, int64_t D, double* b);
+int trtri_diag_packed(blr_ctx* ctx, const double* L, int64_t D, double* Dinv);
+int trsv_lower_forward(blr_ctx* ctx, const double* L, int64_t D, const double* Dinv, double* b);
+int trsv_lower_backward(blr_ctx* ctx, const double* L, int64_t D, const double* Dinv, double* b);
 // out[0] = 2 * sum log diag(L)
 int logdet_from_chol(blr_ctx* ctx, const double* L, int64_t D, double* out_dev);
 int infer_solve(blr_ctx* ctx, const blr_prior* prior, const blr_stats* st, double* logpdf_out, double* m_post,

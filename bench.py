@@ -156,8 +156,18 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        ctx.init_comm_from_torch()
+        # NCCL prints its version banner on stdout at communicator creation: keep stdout to the ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            ctx.init_comm_from_torch()
+            dist.barrier()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     N, D = args.n_obs, args.dim
     lo, hi = blr.ShardPlan(N, world).bounds(rank)

@@ -110,6 +110,7 @@ INFER_CASES = [
     (7, 13, True, False, False),
     (33, 257, True, False, True),
     (64, 500, True, False, False),
+    (70, 400, True, False, False),
     (100, 999, False, False, False),
     (130, 515, True, False, False),
     (200, 3000, True, False, False),

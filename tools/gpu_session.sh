@@ -49,6 +49,12 @@ print(json.dumps(c.calibrate()))
           echo "bench_multi n=$n exit $?"; tail -c 1200 "$OUT/bench_g$n.json"; tail -3 "$OUT/bench_g$n.err"
         fi
       done;;
+    solve_timing)
+      for cfg in "--n-obs 1048576 --dim 256" "--n-obs 1048576 --dim 1024" "--n-obs 262144 --dim 4096"; do
+        echo "cfg=$cfg"
+        timeout 600 python bench.py $cfg --steps 5 --warmup 3 --no-cpu --no-e2e --no-calibrate 2>> "$OUT/solve.err" \
+          | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('ms_per_step', d['ms_per_step'], 'gram', d['roofline']['kernel_ms'], 'solve', d['roofline']['solve_ms'], 'TF', d['roofline']['achieved'])"
+      done 2>&1 | tee "$OUT/solve_timing.log";;
     dmma_probe)
       timeout 300 python -c "
 import blr_b200 as b, ctypes as C
