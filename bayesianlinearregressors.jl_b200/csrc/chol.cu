@@ -419,6 +419,7 @@ void post_release(blr_post* p) {
     dev_free(p->stream, p->L);
     dev_free(p->stream, p->W);
     dev_free(p->stream, p->Lam);
+    dev_free(p->stream, p->Wp);
     delete p;
 }
 

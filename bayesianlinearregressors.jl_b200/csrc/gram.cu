@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restri
     const int tsz = TS * TS;
     const int s0 = tile_slot_begin ? tile_slot_begin[blockIdx.x] : blockIdx.x * nsplit;
     const int s1 = tile_slot_begin ? tile_slot_begin[blockIdx.x + 1] : (blockIdx.x + 1) * nsplit;
-    for (int e = threadIdx.x; e < tsz; e += blockDim.x) {
+    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < tsz; e += blockDim.x * gridDim.y) {
         const int row = e / TS, col = e % TS;
         const int gi = ti * TS + row, gj = tj * TS + col;
         // diagonal tiles of the fast path only hold sub-tiles whose 8-row block is not above their 8-col block
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restri
             if (gi != gj) G[(int64_t)gi * D + gj] = nv;
         }
     }
-    if (ti == tj) {
+    if (ti == tj && blockIdx.y == 0) {
         for (int m = threadIdx.x; m < TS; m += blockDim.x) {
             const int gi = ti * TS + m;
             if (gi < D) {
@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restri
             }
         }
     }
-    if (blockIdx.x == 0) {
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
         double q = 0.0, l = 0.0;
         for (int b = threadIdx.x; b < prep_blocks; b += blockDim.x) {
             q += prep_partial[2 * b];
@@ -536,7 +536,9 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
         gram_tma_kernel<<<G, gk::THREADS, sizeof(gk::Smem), sm>>>(gp);
         BLR_CHECK_LAUNCH(ctx, "gram_tma_kernel");
         BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], sm));
-        gram_reduce_kernel<<<T, 256, 0, sm>>>(gp.P, gp.Pr, TS, tile_slot_begin, 0, D, st->G(), st->r(), st->scal(),
+        // the slot sum of one tile is spread over several CTAs (few tiles at small D, many slots per tile)
+        const int ysplit = std::max(1, std::min(16, (2 * G) / T));
+        gram_reduce_kernel<<<dim3(T, ysplit), 256, 0, sm>>>(gp.P, gp.Pr, TS, tile_slot_begin, 0, D, st->G(), st->r(), st->scal(),
                                               prep_partial, prep_blocks, (double)N);
         BLR_CHECK_LAUNCH(ctx, "gram_reduce_kernel");
     } else {

@@ -34,6 +34,7 @@ struct blr_post {
     double* L = nullptr;     // D x D lower Cholesky factor of Λw (Λw = L L'), column-major; upper part zero
     double* W = nullptr;     // D x D lower, W = inv(L); built lazily for var / rand
     double* Lam = nullptr;   // D x D precision (kept for download)
+    double* Wp = nullptr;    // zero-padded copy of W (+ padded mw) in the layout of the TMA predict kernels
     bool has_W = false;
     cudaStream_t stream = nullptr;  // stream the buffers were allocated on (stream-ordered pool)
 };
@@ -142,6 +143,14 @@ int sample_weights(blr_ctx* ctx, blr_post* p, int64_t S, const double* Z_dev, do
 int sample_finite(blr_ctx* ctx, const blr_x* x, const double* Wsamp_dev, int64_t S, const double* sigma2,
                   double sigma2_scalar, const double* Zy_dev, uint64_t seed, double* Y_dev);
 int apply_weights(blr_ctx* ctx, const blr_x* x, const double* w_dev, double* out_dev);
+
+// ---- predict_tma.cu
+bool predict_fast_eligible(const blr_post* p, const blr_x* x);
+bool sample_fast_eligible(const blr_x* x);
+int sample_finite_fast(blr_ctx* ctx, const blr_x* x, const double* Wsamp_dev, int64_t S, const double* sigma2,
+                       double sigma2_scalar, const double* Zy_dev, uint64_t seed, double* Y_dev);
+int predict_mean_var_fast(blr_ctx* ctx, blr_post* p, const blr_x* x, const double* sigma2, double sigma2_scalar,
+                          double* mean_dev, double* var_dev);
 
 // ---- synth.cu
 int synth_normal(blr_ctx* ctx, double* out, int64_t rows, int64_t cols, int64_t ld, uint64_t seed, uint64_t stream_id,

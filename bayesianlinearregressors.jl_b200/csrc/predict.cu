@@ -121,6 +121,8 @@ __global__ void __launch_bounds__(bg::THREADS) var_kernel(const double* __restri
 int predict_mean_var(blr_ctx* ctx, blr_post* p, const blr_x* x, const double* sigma2, double sigma2_scalar,
                      double* mean_dev, double* var_dev) {
     if (x->N == 0) return 0;
+    if (var_dev && predict_fast_eligible(p, x))
+        return predict_mean_var_fast(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
     if (mean_dev) BLR_TRY(apply_weights(ctx, x, p->mw, mean_dev));
     if (var_dev) {
         BLR_TRY(post_ensure_W(ctx, p));
@@ -236,7 +238,8 @@ int sample_weights(blr_ctx* ctx, blr_post* p, int64_t S, const double* Z_dev, do
     return 0;
 }
 
-// Y[n, s] += sqrt(σ²_n) * z,  z = Zy[n, s] when supplied, else Philox normal (stream 7, element n + s * n_total)
+// Y[n, s] += sqrt(σ²_n) * z,  z = Zy[n, s] when supplied, else Philox normal: stream 7, pair index n + (s / 2) * N,
+// first / second member of the pair for even / odd s (same indexing as the fused epilogue of rand_tma_kernel)
 __global__ void add_obs_noise_kernel(double* __restrict__ Y, int64_t N, int64_t S, const double* __restrict__ sigma2,
                                      double sigma2_scalar, const double* __restrict__ Zy, uint64_t seed) {
     const int64_t total = N * S;
@@ -247,9 +250,10 @@ __global__ void add_obs_noise_kernel(double* __restrict__ Y, int64_t N, int64_t 
         if (Zy) {
             z = Zy[e];
         } else {
+            const int64_t sidx = e / N;
             double z0, z1;
-            philox_normal_pair(seed, 7, (uint64_t)e, z0, z1);
-            z = z0;
+            philox_normal_pair(seed, 7, (uint64_t)n + (uint64_t)(sidx >> 1) * (uint64_t)N, z0, z1);
+            z = (sidx & 1) ? z1 : z0;
         }
         Y[e] = fma(sd, z, Y[e]);
     }
@@ -259,6 +263,7 @@ int sample_finite(blr_ctx* ctx, const blr_x* x, const double* Wsamp_dev, int64_t
                   double sigma2_scalar, const double* Zy_dev, uint64_t seed, double* Y_dev) {
     const int64_t N = x->N, D = x->D;
     if (N == 0 || S == 0) return 0;
+    if (sample_fast_eligible(x)) return sample_finite_fast(ctx, x, Wsamp_dev, S, sigma2, sigma2_scalar, Zy_dev, seed, Y_dev);
     const bool colv = x->layout == BLR_COLVECS;
     // Y (N x S) = X' Wsamp : A[m = n, k = d] = X[d, n]
     BLR_TRY(gemm_generic(ctx, N, S, D, x->p, colv ? x->ld : 1, colv ? 1 : x->ld, Wsamp_dev, 1, D, Y_dev, 1, N, 0.0));

@@ -1,0 +1,493 @@
+// K6 fast path: marginal means and variances for ColVecs test points at throughput scale
+//
+//     mean_n = x_n' mw            var_n = |W x_n|² + σ²_n ,   W = inv(L),  Λw = L L'
+//
+// (reference src/bayesian_linear_regression.jl:33 and :40-43: `α = Uw' \ X; sum(abs2, α; dims=1) .+ diag(Σy)`;
+// the reference materialises the D x N matrix α, here α never leaves the SM).
+//
+// Shape of the computation: α = W X is a triangular GEMM with M = D rows, N = points, K = D.  One persistent CTA
+// per SM owns tiles of 32 points and keeps α (up to 512 rows x 32 points = 128 KB) in registers as DMMA.8x8x4
+// accumulators: 8 consumer warps, warp tile 64 rows x 32 points.  The K dimension is streamed in stages of 16:
+//   A operand = 16 columns of W (rows >= the stage's first non-zero row), [k][row] in shared memory,
+//   B operand = 16 features of the 32 points, [point][k] in shared memory,
+// both filled by TMA bulk copies from a producer warp through a 3-stage mbarrier ring.  X is read from HBM exactly
+// once; W (2 MB at D = 512) streams from L2.
+// Triangular balance: warp w owns the 8-row blocks {w, w + 8, w + 16, ...}, so every warp loses sub-tiles at the
+// same rate as k advances; which sub-tile rows are live is a compile-time template parameter (run-time predication
+// of mma.sync serialises the tensor pipe, see gram.cu).
+// D > 512 is handled in row passes of 512 rows (the point tile is re-streamed per pass).
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "internal.h"
+#include "philox.cuh"
+
+namespace blr {
+namespace vk {
+constexpr int NP = 32;          // points per tile
+constexpr int KT = 16;          // features per stage
+constexpr int STAGES = 3;
+constexpr int LDB = KT + 4;     // B row stride (doubles): == 4 mod 16
+constexpr int CONSUMER_WARPS = 8;
+constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+template <int MI>
+struct Cfg {
+    static constexpr int R = MI * 64;      // rows of α per pass
+    static constexpr int LDA = R + 4;      // A row stride (doubles): == 4 mod 16
+    struct __align__(16) Stage {
+        double a[KT * LDA];   // [k][row - r_base]
+        double b[NP * LDB];   // [point][k]
+        double mw[KT];
+    };
+    struct Smem {
+        Stage st[STAGES];
+        double red[CONSUMER_WARPS][NP];
+        double mred[CONSUMER_WARPS][NP];
+        unsigned long long full[STAGES];
+        unsigned long long empty[STAGES];
+    };
+};
+}  // namespace vk
+
+struct VarParams {
+    const double* Wp;   // padded inverse factor: ldw x dk, column-major, zeros outside the lower triangle / beyond D
+    int64_t ldw;        // multiple of R
+    int D;
+    const double* X;    // ColVecs
+    int64_t ld;
+    int64_t N;
+    const double* mwp;  // prior mean padded with zeros to a multiple of KT
+    const double* sigma2;
+    double sigma2_scalar;
+    double* mean;       // may be null
+    double* var;        // may be null
+};
+
+// one stage for one consumer warp; sub-tile rows mi >= M0 are live
+template <int MI, int M0>
+__device__ __forceinline__ void var_consume(double (&acc)[MI][4][2], const double* __restrict__ As,
+                                            const double* __restrict__ Bs, int warp, int g, int kq) {
+    using C = vk::Cfg<MI>;
+    const double* Ap = As + warp * 8 + g;
+    const double* Bp = Bs + g * vk::LDB;
+#pragma unroll
+    for (int kk = 0; kk < vk::KT / 4; ++kk) {
+        const int kl = kk * 4 + kq;
+        double a[MI], b[4];
+#pragma unroll
+        for (int mi = M0; mi < MI; ++mi) a[mi] = Ap[kl * C::LDA + mi * 64];
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) b[ni] = Bp[ni * 8 * vk::LDB + kl];
+#pragma unroll
+        for (int mi = M0; mi < MI; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
+    }
+}
+
+template <int MI>
+__device__ __forceinline__ void var_consume_dispatch(double (&acc)[MI][4][2], const double* As, const double* Bs,
+                                                     int warp, int g, int kq, int m0) {
+    if (m0 <= 0) var_consume<MI, 0>(acc, As, Bs, warp, g, kq);
+    else if (m0 == 1) var_consume<MI, (1 < MI ? 1 : MI)>(acc, As, Bs, warp, g, kq);
+    else if (m0 == 2) var_consume<MI, (2 < MI ? 2 : MI)>(acc, As, Bs, warp, g, kq);
+    else if (m0 == 3) var_consume<MI, (3 < MI ? 3 : MI)>(acc, As, Bs, warp, g, kq);
+    else if (m0 == 4) var_consume<MI, (4 < MI ? 4 : MI)>(acc, As, Bs, warp, g, kq);
+    else if (m0 == 5) var_consume<MI, (5 < MI ? 5 : MI)>(acc, As, Bs, warp, g, kq);
+    else if (m0 == 6) var_consume<MI, (6 < MI ? 6 : MI)>(acc, As, Bs, warp, g, kq);
+    else if (m0 == 7) var_consume<MI, (7 < MI ? 7 : MI)>(acc, As, Bs, warp, g, kq);
+    // m0 >= MI: nothing live for this warp in this stage
+}
+
+template <int MI>
+__global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams p) {
+    using namespace vk;
+    using C = Cfg<MI>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    typename C::Smem& sm = *reinterpret_cast<typename C::Smem*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    {
+        double* z = reinterpret_cast<double*>(sm.st);
+        const int nz = (int)(sizeof(typename C::Stage) * STAGES / sizeof(double));
+        for (int i = tid; i < nz; i += THREADS) z[i] = 0.0;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(smem_u32(&sm.full[i]), 1);
+            mbar_init(smem_u32(&sm.empty[i]), CONSUMER_WARPS);
+        }
+        mbar_fence_init();
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    const int64_t ntiles = (p.N + NP - 1) / NP;
+    const int npass = (int)(p.ldw / C::R);
+
+    if (warp == CONSUMER_WARPS) {
+        // ------------------------------------------------------------ producer warp (TMA)
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t p0 = tile * NP;
+            const int npts = (int)min((int64_t)NP, p.N - p0);
+            for (int ps = 0; ps < npass; ++ps) {
+                const int r_base = ps * C::R;
+                const int kmax = min(p.D, r_base + C::R);  // W[row][k] = 0 for k > row
+                for (int k0 = 0; k0 < kmax; k0 += KT, ++it) {
+                    const int stg = it % STAGES;
+                    const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                    mbar_wait(smem_u32(&sm.empty[stg]), ph ^ 1u);
+                    typename C::Stage& S = sm.st[stg];
+                    const uint32_t bar = smem_u32(&sm.full[stg]);
+                    const int r_lo = max(r_base, (k0 / 64) * 64);     // first row that can be non-zero in this stage
+                    const int rows = r_base + C::R - r_lo;
+                    const int kc = min(KT, p.D - k0);                 // features present (D even => kc even)
+                    if (lane == 0) {
+                        const uint32_t bytes = (uint32_t)KT * rows * 8u + (uint32_t)npts * kc * 8u + (ps == npass - 1 ? KT * 8u : 0u);
+                        mbar_arrive_expect_tx(bar, bytes);
+                    }
+                    __syncwarp();
+                    if (lane < KT)
+                        bulk_g2s(smem_u32(&S.a[lane * C::LDA + (r_lo - r_base)]), p.Wp + (int64_t)(k0 + lane) * p.ldw + r_lo,
+                                 (uint32_t)rows * 8u, bar);
+                    if (lane < npts)
+                        bulk_g2s(smem_u32(&S.b[lane * LDB]), p.X + (p0 + lane) * p.ld + k0, (uint32_t)kc * 8u, bar);
+                    if (lane == 0 && ps == npass - 1) bulk_g2s(smem_u32(S.mw), p.mwp + k0, KT * 8u, bar);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------- consumer warps (DMMA)
+    const int g = lane >> 2, kq = lane & 3;
+    const int mp = tid & 31, mk = tid >> 5;  // mean: point, k-slice (2 features per stage per thread)
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t p0 = tile * NP;
+        double macc = 0.0;
+        for (int ps = 0; ps < npass; ++ps) {
+            const int r_base = ps * C::R;
+            const int kmax = min(p.D, r_base + C::R);
+            double acc[MI][4][2];
+#pragma unroll
+            for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            for (int k0 = 0; k0 < kmax; k0 += KT, ++it) {
+                const int stg = it % STAGES;
+                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                mbar_wait(smem_u32(&sm.full[stg]), ph);
+                const typename C::Stage& S = sm.st[stg];
+                // row block (mi * 8 + warp) of this pass holds rows r_base + (mi*8 + warp)*8 .. +7; live iff last row >= k0
+                const int num = k0 - 7 - r_base - 8 * warp;
+                const int m0 = num <= 0 ? 0 : (num + 63) / 64;
+                var_consume_dispatch<MI>(acc, S.a, S.b, warp, g, kq, m0);
+                if (ps == npass - 1) {  // the last row pass streams every feature k < D
+                    macc = fma(S.mw[2 * mk], S.b[mp * LDB + 2 * mk], macc);
+                    macc = fma(S.mw[2 * mk + 1], S.b[mp * LDB + 2 * mk + 1], macc);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&sm.empty[stg]));
+            }
+            // fold this pass: squares over the warp's rows (registers, then the 8 fragment rows by shuffle) into the
+            // warp's per-point slots in shared memory (each slot has a single owner lane: no synchronisation needed)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int mi = 0; mi < MI; ++mi) v = fma(acc[mi][ni][c], acc[mi][ni][c], v);
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    if (g == 0) {
+                        double* slot = &sm.red[warp][ni * 8 + kq * 2 + c];
+                        *slot = (ps == 0) ? v : *slot + v;
+                    }
+                }
+        }
+        sm.mred[mk][mp] = macc;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tid < NP && p0 + tid < p.N) {
+            const int64_t n = p0 + tid;
+            if (p.var) {
+                double v = 0.0;
+#pragma unroll
+                for (int w = 0; w < CONSUMER_WARPS; ++w) v += sm.red[w][tid];
+                p.var[n] = v + (p.sigma2 ? p.sigma2[n] : p.sigma2_scalar);
+            }
+            if (p.mean) {
+                double m = 0.0;
+#pragma unroll
+                for (int w = 0; w < CONSUMER_WARPS; ++w) m += sm.mred[w][tid];
+                p.mean[n] = m;
+            }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // slots are rewritten by the next tile
+    }
+}
+
+// Wp (ldw x dk) = zero-padded copy of the lower-triangular W (D x D, ld = D); mwp = zero-padded mw
+__global__ void pad_inverse_factor_kernel(const double* __restrict__ W, int D, double* __restrict__ Wp, int64_t ldw, int dk,
+                                          const double* __restrict__ mw, double* __restrict__ mwp) {
+    const int64_t total = ldw * dk;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(e % ldw), c = (int)(e / ldw);
+        Wp[e] = (r < D && c < D && r >= c) ? W[(int64_t)c * D + r] : 0.0;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dk; i += gridDim.x * blockDim.x) mwp[i] = (i < D) ? mw[i] : 0.0;
+}
+
+template <int MI>
+static int launch_var_tma(blr_ctx* ctx, const VarParams& vp) {
+    using C = vk::Cfg<MI>;
+    const int smem = (int)sizeof(typename C::Smem);
+    BLR_CUDA_OK(ctx, cudaFuncSetAttribute(var_tma_kernel<MI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int64_t ntiles = (vp.N + vk::NP - 1) / vk::NP;
+    const int grid = (int)std::min<int64_t>(ntiles, ctx->sm_count);
+    var_tma_kernel<MI><<<grid, vk::THREADS, smem, ctx->stream>>>(vp);
+    BLR_CHECK_LAUNCH(ctx, "var_tma_kernel");
+    return 0;
+}
+
+bool predict_fast_eligible(const blr_post* p, const blr_x* x) {
+    return x->layout == BLR_COLVECS && p->D >= 128 && (p->D % 2) == 0 && (x->ld % 2) == 0 &&
+           (reinterpret_cast<uintptr_t>(x->p) & 15) == 0 && x->N >= 32;
+}
+
+int predict_mean_var_fast(blr_ctx* ctx, blr_post* p, const blr_x* x, const double* sigma2, double sigma2_scalar,
+                          double* mean_dev, double* var_dev) {
+    const int D = (int)p->D;
+    const int MI = (D <= 256) ? 4 : 8;
+    const int R = MI * 64;
+    const int64_t ldw = ((D + R - 1) / R) * (int64_t)R;
+    const int dk = ((D + vk::KT - 1) / vk::KT) * vk::KT;
+    if (!p->Wp) {
+        BLR_TRY(post_ensure_W(ctx, p));
+        BLR_CUDA_OK(ctx, dev_alloc(ctx, &p->Wp, (size_t)(ldw * dk + dk) * sizeof(double)));
+        pad_inverse_factor_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(p->W, D, p->Wp, ldw, dk, p->mw, p->Wp + ldw * dk);
+        BLR_CHECK_LAUNCH(ctx, "pad_inverse_factor_kernel");
+    }
+    VarParams vp;
+    vp.Wp = p->Wp;
+    vp.ldw = ldw;
+    vp.D = D;
+    vp.X = x->p;
+    vp.ld = x->ld;
+    vp.N = x->N;
+    vp.mwp = p->Wp + ldw * dk;
+    vp.sigma2 = sigma2;
+    vp.sigma2_scalar = sigma2_scalar;
+    vp.mean = mean_dev;
+    vp.var = var_dev;
+    return (MI == 4) ? launch_var_tma<4>(ctx, vp) : launch_var_tma<8>(ctx, vp);
+}
+
+
+// ====================================================================================================
+// K7 fast path: Y (N x S) = X' Wsamp + sqrt(σ²) .* Z      (reference src/bayesian_linear_regression.jl:52)
+//
+// GEMM with M = points, N = samples, K = D.  One persistent CTA per SM owns tiles of 128 points x 64 samples
+// (8 warps as 4 x 2, warp tile 32 x 32 on DMMA.8x8x4); X is streamed once per 64-sample block through a TMA
+// bulk-copy ring ([point][k] rows of 32 features), the sample weights come pre-transposed ([k][sample], 512-byte
+// rows) from L2.  The noise term is fused into the epilogue: Z supplied (parity mode) or Philox on the fly.
+namespace rk {
+constexpr int TP = 128;         // points per tile
+constexpr int TS = 64;          // samples per block
+constexpr int KT = 32;          // features per stage
+constexpr int STAGES = 4;
+constexpr int LDA = KT + 4;     // [point][k]
+constexpr int LDB = TS + 4;     // [k][sample]
+constexpr int CONSUMER_WARPS = 8;
+constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+struct __align__(16) Stage {
+    double a[TP * LDA];
+    double b[KT * LDB];
+};
+struct Smem {
+    Stage st[STAGES];
+    unsigned long long full[STAGES];
+    unsigned long long empty[STAGES];
+};
+}  // namespace rk
+
+struct RandParams {
+    const double* X;
+    int64_t ld;
+    int D;
+    int64_t N;
+    const double* Wt;   // [nsb][dk][64]: transposed, zero-padded sample weights
+    int dk;             // D rounded up to KT
+    int S;
+    const double* sigma2;
+    double sigma2_scalar;
+    const double* Zy;   // N x S column-major, or null
+    uint64_t seed;
+    double* Y;          // N x S column-major
+};
+
+__global__ void __launch_bounds__(rk::THREADS, 1) rand_tma_kernel(const RandParams p) {
+    using namespace rk;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    {
+        double* z = reinterpret_cast<double*>(sm.st);
+        const int nz = (int)(sizeof(Stage) * STAGES / sizeof(double));
+        for (int i = tid; i < nz; i += THREADS) z[i] = 0.0;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(smem_u32(&sm.full[i]), 1);
+            mbar_init(smem_u32(&sm.empty[i]), CONSUMER_WARPS);
+        }
+        mbar_fence_init();
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    const int64_t ntiles = (p.N + TP - 1) / TP;
+    const int nsb = (p.S + TS - 1) / TS;
+
+    if (warp == CONSUMER_WARPS) {
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t p0 = tile * TP;
+            const int npts = (int)min((int64_t)TP, p.N - p0);
+            for (int sb = 0; sb < nsb; ++sb) {
+                const double* Wsb = p.Wt + (int64_t)sb * p.dk * TS;
+                for (int k0 = 0; k0 < p.D; k0 += KT, ++it) {
+                    const int stg = it % STAGES;
+                    const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                    mbar_wait(smem_u32(&sm.empty[stg]), ph ^ 1u);
+                    Stage& S = sm.st[stg];
+                    const uint32_t bar = smem_u32(&sm.full[stg]);
+                    const int kc = min(KT, p.D - k0);
+                    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)npts * kc * 8u + (uint32_t)KT * TS * 8u);
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < TP / 32; ++q) {
+                        const int pt = q * 32 + lane;
+                        if (pt < npts) bulk_g2s(smem_u32(&S.a[pt * LDA]), p.X + (p0 + pt) * p.ld + k0, (uint32_t)kc * 8u, bar);
+                    }
+                    bulk_g2s(smem_u32(&S.b[lane * LDB]), Wsb + (int64_t)(k0 + lane) * TS, TS * 8u, bar);
+                }
+            }
+        }
+        return;
+    }
+
+    const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, kq = lane & 3;
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t p0 = tile * TP;
+        for (int sb = 0; sb < nsb; ++sb) {
+            double acc[4][4][2];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            for (int k0 = 0; k0 < p.D; k0 += KT, ++it) {
+                const int stg = it % STAGES;
+                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                mbar_wait(smem_u32(&sm.full[stg]), ph);
+                const Stage& S = sm.st[stg];
+                const double* Ap = S.a + (wm * 32 + g) * LDA;
+                const double* Bp = S.b + wn * 32 + g;
+#pragma unroll
+                for (int kk = 0; kk < KT / 4; ++kk) {
+                    const int kl = kk * 4 + kq;
+                    double a[4], b[4];
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) a[mi] = Ap[mi * 8 * LDA + kl];
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) b[ni] = Bp[kl * LDB + ni * 8];
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&sm.empty[stg]));
+            }
+            // epilogue: add the observation noise and store (column-major N x S)
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const int64_t n = p0 + wm * 32 + mi * 8 + g;
+                if (n < p.N) {
+                    const double sd = sqrt(p.sigma2 ? p.sigma2[n] : p.sigma2_scalar);
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) {
+                        const int s0 = sb * TS + wn * 32 + ni * 8 + kq * 2;  // even
+                        if (s0 < p.S) {
+                            double z0, z1;
+                            if (p.Zy) {
+                                z0 = p.Zy[(int64_t)s0 * p.N + n];
+                                z1 = (s0 + 1 < p.S) ? p.Zy[(int64_t)(s0 + 1) * p.N + n] : 0.0;
+                            } else {
+                                philox_normal_pair(p.seed, 7, (uint64_t)n + (uint64_t)(s0 >> 1) * (uint64_t)p.N, z0, z1);
+                            }
+                            p.Y[(int64_t)s0 * p.N + n] = fma(sd, z0, acc[mi][ni][0]);
+                            if (s0 + 1 < p.S) p.Y[(int64_t)(s0 + 1) * p.N + n] = fma(sd, z1, acc[mi][ni][1]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Wt[sb][k][j] = Wsamp[k, sb*64 + j]  (zero beyond D / S)
+__global__ void transpose_samples_kernel(const double* __restrict__ Wsamp, int D, int S, double* __restrict__ Wt, int dk,
+                                         int nsb) {
+    const int64_t total = (int64_t)nsb * dk * rk::TS;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(e % rk::TS);
+        const int k = (int)((e / rk::TS) % dk);
+        const int sb = (int)(e / ((int64_t)rk::TS * dk));
+        const int s = sb * rk::TS + j;
+        Wt[e] = (k < D && s < S) ? Wsamp[(int64_t)s * D + k] : 0.0;
+    }
+}
+
+bool sample_fast_eligible(const blr_x* x) {
+    return x->layout == BLR_COLVECS && x->D >= 64 && (x->D % 2) == 0 && (x->ld % 2) == 0 &&
+           (reinterpret_cast<uintptr_t>(x->p) & 15) == 0 && x->N >= 128;
+}
+
+int sample_finite_fast(blr_ctx* ctx, const blr_x* x, const double* Wsamp_dev, int64_t S, const double* sigma2,
+                       double sigma2_scalar, const double* Zy_dev, uint64_t seed, double* Y_dev) {
+    const int D = (int)x->D;
+    const int dk = ((D + rk::KT - 1) / rk::KT) * rk::KT;
+    const int nsb = (int)((S + rk::TS - 1) / rk::TS);
+    double* Wt = nullptr;
+    BLR_CUDA_OK(ctx, dev_alloc(ctx, &Wt, (size_t)nsb * dk * rk::TS * sizeof(double)));
+    transpose_samples_kernel<<<std::min(ctx->sm_count * 4, nsb * dk), 256, 0, ctx->stream>>>(Wsamp_dev, D, (int)S, Wt, dk, nsb);
+    BLR_CHECK_LAUNCH(ctx, "transpose_samples_kernel");
+    RandParams rp;
+    rp.X = x->p;
+    rp.ld = x->ld;
+    rp.D = D;
+    rp.N = x->N;
+    rp.Wt = Wt;
+    rp.dk = dk;
+    rp.S = (int)S;
+    rp.sigma2 = sigma2;
+    rp.sigma2_scalar = sigma2_scalar;
+    rp.Zy = Zy_dev;
+    rp.seed = seed;
+    rp.Y = Y_dev;
+    BLR_CUDA_OK(ctx, cudaFuncSetAttribute(rand_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(rk::Smem)));
+    const int64_t ntiles = (x->N + rk::TP - 1) / rk::TP;
+    rand_tma_kernel<<<(int)std::min<int64_t>(ntiles, ctx->sm_count), rk::THREADS, sizeof(rk::Smem), ctx->stream>>>(rp);
+    BLR_CHECK_LAUNCH(ctx, "rand_tma_kernel");
+    dev_free(ctx->stream, Wt);
+    return 0;
+}
+
+}  // namespace blr

@@ -189,7 +189,8 @@ def test_posterior_low_noise():
 
 
 # ------------------------------------------------------------------------------------------------ prediction / sampling
-PRED_CASES = [(2, 1000, False), (7, 13, True), (64, 300, True), (130, 515, True), (256, 2000, True), (512, 1111, True)]
+PRED_CASES = [(2, 1000, False), (7, 13, True), (64, 300, True), (130, 515, True), (256, 2000, True), (512, 1111, True),
+              (768, 700, True), (1024, 333, True), (128, 31, True)]
 
 
 @pytest.mark.parametrize("D,N,dense", PRED_CASES)
@@ -202,7 +203,8 @@ def test_mean_var_cov_match_oracle(D, N, dense, Tx):
     m, v = blr.mean_and_var(fx)
     mo, vo = ref.mean_and_var(fxo)
     assert relerr(m, mo) < RTOL and relerr(v, vo) < RTOL
-    assert np.array_equal(blr.mean(fx), m) and np.array_equal(blr.var(fx), v)
+    # mean alone runs the streaming GEMV kernel, mean_and_var the fused one: same numbers up to summation order
+    assert relerr(blr.mean(fx), m) < 1e-13 and np.array_equal(blr.var(fx), v)
     mm, ss = blr.marginals(fx)
     assert relerr(ss, np.sqrt(vo)) < RTOL
     if N <= 600:
@@ -211,7 +213,8 @@ def test_mean_var_cov_match_oracle(D, N, dense, Tx):
         assert relerr(np.diag(Cg), v) < 1e-12
 
 
-@pytest.mark.parametrize("D,N,S", [(2, 10, 5), (7, 13, 1), (64, 300, 8), (200, 1000, 64), (256, 513, 3)])
+@pytest.mark.parametrize("D,N,S", [(2, 10, 5), (7, 13, 1), (64, 300, 8), (200, 1000, 64), (256, 513, 3), (512, 2000, 70),
+                                   (130, 129, 65)])
 def test_rand_matches_oracle_with_same_draws(D, N, S):
     X, mw, Λ, σ2, _ = problem(D, N, seed=17 * D + S)
     f, fo = both_priors(mw, Λ, D)

@@ -55,6 +55,8 @@ print(json.dumps(c.calibrate()))
         timeout 600 python bench.py $cfg --steps 5 --warmup 3 --no-cpu --no-e2e --no-calibrate 2>> "$OUT/solve.err" \
           | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('ms_per_step', d['ms_per_step'], 'gram', d['roofline']['kernel_ms'], 'solve', d['roofline']['solve_ms'], 'TF', d['roofline']['achieved'])"
       done 2>&1 | tee "$OUT/solve_timing.log";;
+    configs)
+      timeout 1200 python tools/bench_configs.py > "$OUT/configs.jsonl" 2> "$OUT/configs.err"; echo "configs exit $?"; cat "$OUT/configs.jsonl"; tail -5 "$OUT/configs.err";;
     dmma_probe)
       timeout 300 python -c "
 import blr_b200 as b, ctypes as C
