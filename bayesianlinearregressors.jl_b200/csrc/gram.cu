@@ -99,7 +99,8 @@ constexpr int KT = 16;                    // observations per pipeline stage
 constexpr int LDT = TM + 4;               // padded smem row: stride == 4 (mod 16) doubles -> conflict-free LDS.64
 constexpr int STAGES = 4;
 constexpr int CONSUMER_WARPS = 8;         // 2 (m) x 4 (n) warps, warp tile 64 x 32
-constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+constexpr int PRODUCER_WARPS = 2;         // bulk copies are uniform-datapath ops (one lane at a time): panel I | panel J
+constexpr int THREADS = (CONSUMER_WARPS + PRODUCER_WARPS) * 32;
 constexpr int W_OFF = 64;                 // schedule weight of one stage of an off-diagonal tile
 struct __align__(16) Stage {
     double a[KT * LDT];  // panel I rows  [k][m]
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(gk::THREADS, 1) gram_tma_kernel(const GramPara
     }
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) {
-            mbar_init(smem_u32(&sm.full[i]), 1);
+            mbar_init(smem_u32(&sm.full[i]), PRODUCER_WARPS);
             mbar_init(smem_u32(&sm.empty[i]), CONSUMER_WARPS);
         }
         mbar_fence_init();
@@ -222,8 +223,9 @@ __global__ void __launch_bounds__(gk::THREADS, 1) gram_tma_kernel(const GramPara
     fence_proxy_async();  // order the generic-proxy zero fill before the async-proxy (TMA) writes
     __syncthreads();
 
-    if (warp == CONSUMER_WARPS) {
-        // ------------------------------------------------------------ producer warp (TMA)
+    if (warp >= CONSUMER_WARPS) {
+        // ------------------------------------------------------------ producer warps (TMA): 0 -> panel I + s, 1 -> panel J + t
+        const int pw = warp - CONSUMER_WARPS;
         int it = 0;  // running stage counter of this CTA: ring slot and phase continue across segments
         for (int sg = seg_begin; sg < seg_end; ++sg) {
             int ti, tj;
@@ -242,29 +244,21 @@ __global__ void __launch_bounds__(gk::THREADS, 1) gram_tma_kernel(const GramPara
                 const int kc = (int)min((int64_t)KT, p.N - k0);
                 Stage& S = sm.st[stg];
                 const uint32_t bar = smem_u32(&sm.full[stg]);
-                if (narrow) {  // rare (only tiles in the last block row when D % 128 != 0): clear the slot first
-                    double* z = reinterpret_cast<double*>(&S);
-                    for (int i = lane; i < 2 * KT * LDT; i += 32) z[i] = 0.0;
+                if (narrow) {  // rare (only tiles in the last block row when D % 128 != 0): clear my panel first
+                    double* z = pw == 0 ? S.a : S.b;
+                    for (int i = lane; i < KT * LDT; i += 32) z[i] = 0.0;
                     fence_proxy_async();
                     __syncwarp();
                 }
-                if (lane == 0) {
-                    const uint32_t bytes = (uint32_t)kc * (uint32_t)(rowsA + (diag ? 0 : rowsB)) * 8u + 2u * KT * 8u;
-                    mbar_arrive_expect_tx(bar, bytes);
-                }
+                const bool have_panel = (pw == 0) || !diag;
+                const int rows = pw == 0 ? rowsA : rowsB;
+                if (lane == 0)
+                    mbar_arrive_expect_tx(bar, (have_panel ? (uint32_t)kc * (uint32_t)rows * 8u : 0u) + KT * 8u);
                 __syncwarp();
-                if (lane < KT) {
-                    if (lane < kc)
-                        bulk_g2s(smem_u32(&S.a[lane * LDT]), p.X + (k0 + lane) * p.ld + i0, (uint32_t)rowsA * 8u, bar);
-                } else {
-                    const int l = lane - KT;
-                    if (!diag && l < kc)
-                        bulk_g2s(smem_u32(&S.b[l * LDT]), p.X + (k0 + l) * p.ld + j0, (uint32_t)rowsB * 8u, bar);
-                }
-                if (lane == 0) {
-                    bulk_g2s(smem_u32(S.s), p.s + k0, KT * 8u, bar);
-                    bulk_g2s(smem_u32(S.t), p.t + k0, KT * 8u, bar);
-                }
+                if (have_panel && lane < kc)
+                    bulk_g2s(smem_u32((pw == 0 ? S.a : S.b) + lane * LDT), p.X + (k0 + lane) * p.ld + (pw == 0 ? i0 : j0),
+                             (uint32_t)rows * 8u, bar);
+                if (lane == 0) bulk_g2s(smem_u32(pw == 0 ? S.s : S.t), (pw == 0 ? p.s : p.t) + k0, KT * 8u, bar);
             }
         }
         return;

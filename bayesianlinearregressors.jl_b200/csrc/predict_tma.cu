@@ -31,7 +31,11 @@ constexpr int KT = 16;          // features per stage
 constexpr int STAGES = 3;
 constexpr int LDB = KT + 4;     // B row stride (doubles): == 4 mod 16
 constexpr int CONSUMER_WARPS = 8;
-constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+// cp.async.bulk is a uniform-datapath instruction: the per-lane copies of a warp are issued one after another.
+// Four producer warps (A columns 0-7 | A columns 8-15 | points 0-15 | points 16-31) keep the issue rate ahead of
+// the consumers; 12 warps x 168 registers is exactly the register file.
+constexpr int PRODUCER_WARPS = 4;
+constexpr int THREADS = (CONSUMER_WARPS + PRODUCER_WARPS) * 32;
 template <int MI>
 struct Cfg {
     static constexpr int R = MI * 64;      // rows of α per pass
@@ -101,6 +105,12 @@ __device__ __forceinline__ void var_consume_dispatch(double (&acc)[MI][4][2], co
     // m0 >= MI: nothing live for this warp in this stage
 }
 
+// Stage order within a row pass: heavy (small k: many live rows) and light (large k) stages alternate, so the time a
+// (STAGES - 1)-deep prefetch covers stays ~constant instead of collapsing at the light end of the triangle.
+__device__ __forceinline__ int var_stage_k0(int s, int nst) {
+    return ((s & 1) ? (nst - 1 - (s >> 1)) : (s >> 1)) * vk::KT;
+}
+
 template <int MI>
 __global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams p) {
     using namespace vk;
@@ -116,7 +126,7 @@ __global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams
     }
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) {
-            mbar_init(smem_u32(&sm.full[i]), 1);
+            mbar_init(smem_u32(&sm.full[i]), PRODUCER_WARPS);
             mbar_init(smem_u32(&sm.empty[i]), CONSUMER_WARPS);
         }
         mbar_fence_init();
@@ -127,8 +137,9 @@ __global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams
     const int64_t ntiles = (p.N + NP - 1) / NP;
     const int npass = (int)(p.ldw / C::R);
 
-    if (warp == CONSUMER_WARPS) {
-        // ------------------------------------------------------------ producer warp (TMA)
+    if (warp >= CONSUMER_WARPS) {
+        // ------------------------------------------------------------ producer warps (TMA)
+        const int pw = warp - CONSUMER_WARPS;
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t p0 = tile * NP;
@@ -136,7 +147,9 @@ __global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams
             for (int ps = 0; ps < npass; ++ps) {
                 const int r_base = ps * C::R;
                 const int kmax = min(p.D, r_base + C::R);  // W[row][k] = 0 for k > row
-                for (int k0 = 0; k0 < kmax; k0 += KT, ++it) {
+                const int nst = (kmax + KT - 1) / KT;
+                for (int si = 0; si < nst; ++si, ++it) {
+                    const int k0 = var_stage_k0(si, nst);
                     const int stg = it % STAGES;
                     const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
                     mbar_wait(smem_u32(&sm.empty[stg]), ph ^ 1u);
@@ -145,17 +158,26 @@ __global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams
                     const int r_lo = max(r_base, (k0 / 64) * 64);     // first row that can be non-zero in this stage
                     const int rows = r_base + C::R - r_lo;
                     const int kc = min(KT, p.D - k0);                 // features present (D even => kc even)
-                    if (lane == 0) {
-                        const uint32_t bytes = (uint32_t)KT * rows * 8u + (uint32_t)npts * kc * 8u + (ps == npass - 1 ? KT * 8u : 0u);
-                        mbar_arrive_expect_tx(bar, bytes);
+                    const bool with_mw = (ps == npass - 1);
+                    if (pw < 2) {  // 8 columns of W each
+                        if (lane == 0)
+                            mbar_arrive_expect_tx(bar, (uint32_t)(KT / 2) * rows * 8u + ((pw == 0 && with_mw) ? KT * 8u : 0u));
+                        __syncwarp();
+                        if (lane < KT / 2) {
+                            const int kr = pw * (KT / 2) + lane;
+                            bulk_g2s(smem_u32(&S.a[kr * C::LDA + (r_lo - r_base)]), p.Wp + (int64_t)(k0 + kr) * p.ldw + r_lo,
+                                     (uint32_t)rows * 8u, bar);
+                        }
+                        if (lane == 0 && pw == 0 && with_mw) bulk_g2s(smem_u32(S.mw), p.mwp + k0, KT * 8u, bar);
+                    } else {       // 16 points each
+                        const int pbase = (pw - 2) * (NP / 2);
+                        const int my_pts = max(0, min(NP / 2, npts - pbase));
+                        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)my_pts * kc * 8u);
+                        __syncwarp();
+                        if (lane < my_pts)
+                            bulk_g2s(smem_u32(&S.b[(pbase + lane) * LDB]), p.X + (p0 + pbase + lane) * p.ld + k0,
+                                     (uint32_t)kc * 8u, bar);
                     }
-                    __syncwarp();
-                    if (lane < KT)
-                        bulk_g2s(smem_u32(&S.a[lane * C::LDA + (r_lo - r_base)]), p.Wp + (int64_t)(k0 + lane) * p.ldw + r_lo,
-                                 (uint32_t)rows * 8u, bar);
-                    if (lane < npts)
-                        bulk_g2s(smem_u32(&S.b[lane * LDB]), p.X + (p0 + lane) * p.ld + k0, (uint32_t)kc * 8u, bar);
-                    if (lane == 0 && ps == npass - 1) bulk_g2s(smem_u32(S.mw), p.mwp + k0, KT * 8u, bar);
                 }
             }
         }
@@ -164,11 +186,11 @@ __global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams
 
     // ---------------------------------------------------------------- consumer warps (DMMA)
     const int g = lane >> 2, kq = lane & 3;
-    const int mp = tid & 31, mk = tid >> 5;  // mean: point, k-slice (2 features per stage per thread)
+    const int mk = tid & 15, mpg = tid >> 4;  // mean: feature within the stage, point pair (conflict-free smem reads)
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t p0 = tile * NP;
-        double macc = 0.0;
+        double macc0 = 0.0, macc1 = 0.0;
         for (int ps = 0; ps < npass; ++ps) {
             const int r_base = ps * C::R;
             const int kmax = min(p.D, r_base + C::R);
@@ -177,7 +199,9 @@ __global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams
             for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-            for (int k0 = 0; k0 < kmax; k0 += KT, ++it) {
+            const int nst = (kmax + KT - 1) / KT;
+            for (int si = 0; si < nst; ++si, ++it) {
+                const int k0 = var_stage_k0(si, nst);
                 const int stg = it % STAGES;
                 const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
                 mbar_wait(smem_u32(&sm.full[stg]), ph);
@@ -187,8 +211,9 @@ __global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams
                 const int m0 = num <= 0 ? 0 : (num + 63) / 64;
                 var_consume_dispatch<MI>(acc, S.a, S.b, warp, g, kq, m0);
                 if (ps == npass - 1) {  // the last row pass streams every feature k < D
-                    macc = fma(S.mw[2 * mk], S.b[mp * LDB + 2 * mk], macc);
-                    macc = fma(S.mw[2 * mk + 1], S.b[mp * LDB + 2 * mk + 1], macc);
+                    const double mwk = S.mw[mk];
+                    macc0 = fma(mwk, S.b[(2 * mpg) * LDB + mk], macc0);
+                    macc1 = fma(mwk, S.b[(2 * mpg + 1) * LDB + mk], macc1);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&sm.empty[stg]));
@@ -211,7 +236,15 @@ __global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams
                     }
                 }
         }
-        sm.mred[mk][mp] = macc;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {  // fold the 16 features held by 16 consecutive lanes
+            macc0 += __shfl_xor_sync(0xffffffffu, macc0, o);
+            macc1 += __shfl_xor_sync(0xffffffffu, macc1, o);
+        }
+        if (mk == 0) {
+            sm.mred[0][2 * mpg] = macc0;
+            sm.mred[0][2 * mpg + 1] = macc1;
+        }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (tid < NP && p0 + tid < p.N) {
             const int64_t n = p0 + tid;
@@ -221,12 +254,7 @@ __global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams
                 for (int w = 0; w < CONSUMER_WARPS; ++w) v += sm.red[w][tid];
                 p.var[n] = v + (p.sigma2 ? p.sigma2[n] : p.sigma2_scalar);
             }
-            if (p.mean) {
-                double m = 0.0;
-#pragma unroll
-                for (int w = 0; w < CONSUMER_WARPS; ++w) m += sm.mred[w][tid];
-                p.mean[n] = m;
-            }
+            if (p.mean) p.mean[n] = sm.mred[0][tid];
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");  // slots are rewritten by the next tile
     }
@@ -304,7 +332,8 @@ constexpr int STAGES = 4;
 constexpr int LDA = KT + 4;     // [point][k]
 constexpr int LDB = TS + 4;     // [k][sample]
 constexpr int CONSUMER_WARPS = 8;
-constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+constexpr int PRODUCER_WARPS = 4;  // UBLKCP is a uniform-datapath op: per-lane copies serialise, so split them over 4 warps
+constexpr int THREADS = (CONSUMER_WARPS + PRODUCER_WARPS) * 32;
 struct __align__(16) Stage {
     double a[TP * LDA];
     double b[KT * LDB];
@@ -343,7 +372,7 @@ __global__ void __launch_bounds__(rk::THREADS, 1) rand_tma_kernel(const RandPara
     }
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) {
-            mbar_init(smem_u32(&sm.full[i]), 1);
+            mbar_init(smem_u32(&sm.full[i]), PRODUCER_WARPS);
             mbar_init(smem_u32(&sm.empty[i]), CONSUMER_WARPS);
         }
         mbar_fence_init();
@@ -354,7 +383,8 @@ __global__ void __launch_bounds__(rk::THREADS, 1) rand_tma_kernel(const RandPara
     const int64_t ntiles = (p.N + TP - 1) / TP;
     const int nsb = (p.S + TS - 1) / TS;
 
-    if (warp == CONSUMER_WARPS) {
+    if (warp >= CONSUMER_WARPS) {
+        const int pw = warp - CONSUMER_WARPS;  // producer pw: points 32 pw .. 32 pw + 31 and W rows 8 pw .. 8 pw + 7
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t p0 = tile * TP;
@@ -368,14 +398,17 @@ __global__ void __launch_bounds__(rk::THREADS, 1) rand_tma_kernel(const RandPara
                     Stage& S = sm.st[stg];
                     const uint32_t bar = smem_u32(&sm.full[stg]);
                     const int kc = min(KT, p.D - k0);
-                    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)npts * kc * 8u + (uint32_t)KT * TS * 8u);
+                    const int my_pts = max(0, min(TP / 4, npts - pw * (TP / 4)));
+                    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)my_pts * kc * 8u + (uint32_t)(KT / 4) * TS * 8u);
                     __syncwarp();
-#pragma unroll
-                    for (int q = 0; q < TP / 32; ++q) {
-                        const int pt = q * 32 + lane;
+                    {
+                        const int pt = pw * (TP / 4) + lane;
                         if (pt < npts) bulk_g2s(smem_u32(&S.a[pt * LDA]), p.X + (p0 + pt) * p.ld + k0, (uint32_t)kc * 8u, bar);
                     }
-                    bulk_g2s(smem_u32(&S.b[lane * LDB]), Wsb + (int64_t)(k0 + lane) * TS, TS * 8u, bar);
+                    if (lane < KT / 4) {
+                        const int kr = pw * (KT / 4) + lane;
+                        bulk_g2s(smem_u32(&S.b[kr * LDB]), Wsb + (int64_t)(k0 + kr) * TS, TS * 8u, bar);
+                    }
                 }
             }
         }

@@ -57,6 +57,9 @@ print(json.dumps(c.calibrate()))
       done 2>&1 | tee "$OUT/solve_timing.log";;
     configs)
       timeout 1200 python tools/bench_configs.py > "$OUT/configs.jsonl" 2> "$OUT/configs.err"; echo "configs exit $?"; cat "$OUT/configs.jsonl"; tail -5 "$OUT/configs.err";;
+    ncu_pred)
+      timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"var_tma|rand_tma" -s 2 -c 2 -o "$OUT/prof_pred" -f \
+        python tools/run_predict.py 512 2097152 64 > "$OUT/ncu_pred.log" 2>&1; echo "ncu_pred exit $?"; tail -3 "$OUT/ncu_pred.log";;
     dmma_probe)
       timeout 300 python -c "
 import blr_b200 as b, ctypes as C
