@@ -150,6 +150,10 @@ int blr_ctx_create(blr_ctx** out, int device) {
         return BLR_E_CUDA;
     }
     ctx->small_bytes = (size_t)SMALL_TOTAL * sizeof(double);
+    if (const char* k = getenv("BLR_GRAM_KT")) {
+        if (atoi(k) == 16) ctx->gram_kt = 16;
+        if (atoi(k) == 32) ctx->gram_kt = 32;
+    }
     if (const char* w = getenv("BLR_DIAG_WEIGHT")) {
         const int v = atoi(w);
         if (v >= 8 && v <= 128) ctx->diag_weight = v;

@@ -95,21 +95,22 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(const double* __rest
 // ====================================================================== K1 fast path
 namespace gk {
 constexpr int TM = 128;                   // tile edge (rows of G per panel)
-constexpr int KT = 16;                    // observations per pipeline stage
+constexpr int KT_MAX = 32;                // observations per pipeline stage: 16 (4-stage ring) or 32 (3-stage ring)
 constexpr int LDT = TM + 4;               // padded smem row: stride == 4 (mod 16) doubles -> conflict-free LDS.64
-constexpr int STAGES = 4;
 constexpr int CONSUMER_WARPS = 8;         // 2 (m) x 4 (n) warps, warp tile 64 x 32
 constexpr int PRODUCER_WARPS = 2;         // bulk copies are uniform-datapath ops (one lane at a time): panel I | panel J
 constexpr int THREADS = (CONSUMER_WARPS + PRODUCER_WARPS) * 32;
 constexpr int W_OFF = 64;                 // schedule weight of one stage of an off-diagonal tile
+template <int KT>
 struct __align__(16) Stage {
     double a[KT * LDT];  // panel I rows  [k][m]
     double b[KT * LDT];  // panel J rows  [k][n]  (unused on diagonal tiles)
     double s[KT];        // 1/σ²
     double t[KT];        // δ/σ²
 };
+template <int KT, int STAGES>
 struct Smem {
-    Stage st[STAGES];
+    Stage<KT> st[STAGES];
     double rred[TM];
     unsigned long long full[STAGES];
     unsigned long long empty[STAGES];
@@ -131,7 +132,7 @@ struct GramParams {
     double* Pr;   // [nseg][TM]
     const int* cta_seg_begin;  // [grid + 1]
     const int* seg_tile;       // [nseg]
-    const int* seg_g0;         // [nseg] first stage (16 observations each)
+    const int* seg_g0;         // [nseg] first stage (KT observations each)
     const int* seg_g1;         // [nseg] one past the last stage
 };
 
@@ -147,8 +148,8 @@ __device__ __forceinline__ void tile_from_index(int idx, int& ti, int& tj) {
 // mi - ni >= wn*4 - wm*8).  Compile-time, because predicating an mma.sync at run time makes ptxas wrap every DMMA in
 // WARPSYNC.ALL, which serialises the tensor pipe (measured: no speed-up at all from run-time skipping).
 //   THR = -8: all 32 sub-tiles;  THR = 0: 26;  THR = 4: 10.
-template <bool DIAG, int THR>
-__device__ __forceinline__ void consume_stage(double (&acc)[8][4][2], const gk::Stage& S, int wm, int wn, int g, int kq) {
+template <bool DIAG, int THR, int KT>
+__device__ __forceinline__ void consume_stage(double (&acc)[8][4][2], const gk::Stage<KT>& S, int wm, int wn, int g, int kq) {
     using namespace gk;
     const double* Ap = S.a + wm * 64 + g;
     const double* Bp = (DIAG ? S.a : S.b) + wn * 32 + g;
@@ -174,19 +175,19 @@ __device__ __forceinline__ void consume_stage(double (&acc)[8][4][2], const gk::
 
 // All stages of one segment for one consumer warp.  MODE: 0 off-diagonal; 1..3 diagonal with THR -8 / 0 / 4;
 // 4 diagonal, warp entirely above the diagonal (only helps with the r block).
-template <int MODE>
-__device__ __forceinline__ void run_segment(double (&acc)[8][4][2], double& racc, gk::Smem& sm, int& it, int nst, int wm,
-                                            int wn, int g, int kq, int rm, int rhalf, int lane) {
+template <int MODE, int KT, int STAGES>
+__device__ __forceinline__ void run_segment(double (&acc)[8][4][2], double& racc, gk::Smem<KT, STAGES>& sm, int& it, int nst,
+                                            int wm, int wn, int g, int kq, int rm, int rhalf, int lane) {
     using namespace gk;
     for (int i = 0; i < nst; ++i, ++it) {
         const int stg = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(smem_u32(&sm.full[stg]), ph);
-        const Stage& S = sm.st[stg];
-        if (MODE == 0) consume_stage<false, -8>(acc, S, wm, wn, g, kq);
-        if (MODE == 1) consume_stage<true, -8>(acc, S, wm, wn, g, kq);
-        if (MODE == 2) consume_stage<true, 0>(acc, S, wm, wn, g, kq);
-        if (MODE == 3) consume_stage<true, 4>(acc, S, wm, wn, g, kq);
+        const Stage<KT>& S = sm.st[stg];
+        if (MODE == 0) consume_stage<false, -8, KT>(acc, S, wm, wn, g, kq);
+        if (MODE == 1) consume_stage<true, -8, KT>(acc, S, wm, wn, g, kq);
+        if (MODE == 2) consume_stage<true, 0, KT>(acc, S, wm, wn, g, kq);
+        if (MODE == 3) consume_stage<true, 4, KT>(acc, S, wm, wn, g, kq);
         if (MODE != 0) {
 #pragma unroll
             for (int k = 0; k < KT / 2; ++k) {  // r block of this row panel: r[m] += Σ_k X[m,k] t_k
@@ -199,8 +200,11 @@ __device__ __forceinline__ void run_segment(double (&acc)[8][4][2], double& racc
     }
 }
 
+template <int KT, int STAGES>
 __global__ void __launch_bounds__(gk::THREADS, 1) gram_tma_kernel(const GramParams p) {
     using namespace gk;
+    using Stage = gk::Stage<KT>;
+    using Smem = gk::Smem<KT, STAGES>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
@@ -288,11 +292,11 @@ __global__ void __launch_bounds__(gk::THREADS, 1) gram_tma_kernel(const GramPara
         double racc = 0.0;
 
         // warp-uniform dispatch to a fully unrolled, unpredicated instruction stream
-        if (!diag) run_segment<0>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
-        else if (thr <= -3) run_segment<1>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
-        else if (thr == 0) run_segment<2>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
-        else if (thr == 4) run_segment<3>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
-        else run_segment<4>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
+        if (!diag) run_segment<0, KT, STAGES>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
+        else if (thr <= -3) run_segment<1, KT, STAGES>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
+        else if (thr == 0) run_segment<2, KT, STAGES>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
+        else if (thr == 4) run_segment<3, KT, STAGES>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
+        else run_segment<4, KT, STAGES>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
 
         // ------------------------------------------------------------ segment epilogue: partial tile -> its slot
         double* Pt = p.P + (int64_t)sg * (TM * TM);
@@ -442,7 +446,8 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
     BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], sm));
 
     // ---- K0: prep
-    const int64_t npad = round_up(N, gk::KT) + gk::KT;
+    const int KT = ctx->gram_kt;  // 16 or 32
+    const int64_t npad = round_up(N, gk::KT_MAX) + gk::KT_MAX;
     BLR_TRY(ensure_nbuf(ctx, (size_t)(2 * npad) * sizeof(double)));
     double* s = ctx->nbuf;
     double* t = ctx->nbuf + npad;
@@ -484,10 +489,10 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
     if (fast) {
         const int TS = gk::TM;
         const int nt = (D + TS - 1) / TS;
-        const int64_t n_stages = (N + gk::KT - 1) / gk::KT;
+        const int64_t n_stages = (N + KT - 1) / KT;
         const int G = ctx->sm_count;
         if (ctx->sched_key[0] != nt || ctx->sched_key[1] != n_stages || ctx->sched_key[2] != G ||
-            ctx->sched_key[3] != ctx->diag_weight) {
+            ctx->sched_key[3] != ctx->diag_weight) {  // n_stages encodes KT for a given N
             Schedule sc;
             build_schedule(sc, nt, n_stages, G, ctx->diag_weight);
             const size_t bytes = sc.table.size() * sizeof(int);
@@ -525,9 +530,17 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
         gp.seg_tile = tile_slot_begin + (T + 1);
         gp.seg_g0 = gp.seg_tile + nseg;
         gp.seg_g1 = gp.seg_g0 + nseg;
-        BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)sizeof(gk::Smem)));
-        gram_tma_kernel<<<G, gk::THREADS, sizeof(gk::Smem), sm>>>(gp);
+        if (KT == 32) {
+            using SM = gk::Smem<32, 3>;
+            BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_tma_kernel<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)sizeof(SM)));
+            gram_tma_kernel<32, 3><<<G, gk::THREADS, sizeof(SM), sm>>>(gp);
+        } else {
+            using SM = gk::Smem<16, 4>;
+            BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_tma_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)sizeof(SM)));
+            gram_tma_kernel<16, 4><<<G, gk::THREADS, sizeof(SM), sm>>>(gp);
+        }
         BLR_CHECK_LAUNCH(ctx, "gram_tma_kernel");
         BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], sm));
         // the slot sum of one tile is spread over several CTAs (few tiles at small D, many slots per tile)

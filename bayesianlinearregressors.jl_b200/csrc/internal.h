@@ -64,6 +64,7 @@ struct blr_ctx {
     size_t sched_bytes = 0;
     int64_t sched_key[4] = {-1, -1, -1, -1};
     int sched_T = 0, sched_nseg = 0;
+    int gram_kt = 32;      // observations per pipeline stage of the Gram kernel: 16 or 32 (BLR_GRAM_KT)
     int diag_weight = 40;  // cost of a diagonal-tile stage relative to W_OFF = 64 (BLR_DIAG_WEIGHT overrides)
     // host-streaming path (blr_stats_accumulate_host): copy stream, two staging slots
     cudaStream_t copy_stream = nullptr;

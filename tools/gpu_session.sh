@@ -38,7 +38,7 @@ print(json.dumps(c.calibrate()))
       timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -x --timeout 600 > "$OUT/multi_tests.log" 2>&1; echo "multi_tests exit $?"; tail -15 "$OUT/multi_tests.log";;
     bench_multi)
       NG=$(nvidia-smi -L | wc -l)
-      for n in 1 2 4 8; do
+      for n in ${NLIST:-1 2 4 8}; do
         if [ $n -le $NG ]; then
           if [ $n -eq 1 ]; then
             timeout 900 python bench.py --gpus 1 --steps 3 --warmup 3 --no-cpu --no-e2e > "$OUT/bench_g$n.json" 2> "$OUT/bench_g$n.err"
@@ -60,6 +60,15 @@ print(json.dumps(c.calibrate()))
     ncu_pred)
       timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"var_tma|rand_tma" -s 2 -c 2 -o "$OUT/prof_pred" -f \
         python tools/run_predict.py 512 2097152 64 > "$OUT/ncu_pred.log" 2>&1; echo "ncu_pred exit $?"; tail -3 "$OUT/ncu_pred.log";;
+    kt_sweep)
+      for kt in 16 32; do
+        for cfg in "--n-obs 1048576 --dim 256" "--n-obs 2097152 --dim 1024"; do
+          echo "KT=$kt cfg=$cfg"
+          BLR_GRAM_KT=$kt timeout 600 python bench.py $cfg --steps 5 --warmup 3 --no-cpu --no-e2e --no-calibrate 2>> "$OUT/kt.err" \
+            | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['achieved'])"
+        done
+      done 2>&1 | tee "$OUT/kt_sweep.log"
+      BLR_GRAM_KT=32 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "statistics or posterior_and_logpdf" > "$OUT/tests_kt32.log" 2>&1; tail -3 "$OUT/tests_kt32.log";;
     dmma_probe)
       timeout 300 python -c "
 import blr_b200 as b, ctypes as C
