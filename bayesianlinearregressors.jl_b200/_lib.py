@@ -20,7 +20,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "blr_cuda.h")
 E_INVALID, E_CUDA, E_NCCL, E_DIM, E_NODEVICE, E_NOMEM = -1, -2, -3, -4, -5, -6
 COLVECS, ROWVECS = 0, 1
 LAMBDA_DIAGONAL, LAMBDA_DENSE = 0, 1
-NOISE_SCALAR, NOISE_VECTOR = 0, 1
+NOISE_SCALAR, NOISE_VECTOR, NOISE_DENSE = 0, 1, 2
 
 c_double_p = C.POINTER(C.c_double)
 c_void_pp = C.POINTER(C.c_void_p)
@@ -31,7 +31,7 @@ class Prior(C.Structure):
 
 
 class Noise(C.Structure):
-    _fields_ = [("kind", C.c_int), ("scalar", C.c_double), ("vec", C.c_void_p)]
+    _fields_ = [("kind", C.c_int), ("scalar", C.c_double), ("vec", C.c_void_p), ("dense", C.c_void_p), ("dense_ld", C.c_int64)]
 
 
 # name -> (restype, argtypes); every symbol include/blr_cuda.h declares (checked by tests/test_abi.py)

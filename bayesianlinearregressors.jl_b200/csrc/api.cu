@@ -101,6 +101,65 @@ static int noise_args(blr_ctx* ctx, const blr_noise* noise, int64_t N, const dou
     return set_err(ctx, BLR_E_INVALID, "unknown noise kind");
 }
 
+// ---------------------------------------------------------------------------------------------- dense Σy side path
+// (reference src/bayesian_linear_regression.jl:79,:81-82 with a dense `_cholesky(fx.Σy)`.)
+struct DenseNoise {
+    int64_t N = 0;
+    double* S = nullptr;     // Σy (N x N, column-major)
+    double* L = nullptr;     // lower Cholesky factor, Σy = L L'  (Σy.U' of the reference)
+    double* diag = nullptr;  // diag(Σy)
+    double* scal = nullptr;  // [0] = logdet Σy
+};
+__global__ void dense_diag_kernel(const double* __restrict__ S, int64_t N, double* __restrict__ diag) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
+        diag[i] = S[i * N + i];
+}
+__global__ void add_to_scalar_kernel(double* __restrict__ dst, const double* __restrict__ src) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) dst[0] += src[0];
+}
+__global__ void add_matrix_kernel(double* __restrict__ C, const double* __restrict__ A, int64_t n) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) C[e] += A[e];
+}
+static void dense_noise_release(blr_ctx* ctx, DenseNoise* dn) {
+    dev_free(ctx->stream, dn->S);
+    dn->S = dn->L = dn->diag = dn->scal = nullptr;
+}
+// uploads Σy, factorises it (PosDefException info > 0 on failure), extracts diag and logdet
+static int dense_noise_prepare(blr_ctx* ctx, const blr_noise* noise, int64_t N, DenseNoise* dn) {
+    if (!noise->dense) return set_err(ctx, BLR_E_INVALID, "noise.dense is NULL");
+    const int64_t ld = noise->dense_ld > 0 ? noise->dense_ld : N;
+    if (ld < N) return set_err(ctx, BLR_E_DIM, "size(Σy) does not match the number of inputs");
+    if (ctx->nranks > 1) return set_err(ctx, BLR_E_INVALID, "dense observation noise couples observations: single GPU only");
+    dn->N = N;
+    double* buf = nullptr;
+    BLR_CUDA_OK(ctx, dev_alloc(ctx, &buf, (size_t)(2 * N * N + N + 2) * sizeof(double)));
+    dn->S = buf;
+    dn->L = buf + N * N;
+    dn->diag = dn->L + N * N;
+    dn->scal = dn->diag + N;
+    cudaStream_t sm = ctx->stream;
+    cudaError_t e = cudaMemcpy2DAsync(dn->S, (size_t)N * sizeof(double), noise->dense, (size_t)ld * sizeof(double),
+                                      (size_t)N * sizeof(double), (size_t)N, cudaMemcpyHostToDevice, sm);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dn->L, dn->S, (size_t)N * N * sizeof(double), cudaMemcpyDeviceToDevice, sm);
+    if (e != cudaSuccess) {
+        dense_noise_release(ctx, dn);
+        return cuda_fail(ctx, e, "upload Σy");
+    }
+    dense_diag_kernel<<<(int)std::min<int64_t>((N + 255) / 256, 1024), 256, 0, sm>>>(dn->S, N, dn->diag);
+    ctx->launches++;
+    int rc = potrf_lower(ctx, dn->L, N, ctx->d_info);
+    if (rc == 0) rc = logdet_from_chol(ctx, dn->L, N, dn->scal);
+    int info = 0;
+    if (rc == 0) {
+        e = cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, sm);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(sm);
+        if (e != cudaSuccess) rc = cuda_fail(ctx, e, "read info");
+    }
+    if (rc == 0 && info != 0) rc = info;
+    if (rc != 0) dense_noise_release(ctx, dn);
+    return rc;
+}
+
 }  // namespace blr
 
 using namespace blr;
@@ -483,6 +542,50 @@ int blr_stats_accumulate(blr_ctx* ctx, blr_stats* s, const double* mw_host, cons
     if (!s || !x || !y || !mw_host) return set_err(ctx, BLR_E_INVALID, "null argument");
     if (x->D != s->D) return set_err(ctx, BLR_E_INVALID, "size(X, 1) != length(mw)");
     if (y->n != x->N) return set_err(ctx, BLR_E_DIM, "length(y) != size(fx.x.X, 2)");
+    if (noise && noise->kind == BLR_NOISE_DENSE) {
+        // whiten with the factor of Σy and reuse the diagonal-noise path:  à = L^-1 X' (N x D, a RowVecs matrix),
+        // ỹ = L^-1 y, unit noise;  logdet Σy is added to ℓ afterwards.
+        const int64_t N = x->N, D = x->D;
+        if (N == 0) return 0;
+        DenseNoise dn;
+        BLR_TRY(dense_noise_prepare(ctx, noise, N, &dn));
+        double* buf = nullptr;
+        cudaError_t e = dev_alloc(ctx, &buf, (size_t)(N * N + N * D + N) * sizeof(double));
+        if (e != cudaSuccess) {
+            dense_noise_release(ctx, &dn);
+            return cuda_fail(ctx, e, "cudaMallocAsync(whiten)");
+        }
+        double *Wy = buf, *At = buf + N * N, *yt = At + N * D;
+        const bool colv = x->layout == BLR_COLVECS;
+        int rc = trtri_lower(ctx, dn.L, Wy, N);
+        // Ã[n, d] = Σ_m Wy[n, m] X[d, m]
+        if (rc == 0) rc = gemm_generic(ctx, N, D, N, Wy, 1, N, x->p, colv ? x->ld : 1, colv ? 1 : x->ld, At, 1, N, 0.0);
+        if (rc == 0) rc = gemm_generic(ctx, N, 1, N, Wy, 1, N, y->p, 1, N, yt, 1, N, 0.0);
+        if (rc == 0) {
+            bool zero = true;
+            for (int64_t i = 0; i < D; ++i)
+                if (mw_host[i] != 0.0) zero = false;
+            double* mwd = ctx->small + SMALL_MW;
+            if (!zero) {
+                e = cudaMemcpyAsync(mwd, mw_host, (size_t)D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+                if (e != cudaSuccess) rc = cuda_fail(ctx, e, "upload mw");
+            }
+            blr_x xw;
+            xw.p = At;
+            xw.D = D;
+            xw.N = N;
+            xw.ld = N;
+            xw.layout = BLR_ROWVECS;
+            if (rc == 0) rc = gram_accumulate(ctx, s, mwd, zero, &xw, yt, nullptr, 1.0);
+        }
+        if (rc == 0) {
+            add_to_scalar_kernel<<<1, 32, 0, ctx->stream>>>(s->scal() + 1, dn.scal);
+            ctx->launches++;
+        }
+        dev_free(ctx->stream, buf);
+        dense_noise_release(ctx, &dn);
+        return rc;
+    }
     const double* sig = nullptr;
     double sig_scalar = 0.0;
     BLR_TRY(noise_args(ctx, noise, x->N, &sig, &sig_scalar));
@@ -653,6 +756,14 @@ int blr_mean_var_dev(blr_ctx* ctx, blr_post* p, const blr_x* x, const blr_noise*
     CTX_ENTER(ctx);
     if (!p || !x) return set_err(ctx, BLR_E_INVALID, "null argument");
     if (x->D != p->D) return set_err(ctx, BLR_E_INVALID, "size(X, 1) != length(mw)");
+    if (noise && noise->kind == BLR_NOISE_DENSE) {  // only diag(Σy) enters the marginal variances (:42)
+        if (x->N == 0) return 0;
+        DenseNoise dn;
+        BLR_TRY(dense_noise_prepare(ctx, noise, x->N, &dn));
+        const int rc = predict_mean_var(ctx, p, x, dn.diag, 0.0, mean_dev, var_dev);
+        dense_noise_release(ctx, &dn);
+        return rc;
+    }
     const double* sig = nullptr;
     double sig_scalar = 0.0;
     BLR_TRY(noise_args(ctx, noise, x->N, &sig, &sig_scalar));
@@ -689,10 +800,22 @@ int blr_cov(blr_ctx* ctx, blr_post* p, const blr_x* x, const blr_noise* noise, d
     if (N == 0) return 0;
     const double* sig = nullptr;
     double sig_scalar = 0.0;
-    BLR_TRY(noise_args(ctx, noise, N, &sig, &sig_scalar));
+    DenseNoise dn;
+    const bool dense = noise && noise->kind == BLR_NOISE_DENSE;
+    if (dense)
+        BLR_TRY(dense_noise_prepare(ctx, noise, N, &dn));
+    else
+        BLR_TRY(noise_args(ctx, noise, N, &sig, &sig_scalar));
     double* C = nullptr;
     BLR_CUDA_OK(ctx, dev_alloc(ctx, &C, (size_t)N * N * sizeof(double)));
     int rc = predict_cov(ctx, p, x, sig, sig_scalar, C);
+    if (dense) {
+        if (rc == 0) {
+            add_matrix_kernel<<<(int)std::min<int64_t>((N * N + 255) / 256, 2048), 256, 0, ctx->stream>>>(C, dn.S, N * N);
+            ctx->launches++;
+        }
+        dense_noise_release(ctx, &dn);
+    }
     cudaError_t e = cudaSuccess;
     if (rc == 0) e = cudaMemcpyAsync(C_host, C, (size_t)N * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
@@ -737,7 +860,12 @@ int blr_rand_finite_dev(blr_ctx* ctx, blr_post* p, const blr_x* x, const blr_noi
     const int64_t D = p->D;
     const double* sig = nullptr;
     double sig_scalar = 0.0;
-    BLR_TRY(noise_args(ctx, noise, x->N, &sig, &sig_scalar));
+    DenseNoise dn;
+    const bool dense = noise && noise->kind == BLR_NOISE_DENSE;
+    if (dense)
+        BLR_TRY(dense_noise_prepare(ctx, noise, x->N, &dn));
+    else
+        BLR_TRY(noise_args(ctx, noise, x->N, &sig, &sig_scalar));
     double* buf = nullptr;
     BLR_CUDA_OK(ctx, dev_alloc(ctx, &buf, (size_t)2 * (D + 1) * S * sizeof(double)));
     double *Zd = buf, *Wd = buf + (D + 1) * S;
@@ -748,7 +876,22 @@ int blr_rand_finite_dev(blr_ctx* ctx, blr_post* p, const blr_x* x, const blr_noi
     else
         rc = synth_normal(ctx, Zd, D, S, D, seed, 5, 0);
     if (rc == 0 && e == cudaSuccess) rc = sample_weights(ctx, p, S, Zd, Wd);
-    if (rc == 0 && e == cudaSuccess) rc = sample_finite(ctx, x, Wd, S, sig, sig_scalar, Zy_dev, seed, Y_dev);
+    if (dense) {
+        // Y = X'w + Uy' Zy with Uy' = L (dense lower factor): noiseless product first, then Y += L Z  (:52)
+        const int64_t N = x->N;
+        if (rc == 0 && e == cudaSuccess) rc = sample_finite(ctx, x, Wd, S, nullptr, 0.0, nullptr, seed, Y_dev);
+        double* Zgen = nullptr;
+        if (rc == 0 && e == cudaSuccess && !Zy_dev) {
+            e = dev_alloc(ctx, &Zgen, (size_t)(N + 1) * S * sizeof(double));
+            if (e == cudaSuccess) rc = synth_normal(ctx, Zgen, N, S, N, seed, 7, 0);
+        }
+        if (rc == 0 && e == cudaSuccess)
+            rc = gemm_generic(ctx, N, S, N, dn.L, 1, N, Zy_dev ? Zy_dev : Zgen, 1, N, Y_dev, 1, N, 1.0);
+        dev_free(ctx->stream, Zgen);
+        dense_noise_release(ctx, &dn);
+    } else if (rc == 0 && e == cudaSuccess) {
+        rc = sample_finite(ctx, x, Wd, S, sig, sig_scalar, Zy_dev, seed, Y_dev);
+    }
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
     dev_free(ctx->stream, buf);
     if (rc != 0) return rc;

@@ -144,6 +144,9 @@ int sample_weights(blr_ctx* ctx, blr_post* p, int64_t S, const double* Z_dev, do
 int sample_finite(blr_ctx* ctx, const blr_x* x, const double* Wsamp_dev, int64_t S, const double* sigma2,
                   double sigma2_scalar, const double* Zy_dev, uint64_t seed, double* Y_dev);
 int apply_weights(blr_ctx* ctx, const blr_x* x, const double* w_dev, double* out_dev);
+// C[m, n] = beta * C + Σ_k A[m, k] B[k, n] with arbitrary element strides (small / odd shapes; plain DFMA)
+int gemm_generic(blr_ctx* ctx, int64_t M, int64_t Nn, int64_t K, const double* A, int64_t as_m, int64_t as_k,
+                 const double* B, int64_t bs_k, int64_t bs_n, double* C, int64_t cs_m, int64_t cs_n, double beta);
 
 // ---- predict_tma.cu
 bool predict_fast_eligible(const blr_post* p, const blr_x* x);

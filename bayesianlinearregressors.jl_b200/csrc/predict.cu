@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) gemm_generic_kernel(int64_t M, int64_t Nn
         }
 }
 
-static int gemm_generic(blr_ctx* ctx, int64_t M, int64_t Nn, int64_t K, const double* A, int64_t as_m, int64_t as_k,
+int gemm_generic(blr_ctx* ctx, int64_t M, int64_t Nn, int64_t K, const double* A, int64_t as_m, int64_t as_k,
                         const double* B, int64_t bs_k, int64_t bs_n, double* C, int64_t cs_m, int64_t cs_n, double beta) {
     if (M == 0 || Nn == 0) return 0;
     const int64_t gx = (M + 31) / 32, gy = (Nn + 31) / 32;

@@ -253,26 +253,35 @@ def make_noise(ctx: Context, Σy, N: int):
     """FiniteGP noise normalisation -> (Noise struct, keepalive).  Real -> Diagonal(Fill), vector -> Diagonal."""
     from .model import Diagonal  # local import: model imports runtime
 
+    from .model import PDMat, Symmetric
+
     if isinstance(Σy, DeviceVector):
-        return L.Noise(L.NOISE_VECTOR, 0.0, Σy.handle), Σy
+        return L.Noise(L.NOISE_VECTOR, 0.0, Σy.handle, None, 0), Σy
     if isinstance(Σy, Diagonal):
         Σy = Σy.diag
+    if isinstance(Σy, (Symmetric, PDMat)):
+        Σy = Σy.dense()
     if isinstance(Σy, DeviceVector):
-        return L.Noise(L.NOISE_VECTOR, 0.0, Σy.handle), Σy
+        return L.Noise(L.NOISE_VECTOR, 0.0, Σy.handle, None, 0), Σy
     try:
         import torch
 
         if isinstance(Σy, torch.Tensor) and Σy.is_cuda:
             v = DeviceVector.wrap_torch(ctx, Σy)
-            return L.Noise(L.NOISE_VECTOR, 0.0, v.handle), v
+            return L.Noise(L.NOISE_VECTOR, 0.0, v.handle, None, 0), v
     except ImportError:  # pragma: no cover
         pass
     a = np.asarray(Σy, dtype=np.float64)
     if a.ndim == 0:
-        return L.Noise(L.NOISE_SCALAR, float(a), None), None
+        return L.Noise(L.NOISE_SCALAR, float(a), None, None, 0), None
     if a.ndim == 1:
+        if a.shape[0] != N:
+            raise L.DimensionMismatch(L.E_DIM, "length(diag(Σy)) != number of inputs")
         v = DeviceVector.upload(ctx, a)
-        return L.Noise(L.NOISE_VECTOR, 0.0, v.handle), v
-    raise NotImplementedError(
-        "dense (non-diagonal) observation noise is outside this graft's hot path (SURVEY.md section 8f, item 2)"
-    )
+        return L.Noise(L.NOISE_VECTOR, 0.0, v.handle, None, 0), v
+    if a.ndim == 2:  # dense Σy: the small-N side path (whitening on the device)
+        if a.shape != (N, N):
+            raise L.DimensionMismatch(L.E_DIM, "size(Σy) does not match the number of inputs")
+        af = _f64(a, "F")
+        return L.Noise(L.NOISE_DENSE, 0.0, None, af.ctypes.data_as(C.c_void_p), N), af
+    raise L.BLRError(L.E_INVALID, "unsupported observation-noise argument")

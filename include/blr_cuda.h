@@ -47,6 +47,8 @@ extern "C" {
 /* observation-noise kinds of FiniteGP.Σy */
 #define BLR_NOISE_SCALAR 0 /* Diagonal(Fill(σ², N)) : f(X, 0.1) */
 #define BLR_NOISE_VECTOR 1 /* Diagonal(v)           : f(X, Diagonal(v)) */
+#define BLR_NOISE_DENSE 2  /* dense N x N Σy (the reference's test fixtures, test/test_utils.jl:7-8): small-N side path --
+                              Σy is factorised on the device and X, y are whitened before the same Gram kernel runs */
 
 typedef struct blr_ctx blr_ctx;
 typedef struct blr_x blr_x;         /* device design matrix (this rank's N-shard) */
@@ -65,6 +67,8 @@ typedef struct blr_noise {
     int kind;           /* BLR_NOISE_* */
     double scalar;      /* σ² when kind == SCALAR */
     const blr_vec* vec; /* σ²_n when kind == VECTOR (same N partition as X) */
+    const double* dense; /* host, N x N symmetric column-major when kind == DENSE (single GPU: couples observations) */
+    int64_t dense_ld;    /* leading dimension of `dense` (>= N) */
 } blr_noise;
 
 /* ------------------------------------------------------------------ context */

@@ -16,7 +16,11 @@ _prior(f::BayesianLinearRegressor) =
     (mw = collect(Float64, f.mw); Λ = Matrix{Float64}(f.Λw);
      (LibBLR.Prior(pointer(mw), LibBLR.LAMBDA_DENSE, pointer(Λ), size(Λ, 1)), (mw, Λ)))
 
-# Σy kinds of FiniteGP: Diagonal(Fill) -> scalar, Diagonal(v) -> device vector.  Dense Σy keeps the reference path.
+# Σy kinds of FiniteGP: Diagonal(Fill) -> scalar, Diagonal(v) -> device vector, dense -> small-N whitening side path.
+function _noise(ctx, Σy::AbstractMatrix)
+    S = Matrix{Float64}(Σy)
+    return LibBLR.Noise(LibBLR.NOISE_DENSE, 0.0, C_NULL, pointer(S), size(S, 1)), S
+end
 _noise(ctx, Σy::Diagonal{<:Real,<:FillArrays.Fill}) = (LibBLR.Noise(LibBLR.NOISE_SCALAR, first(Σy.diag), C_NULL), nothing)
 function _noise(ctx, Σy::Diagonal)
     v = LibBLR.upload_vec(ctx, collect(Float64, Σy.diag))

@@ -11,7 +11,7 @@ const libblr = get(ENV, "LIBBLR_CUDA", "libblr_cuda")
 
 const COLVECS, ROWVECS = Cint(0), Cint(1)
 const LAMBDA_DIAGONAL, LAMBDA_DENSE = Cint(0), Cint(1)
-const NOISE_SCALAR, NOISE_VECTOR = Cint(0), Cint(1)
+const NOISE_SCALAR, NOISE_VECTOR, NOISE_DENSE = Cint(0), Cint(1), Cint(2)
 const E_DIM = Cint(-4)
 
 struct Prior
@@ -25,7 +25,10 @@ struct Noise
     kind::Cint
     scalar::Float64
     vec::Ptr{Cvoid}
+    dense::Ptr{Float64}     # host N x N matrix when kind == NOISE_DENSE
+    dense_ld::Int64
 end
+Noise(kind, scalar, vec) = Noise(kind, scalar, vec, C_NULL, 0)
 
 mutable struct Context
     ptr::Ptr{Cvoid}
