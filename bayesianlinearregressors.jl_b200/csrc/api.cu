@@ -209,6 +209,10 @@ int blr_ctx_create(blr_ctx** out, int device) {
         return BLR_E_CUDA;
     }
     ctx->small_bytes = (size_t)SMALL_TOTAL * sizeof(double);
+    if (const char* po = getenv("BLR_GRAM_PERIOD_OBS")) {
+        const long long v = atoll(po);
+        if (v >= 32) ctx->gram_period_obs = v;
+    }
     if (const char* k = getenv("BLR_GRAM_KT")) {
         if (atoi(k) == 16) ctx->gram_kt = 16;
         if (atoi(k) == 32) ctx->gram_kt = 32;

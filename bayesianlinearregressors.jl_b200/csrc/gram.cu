@@ -132,9 +132,20 @@ struct GramParams {
     double* Pr;   // [nseg][TM]
     const int* cta_seg_begin;  // [grid + 1]
     const int* seg_tile;       // [nseg]
-    const int* seg_g0;         // [nseg] first stage (KT observations each)
-    const int* seg_g1;         // [nseg] one past the last stage
+    const int* seg_g0;         // [nseg] first stage WITHIN a period, 16.16 fixed point (see schedule.h)
+    const int* seg_g1;         // [nseg] one past the last stage within a period, 16.16 fixed point
+    int PS;                    // stages per period: the same cut of the (tile, stage) space is repeated every period,
+    int NP;                    //   so all CTAs sweep the observations together and a period's panels stay L2-resident
+    int n_stages;              // total stages = ceil(N / KT)
+    int fix_bits;              // fractional bits of seg_g0 / seg_g1
+    unsigned int* period_counter;  // soft barrier: number of (CTA, period) pairs whose loads have all been issued
 };
+
+// integer stage of a fixed-point boundary in period `per` (dither θ_per shared by all CTAs, θ_0 = 0)
+__device__ __forceinline__ int sched_stage(int fix, int per, int bits) {
+    const unsigned int theta = per == 0 ? 0u : (((unsigned int)per * 40503u) & 0xffffu) >> (16 - bits);
+    return (int)(((unsigned int)fix + theta) >> bits);
+}
 
 __device__ __forceinline__ void tile_from_index(int idx, int& ti, int& tj) {
     int i = 0;
@@ -230,40 +241,56 @@ __global__ void __launch_bounds__(gk::THREADS, 1) gram_tma_kernel(const GramPara
     if (warp >= CONSUMER_WARPS) {
         // ------------------------------------------------------------ producer warps (TMA): 0 -> panel I + s, 1 -> panel J + t
         const int pw = warp - CONSUMER_WARPS;
-        int it = 0;  // running stage counter of this CTA: ring slot and phase continue across segments
-        for (int sg = seg_begin; sg < seg_end; ++sg) {
-            int ti, tj;
-            tile_from_index(p.seg_tile[sg], ti, tj);
-            const bool diag = (ti == tj);
-            const int i0 = ti * TM, j0 = tj * TM;
-            const int rowsA = min(TM, p.D - i0), rowsB = min(TM, p.D - j0);
-            const int g0 = p.seg_g0[sg], g1 = p.seg_g1[sg];
-            // a tail tile has fewer rows than the previous tenant of the ring slot: stale rows would be read as data
-            const bool narrow = (rowsA < TM) || (!diag && rowsB < TM);
-            for (int gi = g0; gi < g1; ++gi, ++it) {
-                const int stg = it % STAGES;
-                const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-                mbar_wait(smem_u32(&sm.empty[stg]), ph ^ 1u);
-                const int64_t k0 = (int64_t)gi * KT;
-                const int kc = (int)min((int64_t)KT, p.N - k0);
-                Stage& S = sm.st[stg];
-                const uint32_t bar = smem_u32(&sm.full[stg]);
-                if (narrow) {  // rare (only tiles in the last block row when D % 128 != 0): clear my panel first
-                    double* z = pw == 0 ? S.a : S.b;
-                    for (int i = lane; i < KT * LDT; i += 32) z[i] = 0.0;
-                    fence_proxy_async();
-                    __syncwarp();
+        int it = 0;  // running stage counter of this CTA: ring slot and phase continue across segments and periods
+        for (int per = 0; per < p.NP; ++per) {
+            // Soft barrier: nobody starts period `per` before every CTA has issued all loads of period per - 2, which
+            // bounds the skew between CTAs to < 2 periods (the working set the L2 has to hold).  Needs all CTAs
+            // co-resident: the kernel is launched cooperatively with one CTA per SM.
+            if (per >= 2) {
+                if (lane == 0) {
+                    const unsigned int need = (unsigned int)(per - 1) * gridDim.x;
+                    while (*reinterpret_cast<volatile unsigned int*>(p.period_counter) < need) {
+                    }
                 }
-                const bool have_panel = (pw == 0) || !diag;
-                const int rows = pw == 0 ? rowsA : rowsB;
-                if (lane == 0)
-                    mbar_arrive_expect_tx(bar, (have_panel ? (uint32_t)kc * (uint32_t)rows * 8u : 0u) + KT * 8u);
                 __syncwarp();
-                if (have_panel && lane < kc)
-                    bulk_g2s(smem_u32((pw == 0 ? S.a : S.b) + lane * LDT), p.X + (k0 + lane) * p.ld + (pw == 0 ? i0 : j0),
-                             (uint32_t)rows * 8u, bar);
-                if (lane == 0) bulk_g2s(smem_u32(pw == 0 ? S.s : S.t), (pw == 0 ? p.s : p.t) + k0, KT * 8u, bar);
             }
+            const int base = per * p.PS;
+            for (int sg = seg_begin; sg < seg_end; ++sg) {
+                int ti, tj;
+                tile_from_index(p.seg_tile[sg], ti, tj);
+                const bool diag = (ti == tj);
+                const int i0 = ti * TM, j0 = tj * TM;
+                const int rowsA = min(TM, p.D - i0), rowsB = min(TM, p.D - j0);
+                const int g0 = base + sched_stage(p.seg_g0[sg], per, p.fix_bits);
+                const int g1 = min(base + sched_stage(p.seg_g1[sg], per, p.fix_bits), p.n_stages);
+                // a tail tile has fewer rows than the previous tenant of the ring slot: stale rows would be read as data
+                const bool narrow = (rowsA < TM) || (!diag && rowsB < TM);
+                for (int gi = g0; gi < g1; ++gi, ++it) {
+                    const int stg = it % STAGES;
+                    const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+                    mbar_wait(smem_u32(&sm.empty[stg]), ph ^ 1u);
+                    const int64_t k0 = (int64_t)gi * KT;
+                    const int kc = (int)min((int64_t)KT, p.N - k0);
+                    Stage& S = sm.st[stg];
+                    const uint32_t bar = smem_u32(&sm.full[stg]);
+                    if (narrow) {  // rare (only tiles in the last block row when D % 128 != 0): clear my panel first
+                        double* z = pw == 0 ? S.a : S.b;
+                        for (int i = lane; i < KT * LDT; i += 32) z[i] = 0.0;
+                        fence_proxy_async();
+                        __syncwarp();
+                    }
+                    const bool have_panel = (pw == 0) || !diag;
+                    const int rows = pw == 0 ? rowsA : rowsB;
+                    if (lane == 0)
+                        mbar_arrive_expect_tx(bar, (have_panel ? (uint32_t)kc * (uint32_t)rows * 8u : 0u) + KT * 8u);
+                    __syncwarp();
+                    if (have_panel && lane < kc)
+                        bulk_g2s(smem_u32((pw == 0 ? S.a : S.b) + lane * LDT), p.X + (k0 + lane) * p.ld + (pw == 0 ? i0 : j0),
+                                 (uint32_t)rows * 8u, bar);
+                    if (lane == 0) bulk_g2s(smem_u32(pw == 0 ? S.s : S.t), (pw == 0 ? p.s : p.t) + k0, KT * 8u, bar);
+                }
+            }
+            if (pw == 0 && lane == 0) atomicAdd(p.period_counter, 1u);
         }
         return;
     }
@@ -277,28 +304,17 @@ __global__ void __launch_bounds__(gk::THREADS, 1) gram_tma_kernel(const GramPara
     const int dmap = (0x7132'6054 >> (4 * warp)) & 0xf;  // warp 0..7 -> (1,0) (1,1) (0,0) (1,2) (0,2) (0,3) (0,1) (1,3)
     const int wm_dg = dmap >> 2, wn_dg = dmap & 3;
     int it = 0;
-    for (int sg = seg_begin; sg < seg_end; ++sg) {
-        int ti, tj;
-        tile_from_index(p.seg_tile[sg], ti, tj);
-        const bool diag = (ti == tj);
-        const int nst = p.seg_g1[sg] - p.seg_g0[sg];
-        const int wm = diag ? wm_dg : wm_off, wn = diag ? wn_dg : wn_off;
-        const int thr = wn * 4 - wm * 8;  // sub-tile (mi, ni) needed iff mi - ni >= thr
-        double acc[8][4][2];
+    // A CTA with a single segment keeps its tile in registers across all periods and flushes once; a CTA that
+    // switches tiles parks the partial tile in its workspace slot at every switch (first period: store, later: add).
+    const bool single = (seg_end - seg_begin) == 1;
+    double acc[8][4][2];
 #pragma unroll
-        for (int mi = 0; mi < 8; ++mi)
+    for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-        double racc = 0.0;
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    double racc = 0.0;
 
-        // warp-uniform dispatch to a fully unrolled, unpredicated instruction stream
-        if (!diag) run_segment<0, KT, STAGES>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
-        else if (thr <= -3) run_segment<1, KT, STAGES>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
-        else if (thr == 0) run_segment<2, KT, STAGES>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
-        else if (thr == 4) run_segment<3, KT, STAGES>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
-        else run_segment<4, KT, STAGES>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
-
-        // ------------------------------------------------------------ segment epilogue: partial tile -> its slot
+    auto flush = [&](int sg, bool diag, int wm, int wn, int thr, bool add) {
         double* Pt = p.P + (int64_t)sg * (TM * TM);
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi) {
@@ -306,16 +322,62 @@ __global__ void __launch_bounds__(gk::THREADS, 1) gram_tma_kernel(const GramPara
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni) {
                 const int col = wn * 32 + ni * 8 + kq * 2;
-                if (!diag || (mi - ni) >= thr)
-                    *reinterpret_cast<double2*>(Pt + row * TM + col) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+                if (!diag || (mi - ni) >= thr) {
+                    double2* dst = reinterpret_cast<double2*>(Pt + row * TM + col);
+                    double2 v = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+                    if (add) {
+                        const double2 o = *dst;
+                        v.x += o.x;
+                        v.y += o.y;
+                    }
+                    *dst = v;
+                }
             }
         }
         if (diag) {
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // rred may still be read by the previous segment
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // rred may still be read by the previous flush
             if (rhalf == 1) sm.rred[rm] = racc;
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (rhalf == 0) p.Pr[(int64_t)sg * TM + rm] = racc + sm.rred[rm];
+            if (rhalf == 0) {
+                double* dst = p.Pr + (int64_t)sg * TM + rm;
+                *dst = (add ? *dst : 0.0) + (racc + sm.rred[rm]);
+            }
         }
+    };
+
+    for (int per = 0; per < p.NP; ++per) {
+        const int base = per * p.PS;
+        for (int sg = seg_begin; sg < seg_end; ++sg) {
+            int ti, tj;
+            tile_from_index(p.seg_tile[sg], ti, tj);
+            const bool diag = (ti == tj);
+            const int nst = max(0, min(base + sched_stage(p.seg_g1[sg], per, p.fix_bits), p.n_stages) - (base + sched_stage(p.seg_g0[sg], per, p.fix_bits)));
+            const int wm = diag ? wm_dg : wm_off, wn = diag ? wn_dg : wn_off;
+            const int thr = wn * 4 - wm * 8;  // sub-tile (mi, ni) needed iff mi - ni >= thr
+
+            // warp-uniform dispatch to a fully unrolled, unpredicated instruction stream
+            if (!diag) run_segment<0, KT, STAGES>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
+            else if (thr <= -3) run_segment<1, KT, STAGES>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
+            else if (thr == 0) run_segment<2, KT, STAGES>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
+            else if (thr == 4) run_segment<3, KT, STAGES>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
+            else run_segment<4, KT, STAGES>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
+
+            if (!single) {
+                flush(sg, diag, wm, wn, thr, per > 0);
+#pragma unroll
+                for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+                racc = 0.0;
+            }
+        }
+    }
+    if (single) {
+        int ti, tj;
+        tile_from_index(p.seg_tile[seg_begin], ti, tj);
+        const bool diag = (ti == tj);
+        const int wm = diag ? wm_dg : wm_off, wn = diag ? wn_dg : wn_off;
+        flush(seg_begin, diag, wm, wn, wn * 4 - wm * 8, false);
     }
 }
 
@@ -491,10 +553,18 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
         const int nt = (D + TS - 1) / TS;
         const int64_t n_stages = (N + KT - 1) / KT;
         const int G = ctx->sm_count;
-        if (ctx->sched_key[0] != nt || ctx->sched_key[1] != n_stages || ctx->sched_key[2] != G ||
-            ctx->sched_key[3] != ctx->diag_weight) {  // n_stages encodes KT for a given N
+        // Periods are OPT-IN (BLR_GRAM_PERIOD_OBS): repeating the cut every ~32 MB of X keeps a period's panels
+        // L2-resident (DRAM traffic ~1x instead of ~8x at D = 1024) but the lockstep costs 8-18 % throughput on B200
+        // (measured), and HBM is nowhere near its limit -- so the default is one period.
+        const int64_t period_obs = ctx->gram_period_obs > 0 ? ctx->gram_period_obs : INT64_MAX / 4;
+        int64_t PS = std::max<int64_t>(1, period_obs / KT);
+        if (n_stages <= PS + PS / 2) PS = n_stages;  // short inputs: one period (plain stream-K)
+        const int64_t NP = (n_stages + PS - 1) / PS;
+        const int64_t flush_cost = NP > 1 ? gk::W_OFF / 2 : 0;  // ~half a stage per tile switch
+        if (ctx->sched_key[0] != nt || ctx->sched_key[1] != PS || ctx->sched_key[2] != G ||
+            ctx->sched_key[3] != ctx->diag_weight * 1000 + flush_cost) {
             Schedule sc;
-            build_schedule(sc, nt, n_stages, G, ctx->diag_weight);
+            build_schedule(sc, nt, PS, G, ctx->diag_weight, flush_cost);
             const size_t bytes = sc.table.size() * sizeof(int);
             if (ctx->sched_bytes < bytes) {
                 BLR_CUDA_OK(ctx, cudaStreamSynchronize(sm));
@@ -507,9 +577,9 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
             BLR_CUDA_OK(ctx, cudaMemcpyAsync(ctx->sched, sc.table.data(), bytes, cudaMemcpyHostToDevice, sm));
             BLR_CUDA_OK(ctx, cudaStreamSynchronize(sm));  // the host vector dies at the end of this scope
             ctx->sched_key[0] = nt;
-            ctx->sched_key[1] = n_stages;
+            ctx->sched_key[1] = PS;
             ctx->sched_key[2] = G;
-            ctx->sched_key[3] = ctx->diag_weight;
+            ctx->sched_key[3] = ctx->diag_weight * 1000 + flush_cost;
             ctx->sched_T = sc.T;
             ctx->sched_nseg = sc.nseg;
         }
@@ -530,16 +600,26 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
         gp.seg_tile = tile_slot_begin + (T + 1);
         gp.seg_g0 = gp.seg_tile + nseg;
         gp.seg_g1 = gp.seg_g0 + nseg;
+        gp.PS = (int)PS;
+        gp.NP = (int)NP;
+        gp.n_stages = (int)n_stages;
+        gp.fix_bits = sched_fix_bits(PS);
+        gp.period_counter = reinterpret_cast<unsigned int*>(ctx->d_flags + PERIOD_COUNTER_SLOT);
+        BLR_CUDA_OK(ctx, cudaMemsetAsync(gp.period_counter, 0, sizeof(unsigned int), sm));
+        void* args[] = {(void*)&gp};
+        // cooperative launch: the soft barrier between periods needs every CTA resident (grid = #SMs, 1 CTA / SM)
         if (KT == 32) {
             using SM = gk::Smem<32, 3>;
             BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_tma_kernel<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   (int)sizeof(SM)));
-            gram_tma_kernel<32, 3><<<G, gk::THREADS, sizeof(SM), sm>>>(gp);
+            BLR_CUDA_OK(ctx, cudaLaunchCooperativeKernel((void*)gram_tma_kernel<32, 3>, dim3(G), dim3(gk::THREADS), args,
+                                                         sizeof(SM), sm));
         } else {
             using SM = gk::Smem<16, 4>;
             BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_tma_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   (int)sizeof(SM)));
-            gram_tma_kernel<16, 4><<<G, gk::THREADS, sizeof(SM), sm>>>(gp);
+            BLR_CUDA_OK(ctx, cudaLaunchCooperativeKernel((void*)gram_tma_kernel<16, 4>, dim3(G), dim3(gk::THREADS), args,
+                                                         sizeof(SM), sm));
         }
         BLR_CHECK_LAUNCH(ctx, "gram_tma_kernel");
         BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], sm));

@@ -64,6 +64,7 @@ struct blr_ctx {
     size_t sched_bytes = 0;
     int64_t sched_key[4] = {-1, -1, -1, -1};
     int sched_T = 0, sched_nseg = 0;
+    int64_t gram_period_obs = 0;  // observations per L2 period of the Gram kernel (0 = single period; BLR_GRAM_PERIOD_OBS)
     int gram_kt = 32;      // observations per pipeline stage of the Gram kernel: 16 or 32 (BLR_GRAM_KT)
     int diag_weight = 40;  // cost of a diagonal-tile stage relative to W_OFF = 64 (BLR_DIAG_WEIGHT overrides)
     // host-streaming path (blr_stats_accumulate_host): copy stream, two staging slots
@@ -79,6 +80,7 @@ struct blr_ctx {
 namespace blr {
 
 // layout of blr_ctx::small (doubles)
+constexpr int PERIOD_COUNTER_SLOT = 448;  // index into blr_ctx::d_flags (wavefront flags use < 256)
 constexpr int SMALL_PREP = 0;        // prep-kernel block partials (2 per block, <= 4096)
 constexpr int SMALL_SC = 4096;       // scalars
 constexpr int SMALL_VEC = 16384;     // capacity of each D-vector slot (max supported D)

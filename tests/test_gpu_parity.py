@@ -103,6 +103,27 @@ def test_statistics_bit_reproducible():
     assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
 
 
+@pytest.mark.parametrize("D,N,period", [(256, 20011, 512), (384, 9000, 256), (1024, 6000, 128), (130, 5000, 64)])
+def test_periodic_schedule_many_periods(D, N, period, monkeypatch):
+    """The Gram kernel repeats its stream-K cut every `period` observations (soft barrier between periods, partial
+    tiles parked in the workspace by CTAs that switch tiles).  Force tiny periods so that many of them, the
+    read-modify-write flushes and the partial last period are all exercised at test sizes."""
+    X, mw, _, σ2, y = problem(D, N, seed=D + period)
+    monkeypatch.setenv("BLR_GRAM_PERIOD_OBS", str(period))
+    ctx = blr.Context(0)  # reads the environment at creation
+    monkeypatch.delenv("BLR_GRAM_PERIOD_OBS")
+    f = blr.BayesianLinearRegressor(mw, blr.Diagonal(np.ones(D)))
+    fx = f(blr.ColVecs(X), σ2)
+    fx.ctx = ctx
+    post, lp = blr.posterior_and_logpdf(fx, y)
+    fxo = ref.BayesianLinearRegressor(mw, ref.Diagonal(np.ones(D)))(ref.ColVecs(X), σ2)
+    assert abs(lp - ref.logpdf(fxo, y)) <= RTOL * abs(lp)
+    po = ref.posterior(fxo, y)
+    assert relerr(post.mw, po.mw) < RTOL and relerr(post.Λw.dense(), ref.dense(po.Λw)) < RTOL
+    post2, lp2 = blr.posterior_and_logpdf(fx, y)  # bit-reproducible
+    assert lp2 == lp and np.array_equal(post.mw, post2.mw)
+
+
 # ------------------------------------------------------------------------------------------------ posterior + logpdf
 INFER_CASES = [
     # D, N, dense prior, zero mean, scalar noise

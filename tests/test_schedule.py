@@ -33,3 +33,17 @@ def test_schedule_properties(exe, nt, n_stages, G, wd):
     total = n_stages * (nt * wd + (T - nt) * 64)
     # no CTA carries more than its fair share plus one stage of the heaviest tile per segment boundary
     assert int(mx) <= total // G + 2 * 64 + 1
+
+
+@pytest.mark.parametrize("nt,n_stages,G,wd,flush", [(8, 128, 148, 40, 32), (2, 512, 148, 40, 32), (32, 32, 148, 40, 48), (3, 5, 148, 64, 32),
+                                                    (8, 96, 132, 44, 64)])
+def test_schedule_with_flush_cost(exe, nt, n_stages, G, wd, flush):
+    """Periodic variant: multi-segment CTAs are charged a flush per segment; coverage / order invariants still hold
+    and the heaviest CTA (work + flushes) stays within a few stages of the mean."""
+    res = subprocess.run([exe, str(nt), str(n_stages), str(G), str(wd), str(flush)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout
+    tag, nseg, mx, mn = res.stdout.split()
+    assert tag == "ok"
+    T = nt * (nt + 1) // 2
+    total = n_stages * (nt * wd + (T - nt) * 64)
+    assert int(mx) <= total // G + flush * (T // G + 3) + 3 * 64

@@ -69,6 +69,14 @@ print(json.dumps(c.calibrate()))
         done
       done 2>&1 | tee "$OUT/kt_sweep.log"
       BLR_GRAM_KT=32 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "statistics or posterior_and_logpdf" > "$OUT/tests_kt32.log" 2>&1; tail -3 "$OUT/tests_kt32.log";;
+    period_sweep)
+      for po in 0 2048 4096 8192 1000000000; do
+        for cfg in "--n-obs 1048576 --dim 256" "--n-obs 2097152 --dim 1024"; do
+          echo "PERIOD_OBS=$po cfg=$cfg"
+          BLR_GRAM_PERIOD_OBS=$po timeout 600 python bench.py $cfg --steps 5 --warmup 3 --no-cpu --no-e2e --no-calibrate 2>> "$OUT/period.err" \
+            | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['achieved'], d['clocks'].get('power_w_max'))"
+        done
+      done 2>&1 | tee "$OUT/period_sweep.log";;
     dmma_probe)
       timeout 300 python -c "
 import blr_b200 as b, ctypes as C
