@@ -959,6 +959,11 @@ int blr_calibrate_dmma_cfg(blr_ctx* ctx, int warps_per_sm, int n_acc, double* tf
     if (!tflops_out) return BLR_E_INVALID;
     return calib_dmma_cfg(ctx, warps_per_sm, n_acc, tflops_out);
 }
+int blr_calibrate_mixed(blr_ctx* ctx, double* tflops2_out) {
+    CTX_ENTER(ctx);
+    if (!tflops2_out) return BLR_E_INVALID;
+    return calib_mixed(ctx, tflops2_out);
+}
 int blr_calibrate_dfma(blr_ctx* ctx, double* tflops_out) {
     CTX_ENTER(ctx);
     if (!tflops_out) return BLR_E_INVALID;

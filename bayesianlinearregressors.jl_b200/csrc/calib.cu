@@ -119,6 +119,47 @@ int calib_dmma_cfg(blr_ctx* ctx, int warps, int nacc, double* tflops) {
     return 0;
 }
 
+// Are DMMA and DFMA separate pipes?  Half of the warps of every SM run the DMMA loop, the other half a DFMA loop.
+__global__ void __launch_bounds__(CAL_THREADS) calib_mixed_kernel(double* __restrict__ out, int iters, double seed) {
+    const int warp = threadIdx.x >> 5;
+    const double a = seed + threadIdx.x * 1e-9, b = seed * 0.5;
+    double s = 0.0;
+    if ((warp >> 2) & 1) {  // warps 4-7, 12-15: one per SM sub-partition each
+        double c[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = i;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) c[i] = fma(a, c[i], b);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += c[i];
+    } else {
+        double c[CAL_ACC][2];
+#pragma unroll
+        for (int i = 0; i < CAL_ACC; ++i) c[i][0] = c[i][1] = 0.0;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < CAL_ACC; ++i) dmma884(c[i], a, b);
+        }
+#pragma unroll
+        for (int i = 0; i < CAL_ACC; ++i) s += c[i][0] + c[i][1];
+    }
+    out[(int64_t)blockIdx.x * CAL_THREADS + threadIdx.x] = s;
+}
+
+// returns the time of the mixed kernel in ms via tflops[0] = DMMA-only-equivalent TF/s, tflops[1] = DFMA TF/s
+int calib_mixed(blr_ctx* ctx, double* tflops2) {
+    const int blocks = ctx->sm_count, iters = 20000;
+    BLR_TRY(ensure_ws(ctx, (size_t)blocks * CAL_THREADS * sizeof(double)));
+    float ms;
+    BLR_TRY(time_best(ctx, 3, [&] { calib_mixed_kernel<<<blocks, CAL_THREADS, 0, ctx->stream>>>(ctx->ws, iters, 1.0); }, &ms));
+    const double warps_each = (double)blocks * (CAL_THREADS / 64);
+    tflops2[0] = warps_each * iters * CAL_ACC * 512.0 / (ms * 1e-3) / 1e12;
+    tflops2[1] = warps_each * 32.0 * iters * 16 * 2.0 / (ms * 1e-3) / 1e12;
+    return 0;
+}
+
 int calib_dfma(blr_ctx* ctx, double* tflops) {
     const int blocks = ctx->sm_count * 2, iters = 20000;
     BLR_TRY(ensure_ws(ctx, (size_t)blocks * CAL_THREADS * sizeof(double)));

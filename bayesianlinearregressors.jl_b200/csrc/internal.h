@@ -170,6 +170,7 @@ int transpose_to_colvecs(blr_ctx* ctx, const blr_x* x, double* out, int64_t ldo)
 // ---- calib.cu
 int calib_dmma(blr_ctx* ctx, double* tflops);
 int calib_dfma(blr_ctx* ctx, double* tflops);
+int calib_mixed(blr_ctx* ctx, double* tflops2);
 int calib_dmma_cfg(blr_ctx* ctx, int warps, int nacc, double* tflops);
 int calib_hbm(blr_ctx* ctx, double* gbs);
 

@@ -263,8 +263,11 @@ def _infer(fx: FiniteGP, y, want_logpdf: bool, want_post: bool):
     return (lp.value if want_logpdf else None), post
 
 
-def logpdf(fx: FiniteGP, y) -> float:
-    """src/bayesian_linear_regression.jl:55-58 / basis_function_regression.jl:60."""
+def logpdf(fx: FiniteGP, y):
+    """src/bayesian_linear_regression.jl:55-58 / basis_function_regression.jl:60.  A matrix `Y` (N x k, one
+    observation vector per column) returns the k log densities, as AbstractGPs' `logpdf(fx, Y::AbstractMatrix)`."""
+    if isinstance(y, np.ndarray) and y.ndim == 2:
+        return np.array([_infer(fx, np.ascontiguousarray(y[:, j]), True, False)[0] for j in range(y.shape[1])])
     return _infer(fx, y, True, False)[0]
 
 
@@ -449,6 +452,8 @@ def rand(rng, target, *dims):
 
     `rng` is a numpy Generator (draws Zw = randn(D, S) FIRST, then Zy = randn(N, S), as :51-52) or a DeviceRNG.
     """
+    if rng is None:  # Julia's `rand(fx)` / `rand(b)`: the global default RNG
+        rng = np.random.default_rng()
     if isinstance(target, FiniteGP):
         S = int(dims[0]) if dims else 1
         Y = _rand_finite(rng, target, S)

@@ -52,6 +52,9 @@ def test_public_interface_consistency(Tx):
     assert Y.shape == (N, 4) and blr.rand(rng, fx).shape == (N,)
     lp = blr.logpdf(fx, Y[:, 0])
     assert isinstance(lp, float) and np.isfinite(lp)
+    lps = blr.logpdf(fx, Y)  # logpdf(fx, Y::Matrix) of AbstractGPs: one density per column
+    assert lps.shape == (4,) and lps[0] == lp
+    assert blr.rand(None, fx).shape == (N,)  # rand(fx) with the default RNG
     assert isinstance(blr.posterior(fx, Y[:, 0]), blr.BayesianLinearRegressor)
 
 
