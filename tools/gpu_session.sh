@@ -77,6 +77,10 @@ print(json.dumps(c.calibrate()))
             | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['achieved'], d['clocks'].get('power_w_max'))"
         done
       done 2>&1 | tee "$OUT/period_sweep.log";;
+    rff_multi)
+      NG=$(nvidia-smi -L | wc -l)
+      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533 \
+        tools/bench_rff.py > "$OUT/rff_g$NG.json" 2> "$OUT/rff_g$NG.err"; echo "rff exit $?"; cat "$OUT/rff_g$NG.json"; tail -3 "$OUT/rff_g$NG.err";;
     dmma_probe)
       timeout 300 python -c "
 import blr_b200 as b, ctypes as C
