@@ -301,7 +301,7 @@ def run_e2e(args, ctx, blr, torch, rank, world):
     from blr_b200.runtime import make_noise
 
     D = args.dim
-    n_host = args.e2e_obs // world  # observations resident in this rank's pinned host buffer
+    n_host = args.e2e_obs  # observations resident in EACH rank's pinned host buffer (every GPU has its own PCIe link)
     chunk = min(args.e2e_chunk, n_host)
     Xh = torch.empty((n_host, D), dtype=torch.float64, pin_memory=True)  # = column-major D x n_host
     yh = torch.empty(n_host, dtype=torch.float64, pin_memory=True)
