@@ -44,6 +44,8 @@ SIGNATURES = {
     "blr_ctx_stream": (C.c_int, [C.c_void_p, c_void_pp]),
     "blr_launch_count": (C.c_int64, [C.c_void_p]),
     "blr_last_timings": (C.c_int, [C.c_void_p, c_double_p]),
+    "blr_host_alloc": (C.c_int, [C.c_void_p, C.c_int64, c_void_pp]),
+    "blr_host_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "blr_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "blr_comm_init_rank": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "blr_comm_destroy": (C.c_int, [C.c_void_p]),

@@ -284,6 +284,20 @@ int blr_last_timings(blr_ctx* ctx, double* out8) {
     return 0;
 }
 
+int blr_host_alloc(blr_ctx* ctx, int64_t bytes, void** out) {
+    CTX_ENTER(ctx);
+    if (!out || bytes < 0) return BLR_E_INVALID;
+    *out = nullptr;
+    BLR_CUDA_OK(ctx, cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 8), cudaHostAllocDefault));
+    return 0;
+}
+int blr_host_free(blr_ctx* ctx, void* p) {
+    if (!p) return 0;
+    if (ctx) cudaSetDevice(ctx->device);
+    cudaFreeHost(p);
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------- NCCL
 int blr_nccl_unique_id(void* out128) {
     NcclApi* a = nccl_api();
@@ -341,10 +355,11 @@ int blr_x_alloc(blr_ctx* ctx, int64_t D, int64_t N, int layout, blr_x** out) {
     x->ld = ld;
     x->layout = layout;
     x->owned = true;
-    cudaError_t e = cudaMalloc(&x->p, std::max<size_t>((size_t)ld * cols * sizeof(double), 16));
+    // stream-ordered pool: a feature map re-evaluated per call (blr_x_rff) must not pay cudaMalloc / cudaFree each time
+    cudaError_t e = dev_alloc(ctx, &x->p, (size_t)ld * cols * sizeof(double));
     if (e != cudaSuccess) {
         delete x;
-        return cuda_fail(ctx, e, "cudaMalloc(X)");
+        return cuda_fail(ctx, e, "cudaMallocAsync(X)");
     }
     *out = x;
     return 0;
@@ -395,8 +410,10 @@ int blr_x_free(blr_ctx* ctx, blr_x* x) {
     if (!x) return 0;
     if (ctx) cudaSetDevice(ctx->device);
     if (x->owned && x->p) {
-        if (ctx && ctx->stream) cudaStreamSynchronize(ctx->stream);
-        cudaFree(x->p);
+        if (ctx && ctx->stream)
+            dev_free(ctx->stream, x->p);
+        else
+            cudaFree(x->p);
     }
     delete x;
     return 0;
@@ -408,10 +425,10 @@ int blr_vec_alloc(blr_ctx* ctx, int64_t n, blr_vec** out) {
     blr_vec* v = new blr_vec();
     v->n = n;
     v->owned = true;
-    cudaError_t e = cudaMalloc(&v->p, std::max<size_t>((size_t)n * sizeof(double), 16));
+    cudaError_t e = dev_alloc(ctx, &v->p, (size_t)n * sizeof(double));
     if (e != cudaSuccess) {
         delete v;
-        return cuda_fail(ctx, e, "cudaMalloc(vec)");
+        return cuda_fail(ctx, e, "cudaMallocAsync(vec)");
     }
     *out = v;
     return 0;
@@ -458,8 +475,10 @@ int blr_vec_free(blr_ctx* ctx, blr_vec* v) {
     if (!v) return 0;
     if (ctx) cudaSetDevice(ctx->device);
     if (v->owned && v->p) {
-        if (ctx && ctx->stream) cudaStreamSynchronize(ctx->stream);
-        cudaFree(v->p);
+        if (ctx && ctx->stream)
+            dev_free(ctx->stream, v->p);
+        else
+            cudaFree(v->p);
     }
     delete v;
     return 0;
@@ -492,14 +511,13 @@ int blr_x_rff(blr_ctx* ctx, const blr_x* xin, const double* W, const double* b, 
     double *Wd = nullptr, *bd = nullptr;
     blr_x* phi = nullptr;
     BLR_TRY(blr_x_alloc(ctx, D, xin->N, BLR_COLVECS, &phi));
-    cudaError_t e = cudaMalloc(&Wd, (size_t)D * din * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&bd, (size_t)D * sizeof(double));
+    cudaError_t e = dev_alloc(ctx, &Wd, (size_t)D * din * sizeof(double));
+    if (e == cudaSuccess) e = dev_alloc(ctx, &bd, (size_t)D * sizeof(double));
     if (e == cudaSuccess) e = cudaMemcpyAsync(Wd, W, (size_t)D * din * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(bd, b, (size_t)D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
     int rc = (e == cudaSuccess) ? rff_features(ctx, xin, Wd, bd, D, phi->p, phi->ld) : cuda_fail(ctx, e, "rff upload");
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(Wd);
-    cudaFree(bd);
+    dev_free(ctx->stream, Wd);
+    dev_free(ctx->stream, bd);
     if (rc != 0) {
         blr_x_free(ctx, phi);
         return rc;

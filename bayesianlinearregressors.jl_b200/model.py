@@ -249,8 +249,8 @@ def _infer(fx: FiniteGP, y, want_logpdf: bool, want_post: bool):
     prior, keep_prior = blr._prior_struct()
     lp = C.c_double()
     m_post = np.empty(D) if want_post else None
-    Λ_post = np.empty((D, D), order="F") if want_post else None
-    T_post = np.empty((D, D), order="F") if (want_post and isinstance(blr.Λw, PDMat)) else None
+    Λ_post = ctx.empty_pinned((D, D)) if want_post else None
+    T_post = ctx.empty_pinned((D, D)) if (want_post and isinstance(blr.Λw, PDMat)) else None
     h = C.c_void_p()
     ctx.check(
         ctx.lib.blr_infer(ctx.handle, C.byref(prior), X.handle, yv.handle, C.byref(noise),
@@ -320,8 +320,8 @@ def posterior_and_logpdf_streamed(f: BayesianLinearRegressor, X, y, Σy, chunk: 
     st.allreduce()
     prior, keep = f._prior_struct()
     lp = C.c_double()
-    m_post, Λ_post = np.empty(D), np.empty((D, D), order="F")
-    T_post = np.empty((D, D), order="F") if isinstance(f.Λw, PDMat) else None
+    m_post, Λ_post = np.empty(D), ctx.empty_pinned((D, D))
+    T_post = ctx.empty_pinned((D, D)) if isinstance(f.Λw, PDMat) else None
     h = C.c_void_p()
     ctx.check(ctx.lib.blr_infer_from_stats(ctx.handle, C.byref(prior), st.handle, C.byref(lp), _ptr(m_post), _ptr(T_post),
                                            _ptr(Λ_post), C.byref(h)))
@@ -340,8 +340,8 @@ def _predict(fx: FiniteGP, want_mean: bool, want_var: bool):
         raise L.BLRError(L.E_INVALID, "size(X, 1) != length(mw)")
     post = fx.f._device(ctx)
     noise, keep = make_noise(ctx, fx.Σy, X.N)
-    m = np.empty(X.N) if want_mean else None
-    v = np.empty(X.N) if want_var else None
+    m = ctx.empty_pinned((X.N,)) if want_mean else None
+    v = ctx.empty_pinned((X.N,)) if want_var else None
     ctx.check(ctx.lib.blr_mean_var(ctx.handle, post.handle, X.handle, C.byref(noise), _ptr(m), _ptr(v)))
     return m, v
 
@@ -500,7 +500,7 @@ def _rand_finite(rng, fx: FiniteGP, S: int, Zw=None, Zy=None) -> np.ndarray:
         Zw = _f64(np.asarray(Zw, dtype=np.float64).reshape(D, S), "F")
     if Zy is not None:
         Zy = _f64(np.asarray(Zy, dtype=np.float64).reshape(X.N, S), "F")
-    Y = np.empty((X.N, S), order="F")
+    Y = ctx.empty_pinned((X.N, S))
     ctx.check(ctx.lib.blr_rand_finite(ctx.handle, post.handle, X.handle, C.byref(noise), S, _ptr(Zw), _ptr(Zy), seed, _ptr(Y)))
     return Y
 

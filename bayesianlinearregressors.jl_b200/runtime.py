@@ -39,7 +39,28 @@ class Context:
         self.handle = h
         self.device = int(device)
         self.rank, self.world = 0, 1
+        self._pinned_free, self._pinned_all = {}, []
         self._fin = weakref.finalize(self, self.lib.blr_ctx_destroy, h)
+
+    # ---- pinned result buffers ---------------------------------------------------------------------
+    def empty_pinned(self, shape, order="F") -> np.ndarray:
+        """np.empty in page-locked memory (large results download at PCIe speed).  Buffers are recycled through a
+        per-context free list once every numpy view of them is gone; small results stay pageable."""
+        n = int(np.prod(shape))
+        nbytes = n * 8
+        if nbytes < (1 << 20):
+            return np.empty(shape, dtype=np.float64, order=order)
+        free = self._pinned_free.setdefault(nbytes, [])
+        if free:
+            ptr = free.pop()
+        else:
+            out = C.c_void_p()
+            self.check(self.lib.blr_host_alloc(self.handle, nbytes, C.byref(out)))
+            ptr = out.value
+            self._pinned_all.append(ptr)
+        buf = (C.c_char * nbytes).from_address(ptr)
+        weakref.finalize(buf, free.append, ptr)  # back to the free list when the last view dies
+        return np.frombuffer(buf, dtype=np.float64).reshape(shape, order=order)
 
     # ---- error mapping -------------------------------------------------------------------------
     def check(self, rc: int):

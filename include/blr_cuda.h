@@ -85,6 +85,10 @@ int64_t blr_launch_count(const blr_ctx* ctx);
  * out[0]=prep (δ, 1/σ²), out[1]=Gram kernel, out[2]=split reduce, out[3]=factorise+solve, out[4..7]=0. */
 int blr_last_timings(blr_ctx* ctx, double* out8);
 
+/* Page-locked host memory for result buffers (D2H at PCIe speed instead of through the driver's pageable staging). */
+int blr_host_alloc(blr_ctx* ctx, int64_t bytes, void** out);
+int blr_host_free(blr_ctx* ctx, void* p);
+
 /* ------------------------------------------------------------------ multi-GPU (N-sharded observations)
  * One rank per GPU; the only exchange of the path is one sum-allreduce of the packed statistics
  * (SURVEY.md section 8e).  NCCL is dlopen'ed on first use. */
