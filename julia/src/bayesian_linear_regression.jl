@@ -30,9 +30,14 @@ end
 function _infer(fx::FiniteBLR, y::AbstractVector{<:Real}; want_T::Bool)
     ctx = LibBLR.default_context()
     length(y) == length(fx.x) || throw(error("length(y) != size(fx.x.X, 2)"))            # :74
-    x = _device_x(ctx, fx.x)
-    yv = LibBLR.upload_vec(ctx, collect(Float64, y))
     prior, keep1 = _prior(fx.f)
+    if fx.Σy isa Diagonal && fx.x isa Union{ColVecs,RowVecs} && fx.x.X isa StridedMatrix{Float64}
+        # host arrays are streamed to the device in chunks (PCIe overlapped with the Gram kernel); no second copy of X
+        return GC.@preserve keep1 LibBLR.infer_host(ctx, prior, fx.x.X, fx.x isa ColVecs ? LibBLR.COLVECS : LibBLR.ROWVECS,
+                                                    collect(Float64, y), fx.Σy; want_T=want_T)
+    end
+    x = _device_x(ctx, fx.x)                                                              # dense Σy, lazy / non-strided inputs
+    yv = LibBLR.upload_vec(ctx, collect(Float64, y))
     noise, keep2 = _noise(ctx, fx.Σy)
     GC.@preserve keep1 keep2 x yv LibBLR.infer(ctx, prior, x, yv, noise; want_T=want_T)
 end

@@ -107,6 +107,37 @@ function infer(ctx::Context, prior::Prior, x::DeviceX, y::DeviceVec, noise::Nois
     return lp[], m, Λ, T, _post(ctx, h[])
 end
 
+# the same from host arrays: blr_stats_create -> blr_stats_accumulate_host -> blr_stats_allreduce -> blr_infer_from_stats
+function infer_host(ctx::Context, prior::Prior, X::StridedMatrix{Float64}, layout::Cint, y::Vector{Float64}, Σy;
+                    want_T::Bool=false, chunk::Integer=1 << 16)
+    D, N = layout == COLVECS ? size(X) : reverse(size(X))
+    st = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx, ccall((:blr_stats_create, libblr), Cint, (Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}), ctx.ptr, D, st))
+    try
+        d = Σy.diag
+        scalar = d isa FillArrays.Fill
+        σ² = scalar ? Float64[] : collect(Float64, d)
+        mw = unsafe_wrap(Array, prior.mw, D)
+        GC.@preserve X y σ² check(ctx, ccall((:blr_stats_accumulate_host, libblr), Cint,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Int64, Cint, Ptr{Float64}, Cint, Float64,
+             Ptr{Float64}, Int64),
+            ctx.ptr, st[], mw, X, D, N, stride(X, 2), layout, y, scalar ? NOISE_SCALAR : NOISE_VECTOR,
+            scalar ? Float64(first(d)) : 0.0, scalar ? C_NULL : pointer(σ²), chunk))
+        check(ctx, ccall((:blr_stats_allreduce, libblr), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.ptr, st[]))
+        lp = Ref{Float64}(NaN)
+        m = Vector{Float64}(undef, D)
+        Λ = Matrix{Float64}(undef, D, D)
+        T = want_T ? Matrix{Float64}(undef, D, D) : nothing
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ctx, ccall((:blr_infer_from_stats, libblr), Cint,
+            (Ptr{Cvoid}, Ref{Prior}, Ptr{Cvoid}, Ref{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Ptr{Cvoid}}),
+            ctx.ptr, prior, st[], lp, m, want_T ? T : C_NULL, Λ, h))
+        return lp[], m, Λ, T, _post(ctx, h[])
+    finally
+        ccall((:blr_stats_free, libblr), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.ptr, st[])
+    end
+end
+
 function post_create(ctx::Context, prior::Prior, D::Integer)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ctx, ccall((:blr_post_create, libblr), Cint, (Ptr{Cvoid}, Ref{Prior}, Int64, Ref{Ptr{Cvoid}}),
