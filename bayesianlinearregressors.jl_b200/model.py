@@ -241,6 +241,12 @@ def _infer(fx: FiniteGP, y, want_logpdf: bool, want_post: bool):
     ctx = fx._context()
     blr = fx.f
     D = blr.mw.shape[0]
+    if isinstance(fx.x, (ColVecs, RowVecs)) and isinstance(fx.x.X, np.ndarray) and fx.x.X.ndim == 2 and not isinstance(y, DeviceVector) \
+            and not _is_torch_cuda(y):
+        layout = L.COLVECS if isinstance(fx.x, ColVecs) else L.ROWVECS
+        hn = _host_noise(fx.Σy, len(fx.x))
+        if hn is not None:  # host data + diagonal noise: stream it (no staging copy of X on the device)
+            return _infer_host(ctx, blr, fx.x.X, layout, y, hn, 1 << 16, want_logpdf, want_post)
     X = x_as_colvecs(ctx, fx.x)
     yv = _as_device_vector(ctx, y)
     if yv.n != X.N:  # src/bayesian_linear_regression.jl:74
@@ -288,45 +294,68 @@ def posterior_and_logpdf(fx: FiniteGP, y):
     return post, lp
 
 
-def posterior_and_logpdf_streamed(f: BayesianLinearRegressor, X, y, Σy, chunk: int = 1 << 16, ctx: Optional[Context] = None,
-                                  layout: int = L.COLVECS):
-    """posterior + logpdf for HOST arrays too large (or too transient) to keep on the device: the observations
-    are streamed through blr_stats_accumulate_host in chunks (H2D overlapped with the Gram kernel), then one
-    allreduce + replicated solve.  X is the D x N matrix (ColVecs; Fortran order is sent without a copy) or the
-    N x D matrix with layout=ROWVECS.  Returns (posterior, logpdf)."""
-    ctx = ctx or default_context()
+def _host_noise(Σy, N: int):
+    """-> (kind, scalar, vector-or-None) for scalar / diagonal host noise, or None if Σy is anything else."""
+    if isinstance(Σy, Diagonal):
+        Σy = Σy.diag
+    if isinstance(Σy, (DeviceVector, Symmetric, PDMat)) or _is_torch_cuda(Σy):
+        return None
+    s2 = np.asarray(Σy, dtype=np.float64)
+    if s2.ndim == 0:
+        return L.NOISE_SCALAR, float(s2), None
+    if s2.ndim == 1:
+        if s2.shape[0] != N:
+            raise L.DimensionMismatch(L.E_DIM, "length(diag(Σy)) != number of inputs")
+        return L.NOISE_VECTOR, 0.0, _f64(s2)
+    return None
+
+
+def _infer_host(ctx: Context, f: BayesianLinearRegressor, X, layout: int, y, noise, chunk: int, want_logpdf: bool,
+                want_post: bool):
+    """Inference from HOST arrays: the observations are streamed through blr_stats_accumulate_host in chunks (H2D on a
+    copy stream overlapped with the Gram kernel, no second full copy of X on the device), then one all-reduce and the
+    replicated solve."""
     D = f.mw.shape[0]
     Xf = _f64(np.asarray(X, dtype=np.float64), "F")
     Dx, N = Xf.shape if layout == L.COLVECS else Xf.shape[::-1]
     yv = _f64(np.asarray(y, dtype=np.float64).reshape(-1))
     if Dx != D:
         raise L.BLRError(L.E_INVALID, "size(X, 1) != length(mw)")
-    if yv.shape[0] != N:
+    if yv.shape[0] != N:  # src/bayesian_linear_regression.jl:74
         raise L.DimensionMismatch(L.E_DIM, "length(y) != size(fx.x.X, 2)")
-    if isinstance(Σy, Diagonal):
-        Σy = Σy.diag
-    s2 = np.asarray(Σy, dtype=np.float64)
-    if s2.ndim == 0:
-        kind, scalar, s2p = L.NOISE_SCALAR, float(s2), None
-    elif s2.ndim == 1 and s2.shape[0] == N:
-        s2 = _f64(s2)
-        kind, scalar, s2p = L.NOISE_VECTOR, 0.0, _ptr(s2)
-    else:
-        raise L.DimensionMismatch(L.E_DIM, "noise must be a scalar or a length-N vector of variances")
+    kind, scalar, s2 = noise
     st = Stats(ctx, D)
     mw = _f64(f.mw)
     ctx.check(ctx.lib.blr_stats_accumulate_host(ctx.handle, st.handle, _ptr(mw), _ptr(Xf), D, N, max(Xf.shape[0], 1), layout,
-                                                _ptr(yv), kind, scalar, s2p, int(chunk)))
+                                                _ptr(yv), kind, scalar, _ptr(s2), int(chunk)))
     st.allreduce()
     prior, keep = f._prior_struct()
     lp = C.c_double()
-    m_post, Λ_post = np.empty(D), ctx.empty_pinned((D, D))
-    T_post = ctx.empty_pinned((D, D)) if isinstance(f.Λw, PDMat) else None
+    m_post = np.empty(D) if want_post else None
+    Λ_post = ctx.empty_pinned((D, D)) if want_post else None
+    T_post = ctx.empty_pinned((D, D)) if (want_post and isinstance(f.Λw, PDMat)) else None
     h = C.c_void_p()
-    ctx.check(ctx.lib.blr_infer_from_stats(ctx.handle, C.byref(prior), st.handle, C.byref(lp), _ptr(m_post), _ptr(T_post),
-                                           _ptr(Λ_post), C.byref(h)))
-    post = BayesianLinearRegressor(m_post, _build_Λ(f.Λw, Λ_post, T_post), _post=DevicePosterior(ctx, h, D))
-    return post, lp.value
+    ctx.check(ctx.lib.blr_infer_from_stats(ctx.handle, C.byref(prior), st.handle, C.byref(lp) if want_logpdf else None,
+                                           _ptr(m_post), _ptr(T_post), _ptr(Λ_post), C.byref(h) if want_post else None))
+    post = None
+    if want_post:
+        post = BayesianLinearRegressor(m_post, _build_Λ(f.Λw, Λ_post, T_post), _post=DevicePosterior(ctx, h, D))
+    return (lp.value if want_logpdf else None), post
+
+
+def posterior_and_logpdf_streamed(f: BayesianLinearRegressor, X, y, Σy, chunk: int = 1 << 16, ctx: Optional[Context] = None,
+                                  layout: int = L.COLVECS):
+    """posterior + logpdf for HOST arrays too large (or too transient) to keep on the device; X is the D x N matrix
+    (ColVecs; Fortran order is sent without a copy) or the N x D matrix with layout=ROWVECS.  Returns
+    (posterior, logpdf).  `posterior` / `logpdf` on numpy inputs take the same path."""
+    ctx = ctx or default_context()
+    Xa = np.asarray(X)
+    N = Xa.shape[1] if layout == L.COLVECS else Xa.shape[0]
+    noise = _host_noise(Σy, N)
+    if noise is None:
+        raise L.BLRError(L.E_INVALID, "noise must be a scalar or a length-N vector of variances")
+    lp, post = _infer_host(ctx, f, Xa, layout, y, noise, chunk, True, True)
+    return post, lp
 
 
 # ------------------------------------------------------------------------------------------------

@@ -163,6 +163,29 @@ def test_posterior_and_logpdf_match_oracle(D, N, dense, zero_mean, scalar_noise,
     assert isinstance(post.Λw, blr.Symmetric)  # src/bayesian_linear_regression.jl:92
 
 
+@pytest.mark.parametrize("D,N", [(7, 13), (256, 5000), (320, 2049)])
+def test_device_resident_inputs(D, N):
+    """blr_infer on handles that already live on the device (DeviceMatrix / DeviceVector / CUDA tensors): the path the
+    benchmark times.  numpy inputs take the host-streaming entry point instead; both must agree bit for bit."""
+    import torch
+
+    X, mw, Λ, σ2, y = problem(D, N, seed=D + N)
+    ctx = blr.default_context()
+    f = blr.BayesianLinearRegressor(mw, Λ)
+    post_h, lp_h = blr.posterior_and_logpdf(f(blr.ColVecs(X), σ2), y)
+    Xd = blr.DeviceMatrix.upload(ctx, X, 0)
+    post_d, lp_d = blr.posterior_and_logpdf(f(blr.ColVecs(Xd), blr.DeviceVector.upload(ctx, σ2)), blr.DeviceVector.upload(ctx, y))
+    Xt = torch.from_numpy(np.ascontiguousarray(X.T)).cuda()  # (N, D) row-major == D x N column-major
+    post_t, lp_t = blr.posterior_and_logpdf(f(blr.ColVecs(Xt), torch.from_numpy(σ2).cuda()), torch.from_numpy(y).cuda())
+    torch.cuda.synchronize()
+    fxo = ref.BayesianLinearRegressor(mw, Λ)(ref.ColVecs(X), σ2)
+    assert abs(lp_d - ref.logpdf(fxo, y)) <= RTOL * abs(lp_d)
+    assert lp_d == lp_t and np.array_equal(post_d.mw, post_t.mw)
+    if N <= (1 << 16):  # a single host chunk sees the same kernel launch as the resident path
+        assert lp_h == lp_d and np.array_equal(post_h.mw, post_d.mw)
+    assert relerr(post_d.mw, ref.posterior(fxo, y).mw) < RTOL
+
+
 def test_pdmat_closure_and_factor():
     """src/bayesian_linear_regression.jl:93 + test/bayesian_linear_regression.jl:71-113."""
     X, mw, Λ, σ2, y = problem(96, 700, seed=3)
