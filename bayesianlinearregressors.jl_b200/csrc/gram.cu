@@ -505,6 +505,20 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
     const int D = (int)x->D;
     if (N == 0) return 0;
     cudaStream_t sm = ctx->stream;
+    // A large RowVecs (feature-major) matrix is consumed in blocks of observations: each block is transposed into a
+    // bounded ColVecs staging buffer and accumulated like any other chunk (the statistics are additive), so the extra
+    // memory is 8 * D * ROWVECS_BLOCK bytes instead of a second copy of X.
+    constexpr int64_t ROWVECS_BLOCK = 1 << 18;
+    if (x->layout == BLR_ROWVECS && D >= 64 && (D % 2) == 0 && N > ROWVECS_BLOCK) {
+        for (int64_t a = 0; a < N; a += ROWVECS_BLOCK) {
+            blr_x sub = *x;
+            sub.p = x->p + a;
+            sub.N = std::min(ROWVECS_BLOCK, N - a);
+            sub.owned = false;
+            BLR_TRY(gram_accumulate(ctx, st, mw_dev, mw_is_zero, &sub, y + a, sigma2 ? sigma2 + a : nullptr, sigma2_scalar));
+        }
+        return 0;
+    }
     BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], sm));
 
     // ---- K0: prep

@@ -99,6 +99,18 @@ def cpu_reference_pass(ref, f, X, y, σ2):
     return post, lp
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core (BLAS thread count is stated)."""
+    cores = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=cores)
+    except Exception:  # pragma: no cover
+        pass
+    return cores
+
+
 def cpu_sample(D, n_sample, seed=0):
     rng = np.random.default_rng(seed)
     X = np.asfortranarray(rng.standard_normal((D, n_sample)))
@@ -115,7 +127,7 @@ def run_reference(args):
         return
     from oracle import blr_oracle as ref
 
-    cores = os.cpu_count() or 1
+    cores = use_all_host_threads()
     D, n_sample = args.dim, args.cpu_sample
     X, y, σ2 = cpu_sample(D, n_sample)
     f = ref.BayesianLinearRegressor(np.zeros(D), ref.Diagonal(np.ones(D)))
@@ -271,6 +283,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import blr_oracle as ref
 
+        use_all_host_threads()
         Xs, ys, ss = cpu_sample(D, args.cpu_sample)
         fo = ref.BayesianLinearRegressor(np.zeros(D), ref.Diagonal(np.ones(D)))
         t0 = time.perf_counter()

@@ -186,6 +186,19 @@ def test_device_resident_inputs(D, N):
     assert relerr(post_d.mw, ref.posterior(fxo, y).mw) < RTOL
 
 
+def test_large_rowvecs_blockwise_staging():
+    """A device-resident RowVecs matrix with more than 2^18 observations is transposed block by block."""
+    D, N = 64, (1 << 18) + 4099
+    X, mw, _, σ2, y = problem(D, N, seed=77, dense=False)
+    ctx = blr.default_context()
+    f = blr.BayesianLinearRegressor(mw, blr.Diagonal(np.ones(D)))
+    Xr = blr.DeviceMatrix.upload(ctx, np.ascontiguousarray(X.T), 1)
+    post, lp = blr.posterior_and_logpdf(f(blr.RowVecs(Xr), blr.DeviceVector.upload(ctx, σ2)), blr.DeviceVector.upload(ctx, y))
+    lpo, mo, To = ref.infer_streaming(mw, ref.Diagonal(np.ones(D)), X, y, σ2)
+    assert abs(lp - lpo) <= RTOL * abs(lpo)
+    assert relerr(post.mw, mo) < RTOL and relerr(post.Λw.dense(), To.T @ To) < RTOL
+
+
 def test_pdmat_closure_and_factor():
     """src/bayesian_linear_regression.jl:93 + test/bayesian_linear_regression.jl:71-113."""
     X, mw, Λ, σ2, y = problem(96, 700, seed=3)
