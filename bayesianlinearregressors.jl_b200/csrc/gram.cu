@@ -548,6 +548,14 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
     BLR_CHECK_LAUNCH(ctx, "prep_kernel");
     BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[1], sm));
 
+    // ---- K1, small D: one warp holds the whole Gram matrix, observations stream straight from HBM
+    if (D <= 64) {
+        BLR_TRY(gram_small(ctx, st, x, s, t, prep_partial, prep_blocks));
+        BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], sm));
+        ctx->ev_valid[0] = ctx->ev_valid[1] = ctx->ev_valid[2] = true;
+        return 0;
+    }
+
     // ---- K1
     const double* Xc = x->p;
     int64_t ldc = x->ld;

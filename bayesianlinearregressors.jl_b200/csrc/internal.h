@@ -120,6 +120,10 @@ int ensure_dinv(blr_ctx* ctx, size_t bytes);
 int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_is_zero, const blr_x* x,
                     const double* y, const double* sigma2, double sigma2_scalar);
 
+// ---- gram_small.cu: D <= 64, any layout / alignment; adds this shard's statistics into st (uses prep's s, t)
+int gram_small(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double* s, const double* t, const double* prep_partial,
+               int prep_blocks);
+
 // ---- chol.cu
 // In-place lower Cholesky of the column-major D x D matrix A (only the lower triangle is read);
 // strictly-upper part is zeroed.  *info_dev (device int) receives 0 or the 1-based failing order.

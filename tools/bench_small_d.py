@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""Small-D regime (few features, many observations): posterior+logpdf through the HBM-bound streaming Gram kernel.
+Reports obs/s and the algorithmic HBM rate 8*N*(D+2) bytes / step time against the measured copy bandwidth."""
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import blr_b200 as blr  # noqa: E402
+
+ctx = blr.Context(0)
+blr.set_default_context(ctx)
+hbm = ctx.calibrate()["hbm_gbs"]
+for D, N in [(2, 1 << 26), (8, 1 << 26), (16, 1 << 25), (32, 1 << 25), (64, 1 << 24)]:
+    X = blr.DeviceMatrix.alloc(ctx, D, N).synth_(0)
+    s2, y = blr.DeviceVector.alloc(ctx, N), blr.DeviceVector.alloc(ctx, N)
+    ctx.check(ctx.lib.blr_vec_synth_noise(ctx.handle, s2.handle, 0, 0))
+    ctx.check(ctx.lib.blr_vec_synth_targets(ctx.handle, X.handle, s2.handle, 0, 0, y.handle))
+    f = blr.BayesianLinearRegressor(np.zeros(D), blr.Diagonal(np.ones(D)))
+    fx = f(blr.ColVecs(X), s2)
+    for _ in range(3):
+        blr.posterior_and_logpdf(fx, y)
+    ctx.sync()
+    st = torch.cuda.ExternalStream(ctx.stream())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(5):
+        post, lp = blr.posterior_and_logpdf(fx, y)
+    e1.record(st)
+    ctx.sync(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    tm = ctx.last_timings()
+    gbs = 8.0 * N * (D + 2) / ms / 1e6
+    print(json.dumps({"config": f"small-D posterior+logpdf D={D} N={N}", "obs_per_s": N / ms * 1e3, "ms": ms, "gram_ms": tm["gram_ms"],
+                      "prep_ms": tm["prep_ms"], "hbm_gbs_algorithmic": gbs, "frac_of_measured_hbm": gbs / hbm}))
+    del X, s2, y, fx
