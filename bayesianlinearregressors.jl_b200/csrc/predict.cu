@@ -118,11 +118,100 @@ __global__ void __launch_bounds__(bg::THREADS) var_kernel(const double* __restri
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small-D marginals (D <= 64): W lives in shared memory, every warp streams groups of 8 test points straight from HBM
+// into m8n8k4 B fragments (lane (k, g) reads feature 4*kk + k of point p + g: whole 32-byte sectors in both layouts),
+// α = W x stays in 2 accumulators per 8-row block, squares are folded by shuffles; the mean rides on the same fragments.
+template <int MI>
+__global__ void __launch_bounds__(256) var_small_kernel(const double* __restrict__ W, const double* __restrict__ mw, int D,
+                                                        const double* __restrict__ X, int64_t sd, int64_t sn, int64_t N,
+                                                        const double* __restrict__ sigma2, double sigma2_scalar,
+                                                        double* __restrict__ mean, double* __restrict__ var) {
+    constexpr int DP = MI * 8, KK = DP / 4, LDW = DP + 4;
+    __shared__ double Ws[DP * LDW];  // Ws[k * LDW + m] = W[m, k]
+    __shared__ double mws[DP];
+    for (int e = threadIdx.x; e < DP * DP; e += 256) {
+        const int m = e % DP, k = e / DP;
+        Ws[k * LDW + m] = (m < D && k < D && m >= k) ? W[(int64_t)k * D + m] : 0.0;
+    }
+    if (threadIdx.x < DP) mws[threadIdx.x] = threadIdx.x < D ? mw[threadIdx.x] : 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, g = lane >> 2, kq = lane & 3;
+    const int64_t nwarps = (int64_t)gridDim.x * 8;
+    const int64_t ngroups = (N + 7) / 8;
+    double a_mw[KK];
+#pragma unroll
+    for (int kk = 0; kk < KK; ++kk) a_mw[kk] = mws[kk * 4 + kq];
+    for (int64_t grp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); grp < ngroups; grp += nwarps) {
+        const int64_t p0 = grp * 8, pt = p0 + g;
+        const bool pok = pt < N;
+        double b[KK];
+#pragma unroll
+        for (int kk = 0; kk < KK; ++kk) {
+            const int k = kk * 4 + kq;
+            b[kk] = (pok && k < D) ? X[(int64_t)k * sd + pt * sn] : 0.0;
+        }
+        double acc[MI][2];
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi) acc[mi][0] = acc[mi][1] = 0.0;
+        double macc = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < KK; ++kk) {
+            macc = fma(a_mw[kk], b[kk], macc);
+#pragma unroll
+            for (int mi = 0; mi < MI; ++mi) {
+                if (mi * 8 + 7 >= kk * 4) {  // W[m, k] = 0 for k > m: static triangular skip
+                    const double a = Ws[(kk * 4 + kq) * LDW + mi * 8 + g];
+                    dmma884(acc[mi], a, b[kk]);
+                }
+            }
+        }
+        double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+        for (int mi = 0; mi < MI; ++mi) {
+            v0 = fma(acc[mi][0], acc[mi][0], v0);
+            v1 = fma(acc[mi][1], acc[mi][1], v1);
+        }
+#pragma unroll
+        for (int o = 4; o <= 16; o <<= 1) {
+            v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+        }
+        macc += __shfl_xor_sync(0xffffffffu, macc, 1);
+        macc += __shfl_xor_sync(0xffffffffu, macc, 2);
+        if (var && g == 0) {  // lane kq owns points p0 + 2 kq, p0 + 2 kq + 1
+            const int64_t q0 = p0 + kq * 2;
+            if (q0 < N) var[q0] = v0 + (sigma2 ? sigma2[q0] : sigma2_scalar);
+            if (q0 + 1 < N) var[q0 + 1] = v1 + (sigma2 ? sigma2[q0 + 1] : sigma2_scalar);
+        }
+        if (mean && kq == 0 && pok) mean[pt] = macc;
+    }
+}
+
+template <int MI>
+static int launch_var_small(blr_ctx* ctx, blr_post* p, const blr_x* x, const double* sigma2, double sigma2_scalar,
+                            double* mean_dev, double* var_dev) {
+    const bool colv = x->layout == BLR_COLVECS;
+    const int64_t sd = colv ? 1 : x->ld, sn = colv ? x->ld : 1;
+    const int grid = (int)std::min<int64_t>(((x->N + 7) / 8 + 7) / 8, (int64_t)ctx->sm_count * 4);
+    var_small_kernel<MI><<<std::max(grid, 1), 256, 0, ctx->stream>>>(p->W, p->mw, (int)p->D, x->p, sd, sn, x->N, sigma2,
+                                                                   sigma2_scalar, mean_dev, var_dev);
+    BLR_CHECK_LAUNCH(ctx, "var_small_kernel");
+    return 0;
+}
+
 int predict_mean_var(blr_ctx* ctx, blr_post* p, const blr_x* x, const double* sigma2, double sigma2_scalar,
                      double* mean_dev, double* var_dev) {
     if (x->N == 0) return 0;
     if (var_dev && predict_fast_eligible(p, x))
         return predict_mean_var_fast(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+    if (var_dev && p->D <= 64) {
+        BLR_TRY(post_ensure_W(ctx, p));
+        if (p->D <= 8) return launch_var_small<1>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+        if (p->D <= 16) return launch_var_small<2>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+        if (p->D <= 32) return launch_var_small<4>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+        return launch_var_small<8>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+    }
     if (mean_dev) BLR_TRY(apply_weights(ctx, x, p->mw, mean_dev));
     if (var_dev) {
         BLR_TRY(post_ensure_W(ctx, p));

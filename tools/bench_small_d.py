@@ -35,6 +35,24 @@ for D, N in [(2, 1 << 26), (8, 1 << 26), (16, 1 << 25), (32, 1 << 25), (64, 1 <<
     ms = e0.elapsed_time(e1) / 5
     tm = ctx.last_timings()
     gbs = 8.0 * N * (D + 2) / ms / 1e6
+    import ctypes as C
+    from blr_b200.runtime import make_noise
+    dpost = post._device(ctx)
+    mv = torch.empty(2 * N, dtype=torch.float64, device="cuda")
+    noise, keep = make_noise(ctx, 0.1, N)
+    def mean_var():
+        ctx.check(ctx.lib.blr_mean_var_dev(ctx.handle, dpost.handle, X.handle, C.byref(noise), C.c_void_p(mv.data_ptr()),
+                                           C.c_void_p(mv.data_ptr() + 8 * N)))
+    mean_var(); mean_var(); ctx.sync()
+    e0.record(st)
+    for _ in range(5):
+        mean_var()
+    e1.record(st)
+    ctx.sync(); torch.cuda.synchronize()
+    ms_mv = e0.elapsed_time(e1) / 5
+    print(json.dumps({"config": f"small-D mean_and_var D={D} N*={N}", "points_per_s": N / ms_mv * 1e3, "ms": ms_mv,
+                      "hbm_gbs_algorithmic": 8.0 * N * (D + 2) / ms_mv / 1e6, "frac_of_measured_hbm": 8.0 * N * (D + 2) / ms_mv / 1e6 / hbm}))
+    del mv
     print(json.dumps({"config": f"small-D posterior+logpdf D={D} N={N}", "obs_per_s": N / ms * 1e3, "ms": ms, "gram_ms": tm["gram_ms"],
                       "prep_ms": tm["prep_ms"], "hbm_gbs_algorithmic": gbs, "frac_of_measured_hbm": gbs / hbm}))
     del X, s2, y, fx
