@@ -104,6 +104,7 @@ SIGNATURES = {
     "blr_apply_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "blr_calibrate_dmma": (C.c_int, [C.c_void_p, c_double_p]),
     "blr_calibrate_dmma_cfg": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p]),
+    "blr_calibrate_gram_inner": (C.c_int, [C.c_void_p, c_double_p]),
     "blr_calibrate_mixed": (C.c_int, [C.c_void_p, c_double_p]),
     "blr_calibrate_dfma": (C.c_int, [C.c_void_p, c_double_p]),
     "blr_calibrate_hbm": (C.c_int, [C.c_void_p, c_double_p]),

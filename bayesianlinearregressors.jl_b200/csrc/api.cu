@@ -213,6 +213,7 @@ int blr_ctx_create(blr_ctx** out, int device) {
         const long long v = atoll(po);
         if (v >= 32) ctx->gram_period_obs = v;
     }
+    if (const char* st = getenv("BLR_GRAM_STAGES")) ctx->gram_stages = atoi(st);
     if (const char* k = getenv("BLR_GRAM_KT")) {
         if (atoi(k) == 16) ctx->gram_kt = 16;
         if (atoi(k) == 32) ctx->gram_kt = 32;
@@ -976,6 +977,11 @@ int blr_calibrate_dmma_cfg(blr_ctx* ctx, int warps_per_sm, int n_acc, double* tf
     CTX_ENTER(ctx);
     if (!tflops_out) return BLR_E_INVALID;
     return calib_dmma_cfg(ctx, warps_per_sm, n_acc, tflops_out);
+}
+int blr_calibrate_gram_inner(blr_ctx* ctx, double* tflops_out) {
+    CTX_ENTER(ctx);
+    if (!tflops_out) return BLR_E_INVALID;
+    return calib_gram_inner(ctx, tflops_out);
 }
 int blr_calibrate_mixed(blr_ctx* ctx, double* tflops2_out) {
     CTX_ENTER(ctx);

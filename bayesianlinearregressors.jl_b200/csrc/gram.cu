@@ -381,6 +381,59 @@ __global__ void __launch_bounds__(gk::THREADS, 1) gram_tma_kernel(const GramPara
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Ceiling probe: the consumer instruction mix alone (12 LDS.64 + LDS + 4 DMUL + 32 DMMA per k4 step, 8 warps per SM) on a
+// resident shared-memory stage -- no TMA, no mbarriers, no epilogue.  The gap between this and the real kernel is what
+// the pipeline synchronisation costs; the gap between this and the pure-DMMA calibration is the cost of the mix itself.
+template <int KT>
+__global__ void __launch_bounds__(256, 1) gram_inner_probe_kernel(double* __restrict__ out, int iters) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    gk::Stage<KT>& S = *reinterpret_cast<gk::Stage<KT>*>(smem_raw);
+    for (int i = threadIdx.x; i < (int)(sizeof(gk::Stage<KT>) / sizeof(double)); i += 256)
+        reinterpret_cast<double*>(&S)[i] = 1.0 + 1e-9 * i;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double acc[8][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    for (int it = 0; it < iters; ++it) consume_stage<false, -8, KT>(acc, S, warp >> 2, warp & 3, lane >> 2, lane & 3);
+    double sum = 0.0;
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) sum += acc[mi][ni][0] + acc[mi][ni][1];
+    out[(int64_t)blockIdx.x * 256 + threadIdx.x] = sum;
+}
+
+int calib_gram_inner(blr_ctx* ctx, double* tflops) {
+    constexpr int KT = 32;
+    const int blocks = ctx->sm_count, iters = 2000;
+    BLR_TRY(ensure_ws(ctx, (size_t)blocks * 256 * sizeof(double)));
+    BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_inner_probe_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(gk::Stage<KT>)));
+    cudaEvent_t e0, e1;
+    BLR_CUDA_OK(ctx, cudaEventCreate(&e0));
+    BLR_CUDA_OK(ctx, cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int r = 0; r < 4; ++r) {
+        BLR_CUDA_OK(ctx, cudaEventRecord(e0, ctx->stream));
+        gram_inner_probe_kernel<KT><<<blocks, 256, sizeof(gk::Stage<KT>), ctx->stream>>>(ctx->ws, iters);
+        ctx->launches++;
+        BLR_CUDA_OK(ctx, cudaEventRecord(e1, ctx->stream));
+        BLR_CUDA_OK(ctx, cudaEventSynchronize(e1));
+        float ms;
+        BLR_CUDA_OK(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        if (r > 0) best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    // hardware flops of the DMMAs only: per block per iteration 128 x 128 x KT FMAs
+    *tflops = (double)blocks * iters * 128.0 * 128.0 * KT * 2.0 / (best * 1e-3) / 1e12;
+    return 0;
+}
+
 // ====================================================================== K1 generic path
 // Any D, any leading dimension, either layout (element (d, n) at d*sd + n*sn).  32 x 32 tiles of the
 // lower triangle, 2 x 2 outputs per thread, plain DFMA.  Used for small / odd shapes (README toy D = 2,
@@ -635,6 +688,12 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
             BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_tma_kernel<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   (int)sizeof(SM)));
             BLR_CUDA_OK(ctx, cudaLaunchCooperativeKernel((void*)gram_tma_kernel<32, 3>, dim3(G), dim3(gk::THREADS), args,
+                                                         sizeof(SM), sm));
+        } else if (ctx->gram_stages == 6) {
+            using SM = gk::Smem<16, 6>;
+            BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_tma_kernel<16, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)sizeof(SM)));
+            BLR_CUDA_OK(ctx, cudaLaunchCooperativeKernel((void*)gram_tma_kernel<16, 6>, dim3(G), dim3(gk::THREADS), args,
                                                          sizeof(SM), sm));
         } else {
             using SM = gk::Smem<16, 4>;

@@ -65,6 +65,7 @@ struct blr_ctx {
     int64_t sched_key[4] = {-1, -1, -1, -1};
     int sched_T = 0, sched_nseg = 0;
     int64_t gram_period_obs = 0;  // observations per L2 period of the Gram kernel (0 = single period; BLR_GRAM_PERIOD_OBS)
+    int gram_stages = 0;   // ring depth override for gram_kt == 16 (BLR_GRAM_STAGES = 6)
     int gram_kt = 32;      // observations per pipeline stage of the Gram kernel: 16 or 32 (BLR_GRAM_KT)
     int diag_weight = 40;  // cost of a diagonal-tile stage relative to W_OFF = 64 (BLR_DIAG_WEIGHT overrides)
     // host-streaming path (blr_stats_accumulate_host): copy stream, two staging slots
@@ -175,6 +176,7 @@ int transpose_to_colvecs(blr_ctx* ctx, const blr_x* x, double* out, int64_t ldo)
 int calib_dmma(blr_ctx* ctx, double* tflops);
 int calib_dfma(blr_ctx* ctx, double* tflops);
 int calib_mixed(blr_ctx* ctx, double* tflops2);
+int calib_gram_inner(blr_ctx* ctx, double* tflops);  // gram.cu
 int calib_dmma_cfg(blr_ctx* ctx, int warps, int nacc, double* tflops);
 int calib_hbm(blr_ctx* ctx, double* gbs);
 

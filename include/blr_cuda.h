@@ -187,6 +187,8 @@ int blr_apply_weights(blr_ctx* ctx, const blr_x* x, const double* w_host, double
 int blr_calibrate_dmma(blr_ctx* ctx, double* tflops_out);
 /* issue-rate probe: `warps_per_sm` warps on every SM, each with `n_acc` (1..32, power of two) independent DMMA chains */
 int blr_calibrate_dmma_cfg(blr_ctx* ctx, int warps_per_sm, int n_acc, double* tflops_out);
+/* the Gram kernel's consumer instruction mix on a resident shared-memory stage (no TMA, no barriers): hardware TFLOP/s */
+int blr_calibrate_gram_inner(blr_ctx* ctx, double* tflops_out);
 /* DMMA and DFMA loops side by side on every SM: out[0] = DMMA TFLOP/s, out[1] = DFMA TFLOP/s achieved concurrently */
 int blr_calibrate_mixed(blr_ctx* ctx, double* tflops2_out);
 int blr_calibrate_dfma(blr_ctx* ctx, double* tflops_out);

@@ -61,6 +61,11 @@ print(json.dumps(c.calibrate()))
       timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"var_tma|rand_tma" -s 2 -c 2 -o "$OUT/prof_pred" -f \
         python tools/run_predict.py 512 2097152 64 > "$OUT/ncu_pred.log" 2>&1; echo "ncu_pred exit $?"; tail -3 "$OUT/ncu_pred.log";;
     kt_sweep)
+      for cfg in "--n-obs 1048576 --dim 256" "--n-obs 2097152 --dim 1024"; do
+        echo "KT=16 STAGES=6 cfg=$cfg"
+        BLR_GRAM_KT=16 BLR_GRAM_STAGES=6 timeout 600 python bench.py $cfg --steps 5 --warmup 3 --no-cpu --no-e2e --no-calibrate 2>> "$OUT/kt.err" \
+          | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['achieved'])"
+      done
       for kt in 16 32; do
         for cfg in "--n-obs 1048576 --dim 256" "--n-obs 2097152 --dim 1024"; do
           echo "KT=$kt cfg=$cfg"
