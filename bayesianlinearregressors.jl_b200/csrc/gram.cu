@@ -98,19 +98,29 @@ constexpr int TM = 128;                   // tile edge (rows of G per panel)
 constexpr int KT_MAX = 32;                // observations per pipeline stage: 16 (4-stage ring) or 32 (3-stage ring)
 constexpr int LDT = TM + 4;               // padded smem row: stride == 4 (mod 16) doubles -> conflict-free LDS.64
 constexpr int CONSUMER_WARPS = 8;         // 2 (m) x 4 (n) warps, warp tile 64 x 32
-constexpr int PRODUCER_WARPS = 2;         // bulk copies are uniform-datapath ops (one lane at a time): panel I | panel J
+// bulk copies are uniform-datapath ops (one lane at a time), so they are spread over four producer warps: two per panel
+// (ColVecs: each takes half of the stage's observations; feature-major: half of the panel's 128 feature rows)
+constexpr int PRODUCER_WARPS = 4;
+constexpr int PRODUCER_WARPS_ROW = 4;
 constexpr int THREADS = (CONSUMER_WARPS + PRODUCER_WARPS) * 32;
+constexpr int THREADS_ROW = (CONSUMER_WARPS + PRODUCER_WARPS_ROW) * 32;
 constexpr int W_OFF = 64;                 // schedule weight of one stage of an off-diagonal tile
-template <int KT>
+// ROW == false: ColVecs input, a panel is staged [k][m] (one bulk copy per observation: its 128-row slice);
+// ROW == true : RowVecs input (feature-major), staged [m][k] (one bulk copy per feature: its KT observations).
+// Either way the non-unit stride is == 4 (mod 16) doubles, so the m8n8k4 fragment reads are bank-conflict free.
+template <int KT, bool ROW = false>
 struct __align__(16) Stage {
-    double a[KT * LDT];  // panel I rows  [k][m]
-    double b[KT * LDT];  // panel J rows  [k][n]  (unused on diagonal tiles)
+    static constexpr int SK = ROW ? 1 : LDT;        // element (k, m) of a panel lives at k * SK + m * SM
+    static constexpr int SM = ROW ? KT + 4 : 1;
+    static constexpr int PANEL = ROW ? TM * (KT + 4) : KT * LDT;
+    double a[PANEL];     // panel I
+    double b[PANEL];     // panel J (unused on diagonal tiles)
     double s[KT];        // 1/σ²
     double t[KT];        // δ/σ²
 };
-template <int KT, int STAGES>
+template <int KT, int STAGES, bool ROW = false>
 struct Smem {
-    Stage<KT> st[STAGES];
+    Stage<KT, ROW> st[STAGES];
     double rred[TM];
     unsigned long long full[STAGES];
     unsigned long long empty[STAGES];
@@ -159,11 +169,13 @@ __device__ __forceinline__ void tile_from_index(int idx, int& ti, int& tj) {
 // mi - ni >= wn*4 - wm*8).  Compile-time, because predicating an mma.sync at run time makes ptxas wrap every DMMA in
 // WARPSYNC.ALL, which serialises the tensor pipe (measured: no speed-up at all from run-time skipping).
 //   THR = -8: all 32 sub-tiles;  THR = 0: 26;  THR = 4: 10.
-template <bool DIAG, int THR, int KT>
-__device__ __forceinline__ void consume_stage(double (&acc)[8][4][2], const gk::Stage<KT>& S, int wm, int wn, int g, int kq) {
+template <bool DIAG, int THR, int KT, bool ROW = false>
+__device__ __forceinline__ void consume_stage(double (&acc)[8][4][2], const gk::Stage<KT, ROW>& S, int wm, int wn, int g,
+                                              int kq) {
     using namespace gk;
-    const double* Ap = S.a + wm * 64 + g;
-    const double* Bp = (DIAG ? S.a : S.b) + wn * 32 + g;
+    constexpr int SK = Stage<KT, ROW>::SK, SM = Stage<KT, ROW>::SM;
+    const double* Ap = S.a + (wm * 64 + g) * SM;
+    const double* Bp = (DIAG ? S.a : S.b) + (wn * 32 + g) * SM;
 #pragma unroll
     for (int kk = 0; kk < KT / 4; ++kk) {
         const int kl = kk * 4 + kq;
@@ -171,10 +183,10 @@ __device__ __forceinline__ void consume_stage(double (&acc)[8][4][2], const gk::
         double a[8], b[4];
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi)
-            if (mi - 0 >= THR) a[mi] = Ap[kl * LDT + mi * 8];  // row block mi is used by some ni iff mi >= THR
+            if (mi - 0 >= THR) a[mi] = Ap[kl * SK + mi * 8 * SM];  // row block mi is used by some ni iff mi >= THR
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni)
-            if (7 - ni >= THR) b[ni] = Bp[kl * LDT + ni * 8] * sk;
+            if (7 - ni >= THR) b[ni] = Bp[kl * SK + ni * 8 * SM] * sk;
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
@@ -186,24 +198,24 @@ __device__ __forceinline__ void consume_stage(double (&acc)[8][4][2], const gk::
 
 // All stages of one segment for one consumer warp.  MODE: 0 off-diagonal; 1..3 diagonal with THR -8 / 0 / 4;
 // 4 diagonal, warp entirely above the diagonal (only helps with the r block).
-template <int MODE, int KT, int STAGES>
-__device__ __forceinline__ void run_segment(double (&acc)[8][4][2], double& racc, gk::Smem<KT, STAGES>& sm, int& it, int nst,
-                                            int wm, int wn, int g, int kq, int rm, int rhalf, int lane) {
+template <int MODE, int KT, int STAGES, bool ROW>
+__device__ __forceinline__ void run_segment(double (&acc)[8][4][2], double& racc, gk::Smem<KT, STAGES, ROW>& sm, int& it,
+                                            int nst, int wm, int wn, int g, int kq, int rm, int rhalf, int lane) {
     using namespace gk;
     for (int i = 0; i < nst; ++i, ++it) {
         const int stg = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(smem_u32(&sm.full[stg]), ph);
-        const Stage<KT>& S = sm.st[stg];
-        if (MODE == 0) consume_stage<false, -8, KT>(acc, S, wm, wn, g, kq);
-        if (MODE == 1) consume_stage<true, -8, KT>(acc, S, wm, wn, g, kq);
-        if (MODE == 2) consume_stage<true, 0, KT>(acc, S, wm, wn, g, kq);
-        if (MODE == 3) consume_stage<true, 4, KT>(acc, S, wm, wn, g, kq);
+        const Stage<KT, ROW>& S = sm.st[stg];
+        if (MODE == 0) consume_stage<false, -8, KT, ROW>(acc, S, wm, wn, g, kq);
+        if (MODE == 1) consume_stage<true, -8, KT, ROW>(acc, S, wm, wn, g, kq);
+        if (MODE == 2) consume_stage<true, 0, KT, ROW>(acc, S, wm, wn, g, kq);
+        if (MODE == 3) consume_stage<true, 4, KT, ROW>(acc, S, wm, wn, g, kq);
         if (MODE != 0) {
 #pragma unroll
             for (int k = 0; k < KT / 2; ++k) {  // r block of this row panel: r[m] += Σ_k X[m,k] t_k
                 const int kl = rhalf * (KT / 2) + k;
-                racc = fma(S.a[kl * LDT + rm], S.t[kl], racc);
+                racc = fma(S.a[kl * Stage<KT, ROW>::SK + rm * Stage<KT, ROW>::SM], S.t[kl], racc);
             }
         }
         __syncwarp();
@@ -211,11 +223,13 @@ __device__ __forceinline__ void run_segment(double (&acc)[8][4][2], double& racc
     }
 }
 
-template <int KT, int STAGES>
-__global__ void __launch_bounds__(gk::THREADS, 1) gram_tma_kernel(const GramParams p) {
+template <int KT, int STAGES, bool ROW = false>
+__global__ void __launch_bounds__(ROW ? gk::THREADS_ROW : gk::THREADS, 1) gram_tma_kernel(const GramParams p) {
     using namespace gk;
-    using Stage = gk::Stage<KT>;
-    using Smem = gk::Smem<KT, STAGES>;
+    using Stage = gk::Stage<KT, ROW>;
+    using Smem = gk::Smem<KT, STAGES, ROW>;
+    constexpr int NTHREADS = ROW ? THREADS_ROW : THREADS;
+    constexpr int NPRODUCERS = ROW ? PRODUCER_WARPS_ROW : PRODUCER_WARPS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
@@ -226,11 +240,11 @@ __global__ void __launch_bounds__(gk::THREADS, 1) gram_tma_kernel(const GramPara
     {
         double* z = reinterpret_cast<double*>(sm.st);
         const int nz = (int)(sizeof(Stage) * STAGES / sizeof(double));
-        for (int i = tid; i < nz; i += THREADS) z[i] = 0.0;
+        for (int i = tid; i < nz; i += NTHREADS) z[i] = 0.0;
     }
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) {
-            mbar_init(smem_u32(&sm.full[i]), PRODUCER_WARPS);
+            mbar_init(smem_u32(&sm.full[i]), NPRODUCERS);
             mbar_init(smem_u32(&sm.empty[i]), CONSUMER_WARPS);
         }
         mbar_fence_init();
@@ -240,7 +254,10 @@ __global__ void __launch_bounds__(gk::THREADS, 1) gram_tma_kernel(const GramPara
 
     if (warp >= CONSUMER_WARPS) {
         // ------------------------------------------------------------ producer warps (TMA): 0 -> panel I + s, 1 -> panel J + t
-        const int pw = warp - CONSUMER_WARPS;
+        // (feature-major: warps 0, 1 -> halves of panel I, warps 2, 3 -> halves of panel J)
+        const int pwr = warp - CONSUMER_WARPS;
+        const int pw = pwr >> 1;   // which panel
+        const int half = pwr & 1;  // which half of its rows (feature-major) / of the stage's observations (ColVecs)
         int it = 0;  // running stage counter of this CTA: ring slot and phase continue across segments and periods
         for (int per = 0; per < p.NP; ++per) {
             // Soft barrier: nobody starts period `per` before every CTA has issued all loads of period per - 2, which
@@ -273,24 +290,47 @@ __global__ void __launch_bounds__(gk::THREADS, 1) gram_tma_kernel(const GramPara
                     const int kc = (int)min((int64_t)KT, p.N - k0);
                     Stage& S = sm.st[stg];
                     const uint32_t bar = smem_u32(&sm.full[stg]);
-                    if (narrow) {  // rare (only tiles in the last block row when D % 128 != 0): clear my panel first
-                        double* z = pw == 0 ? S.a : S.b;
-                        for (int i = lane; i < KT * LDT; i += 32) z[i] = 0.0;
+                    if (narrow) {  // rare (only tiles in the last block row when D % 128 != 0): clear my part first
+                        double* z = (pw == 0 ? S.a : S.b) + half * (Stage::PANEL / 2);
+                        for (int i = lane; i < Stage::PANEL / 2; i += 32) z[i] = 0.0;
                         fence_proxy_async();
                         __syncwarp();
                     }
                     const bool have_panel = (pw == 0) || !diag;
                     const int rows = pw == 0 ? rowsA : rowsB;
-                    if (lane == 0)
-                        mbar_arrive_expect_tx(bar, (have_panel ? (uint32_t)kc * (uint32_t)rows * 8u : 0u) + KT * 8u);
-                    __syncwarp();
-                    if (have_panel && lane < kc)
-                        bulk_g2s(smem_u32((pw == 0 ? S.a : S.b) + lane * LDT), p.X + (k0 + lane) * p.ld + (pw == 0 ? i0 : j0),
-                                 (uint32_t)rows * 8u, bar);
-                    if (lane == 0) bulk_g2s(smem_u32(pw == 0 ? S.s : S.t), (pw == 0 ? p.s : p.t) + k0, KT * 8u, bar);
+                    if (ROW) {
+                        // feature-major input: one copy per feature row of the panel (its kc observations); this warp
+                        // owns rows [64 half, 64 half + 64) of its panel, the first warp of a panel also brings s / t
+                        const int my_rows = have_panel ? max(0, min(TM / 2, rows - half * (TM / 2))) : 0;
+                        if (lane == 0)
+                            mbar_arrive_expect_tx(bar, (uint32_t)kc * (uint32_t)my_rows * 8u + (half == 0 ? KT * 8u : 0u));
+                        __syncwarp();
+                        double* panel = pw == 0 ? S.a : S.b;
+                        const int r0 = pw == 0 ? i0 : j0;
+#pragma unroll
+                        for (int q = 0; q < TM / 64; ++q) {
+                            const int m = half * (TM / 2) + q * 32 + lane;
+                            if (m - half * (TM / 2) < my_rows)
+                                bulk_g2s(smem_u32(panel + m * Stage::SM), p.X + (int64_t)(r0 + m) * p.ld + k0, (uint32_t)kc * 8u,
+                                         bar);
+                        }
+                        if (lane == 0 && half == 0) bulk_g2s(smem_u32(pw == 0 ? S.s : S.t), (pw == 0 ? p.s : p.t) + k0, KT * 8u, bar);
+                    } else {
+                        // one copy per observation (its rows-long slice); this warp owns observations
+                        // [KT/2 half, KT/2 half + KT/2) of the stage
+                        const int my_k = have_panel ? max(0, min(KT / 2, kc - half * (KT / 2))) : 0;
+                        if (lane == 0)
+                            mbar_arrive_expect_tx(bar, (uint32_t)my_k * (uint32_t)rows * 8u + (half == 0 ? KT * 8u : 0u));
+                        __syncwarp();
+                        const int kl = half * (KT / 2) + lane;
+                        if (lane < my_k)
+                            bulk_g2s(smem_u32((pw == 0 ? S.a : S.b) + kl * LDT), p.X + (k0 + kl) * p.ld + (pw == 0 ? i0 : j0),
+                                     (uint32_t)rows * 8u, bar);
+                        if (lane == 0 && half == 0) bulk_g2s(smem_u32(pw == 0 ? S.s : S.t), (pw == 0 ? p.s : p.t) + k0, KT * 8u, bar);
+                    }
                 }
             }
-            if (pw == 0 && lane == 0) atomicAdd(p.period_counter, 1u);
+            if (pwr == 0 && lane == 0) atomicAdd(p.period_counter, 1u);
         }
         return;
     }
@@ -356,11 +396,11 @@ __global__ void __launch_bounds__(gk::THREADS, 1) gram_tma_kernel(const GramPara
             const int thr = wn * 4 - wm * 8;  // sub-tile (mi, ni) needed iff mi - ni >= thr
 
             // warp-uniform dispatch to a fully unrolled, unpredicated instruction stream
-            if (!diag) run_segment<0, KT, STAGES>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
-            else if (thr <= -3) run_segment<1, KT, STAGES>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
-            else if (thr == 0) run_segment<2, KT, STAGES>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
-            else if (thr == 4) run_segment<3, KT, STAGES>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
-            else run_segment<4, KT, STAGES>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
+            if (!diag) run_segment<0, KT, STAGES, ROW>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
+            else if (thr <= -3) run_segment<1, KT, STAGES, ROW>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
+            else if (thr == 0) run_segment<2, KT, STAGES, ROW>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
+            else if (thr == 4) run_segment<3, KT, STAGES, ROW>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
+            else run_segment<4, KT, STAGES, ROW>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
 
             if (!single) {
                 flush(sg, diag, wm, wn, thr, per > 0);
@@ -562,7 +602,10 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
     // bounded ColVecs staging buffer and accumulated like any other chunk (the statistics are additive), so the extra
     // memory is 8 * D * ROWVECS_BLOCK bytes instead of a second copy of X.
     constexpr int64_t ROWVECS_BLOCK = 1 << 18;
-    if (x->layout == BLR_ROWVECS && D >= 64 && (D % 2) == 0 && N > ROWVECS_BLOCK) {
+    // (feature-major input that meets the TMA alignment rules needs no staging at all: see row_native below)
+    const bool row_native = x->layout == BLR_ROWVECS && D > 64 && (N % 2) == 0 && (x->ld % 2) == 0 &&
+                            (reinterpret_cast<uintptr_t>(x->p) & 15) == 0;
+    if (x->layout == BLR_ROWVECS && !row_native && D >= 64 && (D % 2) == 0 && N > ROWVECS_BLOCK) {
         for (int64_t a = 0; a < N; a += ROWVECS_BLOCK) {
             blr_x sub = *x;
             sub.p = x->p + a;
@@ -575,7 +618,6 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
     BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], sm));
 
     // ---- K0: prep
-    const int KT = ctx->gram_kt;  // 16 or 32
     const int64_t npad = round_up(N, gk::KT_MAX) + gk::KT_MAX;
     BLR_TRY(ensure_nbuf(ctx, (size_t)(2 * npad) * sizeof(double)));
     double* s = ctx->nbuf;
@@ -613,8 +655,8 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
     const double* Xc = x->p;
     int64_t ldc = x->ld;
     double* xt = nullptr;  // transposed copy for a large RowVecs input
-    bool fast = (D >= 64) && (D % 2 == 0);
-    if (fast && x->layout == BLR_ROWVECS) {
+    bool fast = row_native || ((D >= 64) && (D % 2 == 0));
+    if (fast && x->layout == BLR_ROWVECS && !row_native) {
         const int64_t ldt = round_up(D, 2);
         BLR_CUDA_OK(ctx, cudaMallocAsync(&xt, (size_t)ldt * N * sizeof(double), sm));
         BLR_TRY(transpose_to_colvecs(ctx, x, xt, ldt));
@@ -622,6 +664,7 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
         ldc = ldt;
     }
     if (fast && ((ldc % 2) != 0 || (reinterpret_cast<uintptr_t>(Xc) & 15) != 0)) fast = false;
+    const int KT = row_native ? 32 : ctx->gram_kt;  // the feature-major ring is built for 32-observation stages
 
     if (fast) {
         const int TS = gk::TM;
@@ -683,7 +726,13 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
         BLR_CUDA_OK(ctx, cudaMemsetAsync(gp.period_counter, 0, sizeof(unsigned int), sm));
         void* args[] = {(void*)&gp};
         // cooperative launch: the soft barrier between periods needs every CTA resident (grid = #SMs, 1 CTA / SM)
-        if (KT == 32) {
+        if (row_native) {
+            using SM = gk::Smem<32, 3, true>;
+            BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_tma_kernel<32, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)sizeof(SM)));
+            BLR_CUDA_OK(ctx, cudaLaunchCooperativeKernel((void*)gram_tma_kernel<32, 3, true>, dim3(G), dim3(gk::THREADS_ROW),
+                                                         args, sizeof(SM), sm));
+        } else if (KT == 32) {
             using SM = gk::Smem<32, 3>;
             BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_tma_kernel<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   (int)sizeof(SM)));

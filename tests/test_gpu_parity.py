@@ -57,7 +57,11 @@ STAT_CASES = [
     (256, 20000, False, False, "col"),
     (320, 7777, True, False, "col"),
     (1024, 5000, False, False, "col"),
-    (256, 3001, False, False, "row"),    # RowVecs -> transposed staging
+    (256, 3001, False, False, "row"),    # RowVecs, odd N -> transposed staging
+    (320, 4096, False, False, "row"),    # RowVecs, even N -> native feature-major TMA ring
+    (130, 516, True, False, "row"),      # native, narrow last tile
+    (257, 1000, False, True, "row"),     # native, odd D
+    (1024, 2048, False, False, "row"),
     (2, 10, True, False, "col"),         # generic path
     (3, 11, False, False, "row"),
     (7, 13, False, True, "col"),
