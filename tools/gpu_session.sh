@@ -82,6 +82,19 @@ print(json.dumps(c.calibrate()))
             | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['achieved'], d['clocks'].get('power_w_max'))"
         done
       done 2>&1 | tee "$OUT/period_sweep.log";;
+    tests_fast)
+      timeout 1500 python -m pytest tests -m gpu -q --timeout 600 --ignore tests/test_gpu_fullsize.py > "$OUT/tests.log" 2>&1; echo "tests exit $?"; tail -15 "$OUT/tests.log";;
+    fullsize)
+      timeout 1500 python -m pytest tests/test_gpu_fullsize.py -m gpu -q --timeout 900 --durations=5 > "$OUT/fullsize.log" 2>&1; echo "fullsize exit $?"; tail -25 "$OUT/fullsize.log";;
+    cfg4_multi)
+      NG=$(nvidia-smi -L | wc -l)
+      if [ $NG -gt 1 ]; then
+        timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29544 \
+          tools/bench_cfg4.py > "$OUT/cfg4_g$NG.json" 2> "$OUT/cfg4_g$NG.err"
+      else
+        timeout 900 python tools/bench_cfg4.py > "$OUT/cfg4_g$NG.json" 2> "$OUT/cfg4_g$NG.err"
+      fi
+      echo "cfg4 exit $?"; cat "$OUT/cfg4_g$NG.json"; tail -3 "$OUT/cfg4_g$NG.err";;
     rff_multi)
       NG=$(nvidia-smi -L | wc -l)
       timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533 \
