@@ -202,6 +202,7 @@ int blr_ctx_create(blr_ctx** out, int device) {
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->small, (size_t)SMALL_TOTAL * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_info, sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_res, (size_t)(SMALL_VEC + 2) * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_flags, 512 * sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(ctx->d_flags, 0, 512 * sizeof(int));
     if (e != cudaSuccess || ctx->sm_count * 16 > SMALL_SC) {
@@ -236,6 +237,7 @@ int blr_ctx_destroy(blr_ctx* ctx) {
     cudaFree(ctx->dinv);
     cudaFree(ctx->small);
     cudaFree(ctx->d_info);
+    if (ctx->h_res) cudaFreeHost(ctx->h_res);
     cudaFree(ctx->d_flags);
     cudaFree(ctx->sched);
     cudaFree(ctx->stage[0]);

@@ -7,6 +7,7 @@
 //     logpdf = -1/2 [ n log 2π + ℓ + q + logdet Λ' - logdet Λw - z'z ],   T = L'^T.
 // All matrices column-major; factors are stored LOWER (T of the reference is the transpose).
 #include <math.h>
+#include <string.h>
 
 #include <algorithm>
 #include <vector>
@@ -20,39 +21,88 @@ namespace blr {
 constexpr int NB = 64;  // block size of the D x D phase
 
 // ---------------------------------------------------------------------------------------------
-// Factor a 64 x 64 diagonal block held in shared memory: Ls[c * 65 + r] = element (r, c), lower part + diagonal
-// hold the (partially updated) matrix.  Right-looking, ONE barrier per column: the scaled column k of the factor
-// is written into the unused upper triangle at the transposed position (row k, col i) = Ls[i * 65 + k], so it never
-// races with the threads still reading the unscaled column.  On return  L[i][k] = Ls[i * 65 + k]  for i >= k
-// (i.e. the factor sits transposed in the upper triangle + diagonal) and rdiag[k] = 1 / L[k][k].
-// Blocks smaller than 64 are padded with the identity by the caller.  256 threads: tx = row, ty = column phase.
-// Returns (to all threads) the 1-based index of the first non-positive pivot, or 0.
+// Factor a 64 x 64 diagonal block held in shared memory, in place: Ls[c * LDL + r] = element (r, c) for r >= c (the
+// strict upper part is never read or written).  The sequential pivot chain is what bounds this phase (D dependent
+// column steps for the whole matrix), so it is kept in registers: the block is processed as four 16-column strips;
+//   1. warp 0 factors the strip's 16 x 16 diagonal sub-block with lane r holding row r (16 registers); pivots and
+//      scaled columns travel by warp shuffle, 1/sqrt comes from rsqrt + one Newton step for the diagonal itself --
+//      one column step is a shuffle, an rsqrt and a multiply deep, no barrier, no shared-memory round trip;
+//   2. one thread per row below solves its 16 entries of the strip against that sub-block (registers);
+//   3. all 256 threads apply the rank-16 update to the rest of the block.
+// On return L[r][c] = Ls[c * LDL + r] for r >= c and rdiag[k] = 1 / L[k][k].  Blocks smaller than 64 are padded
+// with the identity by the caller.  Returns (to all threads) the 1-based index of the first non-positive pivot, or 0.
 constexpr int PANEL_THREADS = 256;
+constexpr int LDL = NB + 2;  // even stride: 16-byte aligned column starts, conflict-free for consecutive rows
+constexpr int SB = 16;       // strip width
 __device__ int factor_block_smem(double* Ls, double* rdiag) {
     __shared__ int fail;
-    const int i = threadIdx.x & 63, ty = threadIdx.x >> 6;
-    if (threadIdx.x == 0) fail = 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) fail = 0;
     __syncthreads();
-    for (int k = 0; k < NB; ++k) {
-        const double akk = Ls[k * 65 + k];
-        const double inv = 1.0 / akk, d = sqrt(akk), rd = 1.0 / d;
-        const double aik = Ls[k * 65 + i];  // element (i, k): still unscaled
-        if (i > k) {
-            for (int j = k + 1 + ty; j <= i; j += 4) Ls[j * 65 + i] -= aik * (Ls[k * 65 + j] * inv);
-        }
-        __syncthreads();  // all reads of column k done; updates visible
-        if (ty == 0) {
-            if (i > k) Ls[i * 65 + k] = aik * rd;  // transposed slot (row k, col i)
-            if (i == k) {
-                Ls[k * 65 + k] = d;
-                rdiag[k] = rd;
-                if (!(akk > 0.0) && fail == 0) fail = k + 1;
+#pragma unroll 1
+    for (int k0 = 0; k0 < NB; k0 += SB) {
+        if (warp == 0) {
+            const int r = lane & (SB - 1);  // lanes 16..31 mirror lanes 0..15 so that every shuffle is full-warp
+            double a[SB];
+#pragma unroll
+            for (int c = 0; c < SB; ++c) a[c] = (c <= r) ? Ls[(k0 + c) * LDL + k0 + r] : 0.0;
+            int bad = 0;
+#pragma unroll
+            for (int k = 0; k < SB; ++k) {
+                const double akk = __shfl_sync(0xffffffffu, a[k], k);
+                const double rd = rsqrt(akk);
+                double d = akk * rd;
+                d = fma(fma(-d, d, akk), 0.5 * rd, d);  // sqrt(akk) to the last bit or two
+                if (!(akk > 0.0) && bad == 0) bad = k0 + k + 1;
+                a[k] = (r == k) ? d : a[k] * rd;        // rows r > k: L[r][k]; rows r < k hold zeros
+                if (lane == k) rdiag[k0 + k] = rd;
+#pragma unroll
+                for (int c = k + 1; c < SB; ++c) {
+                    const double lck = __shfl_sync(0xffffffffu, a[k], c);  // L[c][k]
+                    a[c] = fma(-a[k], lck, a[c]);
+                }
             }
+            if (lane < SB) {
+#pragma unroll
+                for (int c = 0; c < SB; ++c)
+                    if (c <= r) Ls[(k0 + c) * LDL + k0 + r] = a[c];
+            }
+            if (lane == 0 && bad != 0 && fail == 0) fail = bad;
         }
-        // no barrier needed here: the slots just written are in row k (upper part) / the diagonal element (k, k),
-        // which later iterations never read (they read columns k' > k at rows >= k').
+        __syncthreads();
+        const int below = NB - k0 - SB;  // rows of the block under this strip's diagonal sub-block
+        if (below > 0) {
+            if (tid < below) {
+                const int row = k0 + SB + tid;
+                double a[SB];
+#pragma unroll
+                for (int c = 0; c < SB; ++c) a[c] = Ls[(k0 + c) * LDL + row];
+#pragma unroll
+                for (int k = 0; k < SB; ++k) {
+                    const double xk = a[k] * rdiag[k0 + k];
+                    a[k] = xk;
+#pragma unroll
+                    for (int c = k + 1; c < SB; ++c) a[c] = fma(-xk, Ls[(k0 + k) * LDL + k0 + c], a[c]);
+                }
+#pragma unroll
+                for (int c = 0; c < SB; ++c) Ls[(k0 + c) * LDL + row] = a[c];
+            }
+            __syncthreads();
+            const int i = tid & (NB - 1), ty = tid >> 6;
+            if (i >= k0 + SB) {
+                double li[SB];
+#pragma unroll
+                for (int k = 0; k < SB; ++k) li[k] = Ls[(k0 + k) * LDL + i];
+                for (int j = k0 + SB + ty; j <= i; j += PANEL_THREADS / NB) {
+                    double dot = 0.0;
+#pragma unroll
+                    for (int k = 0; k < SB; ++k) dot = fma(li[k], Ls[(k0 + k) * LDL + j], dot);
+                    Ls[j * LDL + i] -= dot;
+                }
+            }
+            __syncthreads();
+        }
     }
-    __syncthreads();
     return fail;
 }
 
@@ -61,22 +111,21 @@ __device__ int factor_block_smem(double* Ls, double* rdiag) {
 // 256 rows of the panel below:  L21 = A21 * L11^-T  (one thread per row, unrolled substitution in registers).
 __global__ void __launch_bounds__(PANEL_THREADS, 1) potrf_panel_kernel(double* __restrict__ A, int64_t ld, int D, int j0,
                                                                        int* __restrict__ info) {
-    __shared__ double Ls[NB * 65];
+    __shared__ __align__(16) double Ls[NB * LDL];
     __shared__ double rdiag[NB];
     const int nbj = min(NB, D - j0);
     for (int e = threadIdx.x; e < NB * NB; e += PANEL_THREADS) {
         const int r = e % NB, c = e / NB;
         double v = (r == c) ? 1.0 : 0.0;
         if (r < nbj && c < nbj && r >= c) v = A[(int64_t)(j0 + c) * ld + j0 + r];
-        Ls[c * 65 + r] = v;
+        Ls[c * LDL + r] = v;
     }
     __syncthreads();
     const int fail = factor_block_smem(Ls, rdiag);
-    // L[r][c] (r >= c) now lives at Ls[r * 65 + c]
     if (blockIdx.x == 0) {
         for (int e = threadIdx.x; e < NB * NB; e += PANEL_THREADS) {
             const int r = e % NB, c = e / NB;
-            if (r < nbj && c < nbj) A[(int64_t)(j0 + c) * ld + j0 + r] = (r >= c) ? Ls[r * 65 + c] : 0.0;
+            if (r < nbj && c < nbj) A[(int64_t)(j0 + c) * ld + j0 + r] = (r >= c) ? Ls[c * LDL + r] : 0.0;
         }
         if (threadIdx.x == 0 && fail != 0 && *info == 0) *info = j0 + fail;
     }
@@ -90,7 +139,7 @@ __global__ void __launch_bounds__(PANEL_THREADS, 1) potrf_panel_kernel(double* _
             const double xk = a[k] * rdiag[k];
             a[k] = xk;
 #pragma unroll
-            for (int c = k + 1; c < NB; ++c) a[c] = fma(-xk, Ls[c * 65 + k], a[c]);  // L[c][k], broadcast read
+            for (int c = k + 1; c < NB; ++c) a[c] = fma(-xk, Ls[k * LDL + c], a[c]);  // L[c][k], broadcast read
         }
 #pragma unroll
         for (int c = 0; c < NB; ++c) A[(int64_t)(j0 + c) * ld + row] = a[c];
@@ -575,12 +624,13 @@ int infer_solve(blr_ctx* ctx, const blr_prior* prior, const blr_stats* st, doubl
     BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[5], sm));
     ctx->ev_valid[3] = true;
 
-    rc = read_info(ctx, &info);
-    if (rc != 0) return fail(rc);
-    if (info != 0) return fail(info);
-
-    if (logpdf_out) BLR_CUDA_OK(ctx, cudaMemcpyAsync(logpdf_out, sc + 3, sizeof(double), cudaMemcpyDeviceToHost, sm));
-    if (m_post) BLR_CUDA_OK(ctx, cudaMemcpyAsync(m_post, p->mw, (size_t)D * sizeof(double), cudaMemcpyDeviceToHost, sm));
+    // Results: the small ones (pivot status, logpdf, m') go through page-locked staging so that every copy is truly
+    // asynchronous and the whole inference costs ONE host synchronisation (a cudaMemcpyAsync into pageable memory
+    // blocks the host, i.e. one GPU-idle round trip per output).
+    double* hr = ctx->h_res;
+    BLR_CUDA_OK(ctx, cudaMemcpyAsync(hr, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, sm));
+    if (logpdf_out) BLR_CUDA_OK(ctx, cudaMemcpyAsync(hr + 1, sc + 3, sizeof(double), cudaMemcpyDeviceToHost, sm));
+    if (m_post) BLR_CUDA_OK(ctx, cudaMemcpyAsync(hr + 2, p->mw, (size_t)D * sizeof(double), cudaMemcpyDeviceToHost, sm));
     if (L_post) BLR_CUDA_OK(ctx, cudaMemcpyAsync(L_post, p->Lam, (size_t)n2 * sizeof(double), cudaMemcpyDeviceToHost, sm));
     if (T_post) {
         // T = L'^T (upper).  Transpose into the (not yet built) W buffer, then download.
@@ -591,6 +641,10 @@ int infer_solve(blr_ctx* ctx, const blr_prior* prior, const blr_stats* st, doubl
         BLR_CUDA_OK(ctx, cudaMemcpyAsync(T_post, p->W, (size_t)n2 * sizeof(double), cudaMemcpyDeviceToHost, sm));
     }
     BLR_CUDA_OK(ctx, cudaStreamSynchronize(sm));
+    memcpy(&info, hr, sizeof(int));
+    if (info != 0) return fail(info);  // non-positive pivot: the outputs above are not meaningful
+    if (logpdf_out) *logpdf_out = hr[1];
+    if (m_post) memcpy(m_post, hr + 2, (size_t)D * sizeof(double));
     if (post_out)
         *post_out = p;
     else

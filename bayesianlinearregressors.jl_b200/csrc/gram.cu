@@ -617,6 +617,15 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
     }
     BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], sm));
 
+    // ---- smallest D: one warp holds the whole Gram matrix, observations stream straight from HBM, K0 fused in
+    if (gram_small_fused(D)) {
+        BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[1], sm));
+        BLR_TRY(gram_small(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, nullptr, nullptr, ctx->small + SMALL_PREP, 0));
+        BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], sm));
+        ctx->ev_valid[0] = ctx->ev_valid[1] = ctx->ev_valid[2] = true;
+        return 0;
+    }
+
     // ---- K0: prep
     const int64_t npad = round_up(N, gk::KT_MAX) + gk::KT_MAX;
     BLR_TRY(ensure_nbuf(ctx, (size_t)(2 * npad) * sizeof(double)));
@@ -643,9 +652,9 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
     BLR_CHECK_LAUNCH(ctx, "prep_kernel");
     BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[1], sm));
 
-    // ---- K1, small D: one warp holds the whole Gram matrix, observations stream straight from HBM
+    // ---- K1, small D: same streaming kernel, s / t from K0
     if (D <= 64) {
-        BLR_TRY(gram_small(ctx, st, x, s, t, prep_partial, prep_blocks));
+        BLR_TRY(gram_small(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, s, t, prep_partial, prep_blocks));
         BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], sm));
         ctx->ev_valid[0] = ctx->ev_valid[1] = ctx->ev_valid[2] = true;
         return 0;

@@ -6,7 +6,7 @@
 // the m8n8k4 operand fragments are loaded straight from global memory -- lane (g, k) reads element (feature 8*mi + g,
 // observation n + k), which for ColVecs is 8 consecutive doubles per observation and for RowVecs 4 consecutive doubles
 // per feature, i.e. whole 32-byte sectors either way -- and the B fragment is the A fragment times s_k, so X is read
-// exactly once and nothing is staged in shared memory.  Works for any D <= 64, any leading dimension / alignment and
+// exactly once and nothing is staged in shared memory.  The preparation pass (s = 1/σ², t = s δ, q, ℓ) is fused in.  Works for any D <= 64, any leading dimension / alignment and
 // both layouts (plain 8-byte loads).  Per-CTA partial matrices are summed in a fixed order by gram_small_reduce_kernel.
 #include <math.h>
 
@@ -19,50 +19,144 @@ namespace blr {
 namespace gs {
 constexpr int WARPS = 8;
 constexpr int THREADS = WARPS * 32;
+constexpr int ctas_per_sm(int MI) { return MI == 1 ? 3 : (MI == 8 ? 1 : 2); }  // register budget: 85 / 128 / 255 per thread
 }  // namespace gs
 
-template <int MI>
-__global__ void __launch_bounds__(gs::THREADS, (MI == 8 ? 1 : (MI == 4 ? 2 : 4)))
-    gram_small_kernel(const double* __restrict__ X, int64_t sd, int64_t sn, int D, int64_t N, const double* __restrict__ s,
-                      const double* __restrict__ t, double* __restrict__ P, double* __restrict__ Pr, int64_t obs_per_warp) {
+// K0 is fused in: the kernel reads y and σ² itself.  Per trip a warp takes 32 observations; lane L first handles
+// observation n + L on its own (coalesced loads of y and σ², s = 1/σ², log σ² -- one divide and one log per observation,
+// not per fragment lane), then the eight k4 steps fetch s and y for their fragment lanes by shuffle.  δ = y - x'mw is
+// formed from the fragments already in registers (three xor-shuffles over the feature lanes) when the prior mean is
+// non-zero.  So the whole path reads 8 (D + 2) bytes per observation -- the algorithmic minimum -- and writes nothing
+// but the per-CTA partials.
+// FUSED == false (D > 16, where the extra shuffles cost more than the 32 bytes per observation they save): s and t come
+// from the separate preparation kernel in gram.cu, as do q and ℓ.
+template <int MI, bool HAS_MEAN, bool FUSED>
+__global__ void __launch_bounds__(gs::THREADS, gs::ctas_per_sm(MI))
+    gram_small_kernel(const double* __restrict__ X, int64_t sd, int64_t sn, int D, int64_t N, const double* __restrict__ y,
+                      const double* __restrict__ sigma2, double sigma2_scalar, const double* __restrict__ mw,
+                      const double* __restrict__ s, const double* __restrict__ t, double* __restrict__ P,
+                      double* __restrict__ Pr, double* __restrict__ Pq, int64_t obs_per_warp) {
     using namespace gs;
     constexpr int DP = MI * 8;
     __shared__ double tile[DP * DP];
     __shared__ double rsum[DP];
+    __shared__ double qsum[WARPS][2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, kq = lane & 3;
     const int64_t wid = (int64_t)blockIdx.x * WARPS + warp;
     const int64_t n0 = wid * obs_per_warp, n1 = min(N, n0 + obs_per_warp);
 
     double acc[MI][MI][2];
-    double racc[MI];
+    double racc[MI], mwr[MI];
     bool rowok[MI];
-    const double* xrow[MI];
+    const double* xbase = X + (int64_t)g * sd;
+    const int64_t sd8 = 8 * sd;
 #pragma unroll
     for (int mi = 0; mi < MI; ++mi) {
         racc[mi] = 0.0;
         rowok[mi] = (mi * 8 + g) < D;
-        xrow[mi] = X + (int64_t)(mi * 8 + g) * sd;
+        mwr[mi] = (HAS_MEAN && rowok[mi]) ? mw[mi * 8 + g] : 0.0;
 #pragma unroll
         for (int ni = 0; ni < MI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
     }
-#pragma unroll 2
-    for (int64_t n = n0; n < n1; n += 4) {
-        const int64_t nk = n + kq;
-        const bool ok = nk < n1;
-        const double sk = ok ? s[nk] : 0.0, tk = ok ? t[nk] : 0.0;
-        double a[MI], b[MI];
+    double qacc = 0.0, lacc = 0.0;
+    if (FUSED) {
+        // Software-pipelined over trips of 32 observations: the loads of trip i + 1 (lane-own y, σ² and the eight fragment
+        // steps) are issued before trip i is reduced, so two trips per warp are in flight -- with only a few doubles per
+        // observation the kernel is bound by bytes in flight (Little: ~6.5 MB for HBM at ~1 us), not by the tensor pipe.
+        double a[8][MI], vo, yo;
+        auto load_trip = [&](int64_t n, double (&aa)[8][MI], double& v, double& yy) {
+            const int64_t no = n + lane;
+            const bool oko = no < n1;
+            v = oko ? (sigma2 ? sigma2[no] : sigma2_scalar) : 1.0;
+            yy = oko ? y[no] : 0.0;
 #pragma unroll
-        for (int mi = 0; mi < MI; ++mi) a[mi] = (ok && rowok[mi]) ? xrow[mi][nk * sn] : 0.0;
+            for (int u = 0; u < 8; ++u) {
+                const int64_t nk = n + 4 * u + kq;
+                const bool ok = nk < n1;
 #pragma unroll
-        for (int mi = 0; mi < MI; ++mi) {
-            racc[mi] = fma(a[mi], tk, racc[mi]);
-            b[mi] = a[mi] * sk;
+                for (int mi = 0; mi < MI; ++mi) aa[u][mi] = (ok && rowok[mi]) ? xbase[mi * sd8 + nk * sn] : 0.0;
+            }
+        };
+        load_trip(n0, a, vo, yo);
+        for (int64_t n = n0; n < n1; n += 32) {
+            double an[8][MI], vn, yn;
+            load_trip(n + 32, an, vn, yn);  // fully predicated off past n1
+            const double so = (n + lane < n1) ? 1.0 / vo : 0.0;
+            lacc += log(vo);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int src = 4 * u + kq;
+                const double sk = __shfl_sync(0xffffffffu, so, src);
+                double dk = __shfl_sync(0xffffffffu, yo, src);
+                if (HAS_MEAN) {
+                    double dot = 0.0;
+#pragma unroll
+                    for (int mi = 0; mi < MI; ++mi) dot = fma(a[u][mi], mwr[mi], dot);
+                    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+                    dot += __shfl_xor_sync(0xffffffffu, dot, 8);
+                    dot += __shfl_xor_sync(0xffffffffu, dot, 16);
+                    dk -= dot;
+                }
+                const double tk = sk * dk;
+                qacc = fma(tk, dk, qacc);  // identical on the eight feature lanes of an observation; lanes g == 0 count
+                double b[MI];
+#pragma unroll
+                for (int mi = 0; mi < MI; ++mi) {
+                    racc[mi] = fma(a[u][mi], tk, racc[mi]);
+                    b[mi] = a[u][mi] * sk;
+                }
+#pragma unroll
+                for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni <= mi; ++ni) dmma884(acc[mi][ni], a[u][mi], b[ni]);
+            }
+            vo = vn;
+            yo = yn;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int mi = 0; mi < MI; ++mi) a[u][mi] = an[u][mi];
         }
+    } else {
+        // U k4-steps per batch, all loads issued before the first DMMA
+        constexpr int U = 2;
+        for (int64_t n = n0; n < n1; n += 32) {
+#pragma unroll(MI == 8 ? 1 : 2)
+            for (int u0 = 0; u0 < 8; u0 += U) {
+                double a[U][MI], sk[U], tk[U];
 #pragma unroll
-        for (int mi = 0; mi < MI; ++mi)
+                for (int u = 0; u < U; ++u) {
+                    const int64_t nk = n + 4 * (u0 + u) + kq;
+                    const bool ok = nk < n1;
+                    sk[u] = ok ? s[nk] : 0.0;
+                    tk[u] = ok ? t[nk] : 0.0;
 #pragma unroll
-            for (int ni = 0; ni <= mi; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
+                    for (int mi = 0; mi < MI; ++mi) a[u][mi] = (ok && rowok[mi]) ? xbase[mi * sd8 + nk * sn] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    double b[MI];
+#pragma unroll
+                    for (int mi = 0; mi < MI; ++mi) {
+                        racc[mi] = fma(a[u][mi], tk[u], racc[mi]);
+                        b[mi] = a[u][mi] * sk[u];
+                    }
+#pragma unroll
+                    for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni <= mi; ++ni) dmma884(acc[mi][ni], a[u][mi], b[ni]);
+                }
+            }
+        }
+    }
+    // q: the four observation lanes with g == 0; ℓ: all 32 lanes (xor tree: fixed order)
+    if (g != 0) qacc = 0.0;
+    qacc = warp_sum(qacc);
+    lacc = warp_sum(lacc);
+    if (lane == 0) {
+        qsum[warp][0] = qacc;
+        qsum[warp][1] = lacc;
     }
     // r: fold the four observation lanes of every feature
 #pragma unroll
@@ -92,6 +186,113 @@ __global__ void __launch_bounds__(gs::THREADS, (MI == 8 ? 1 : (MI == 4 ? 2 : 4))
     double* Pt = P + (int64_t)blockIdx.x * (DP * DP);
     for (int e = tid; e < DP * DP; e += THREADS) Pt[e] = tile[e];
     if (tid < DP) Pr[(int64_t)blockIdx.x * DP + tid] = rsum[tid];
+    if (FUSED && tid == 0) {
+        double q = 0.0, l = 0.0;
+        for (int w = 0; w < WARPS; ++w) {
+            q += qsum[w][0];
+            l += qsum[w][1];
+        }
+        Pq[2 * blockIdx.x] = q;
+        Pq[2 * blockIdx.x + 1] = l;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// D <= 8: one THREAD per observation.  With so few features an m8n8k4 tile is mostly padding and the warp-per-4-
+// observations schedule above is bound by instruction issue (~11 warp instructions per observation); here a warp
+// instruction advances 32 observations: D (D + 1) / 2 + 2 D + 3 DFMAs, one divide and one log per observation per lane,
+// statistics in registers, X / y / σ² read exactly once with fully coalesced loads (ColVecs with ld == D: 16-byte vector
+// loads over a contiguous stream; any other layout: 8-byte loads, coalesced over observations for RowVecs).  K0 is fused.
+// Per-CTA partials use the 8 x 8 layout of the kernel above, so gram_small_reduce_kernel finishes both.
+namespace gt {
+__host__ __device__ constexpr int threads(int DT) { return DT == 8 ? 128 : 256; }
+constexpr int ctas_per_sm(int DT) { return DT == 2 ? 4 : 3; }  // register budget per thread: 64 (DT 2), 85 (4), 168 (8)
+}  // namespace gt
+
+template <int DT, bool HAS_MEAN, bool VEC>
+__global__ void __launch_bounds__(gt::threads(DT), gt::ctas_per_sm(DT))
+    gram_tiny_kernel(const double* __restrict__ X, int64_t sd, int64_t sn, int D, int64_t N, const double* __restrict__ y,
+                     const double* __restrict__ sigma2, double sigma2_scalar, const double* __restrict__ mw,
+                     double* __restrict__ P, double* __restrict__ Pr, double* __restrict__ Pq) {
+    constexpr int THREADS = gt::threads(DT);
+    constexpr int NG = DT * (DT + 1) / 2;
+    __shared__ double red[THREADS / 32][NG + DT + 2];
+    double G[NG], r[DT], mwr[DT], q = 0.0, l = 0.0;
+#pragma unroll
+    for (int e = 0; e < NG; ++e) G[e] = 0.0;
+#pragma unroll
+    for (int d = 0; d < DT; ++d) {
+        r[d] = 0.0;
+        mwr[d] = (HAS_MEAN && d < D) ? mw[d] : 0.0;
+    }
+    const int64_t stride = (int64_t)gridDim.x * THREADS;
+#pragma unroll(DT == 8 ? 1 : 2)
+    for (int64_t n = (int64_t)blockIdx.x * THREADS + threadIdx.x; n < N; n += stride) {
+        double x[DT];
+        if (VEC) {  // ColVecs, ld == D == DT, 16-byte aligned base: the observation is DT / 2 aligned double2
+            const double2* col = reinterpret_cast<const double2*>(X + n * DT);
+#pragma unroll
+            for (int h = 0; h < DT / 2; ++h) {
+                const double2 v2 = col[h];
+                x[2 * h] = v2.x;
+                x[2 * h + 1] = v2.y;
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < DT; ++d) x[d] = (d < D) ? X[(int64_t)d * sd + n * sn] : 0.0;
+        }
+        const double v = sigma2 ? sigma2[n] : sigma2_scalar;
+        double dl = y[n];
+        const double sk = 1.0 / v;
+        l += log(v);
+        if (HAS_MEAN) {
+#pragma unroll
+            for (int d = 0; d < DT; ++d) dl = fma(-x[d], mwr[d], dl);
+        }
+        const double tk = sk * dl;
+        q = fma(tk, dl, q);
+#pragma unroll
+        for (int i = 0; i < DT; ++i) {
+            r[i] = fma(x[i], tk, r[i]);
+            const double xs = x[i] * sk;
+#pragma unroll
+            for (int j = 0; j <= i; ++j) G[i * (i + 1) / 2 + j] = fma(xs, x[j], G[i * (i + 1) / 2 + j]);
+        }
+    }
+    // CTA reduction: xor tree inside the warp, then warps in index order (fixed => bit-reproducible)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int e = 0; e < NG; ++e) {
+        const double t = warp_sum(G[e]);
+        if (lane == 0) red[warp][e] = t;
+    }
+#pragma unroll
+    for (int d = 0; d < DT; ++d) {
+        const double t = warp_sum(r[d]);
+        if (lane == 0) red[warp][NG + d] = t;
+    }
+    q = warp_sum(q);
+    l = warp_sum(l);
+    if (lane == 0) {
+        red[warp][NG + DT] = q;
+        red[warp][NG + DT + 1] = l;
+    }
+    __syncthreads();
+    if (threadIdx.x < NG + DT + 2) {
+        double t = 0.0;
+        for (int w = 0; w < THREADS / 32; ++w) t += red[w][threadIdx.x];
+        const int e = threadIdx.x;
+        if (e < NG) {
+            int i = 0;
+            while ((i + 1) * (i + 2) / 2 <= e) ++i;
+            const int j = e - i * (i + 1) / 2;
+            P[(int64_t)blockIdx.x * 64 + i * 8 + j] = t;  // 8 x 8 tile, element (row i, col j <= i)
+        } else if (e < NG + DT) {
+            Pr[(int64_t)blockIdx.x * 8 + (e - NG)] = t;
+        } else {
+            Pq[2 * blockIdx.x + (e - NG - DT)] = t;
+        }
+    }
 }
 
 // stats.G += Σ_blocks P (lower part mirrored), stats.r += Σ_blocks Pr, scalars from the prep partials.
@@ -133,39 +334,86 @@ __global__ void __launch_bounds__(256) gram_small_reduce_kernel(const double* __
     }
 }
 
-template <int MI>
-static int launch_small(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double* s, const double* t,
-                        const double* prep_partial, int prep_blocks) {
+// FUSED: `partial` receives this launch's per-CTA (q, ℓ) partials; otherwise it holds the preparation kernel's
+// `partial_blocks` partials and s, t are its outputs.
+template <int MI, bool FUSED>
+static int launch_small(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double* y, const double* sigma2,
+                        double sigma2_scalar, const double* mw_dev, bool mw_is_zero, const double* s, const double* t,
+                        double* partial, int partial_blocks) {
     constexpr int DP = MI * 8;
     const int D = (int)x->D;
     const int64_t N = x->N;
-    const int per_sm = (MI == 8 ? 1 : (MI == 4 ? 2 : 4));
+    const int per_sm = gs::ctas_per_sm(MI);
     int nblocks = ctx->sm_count * per_sm;
-    const int64_t groups = (N + 3) / 4;  // k4 steps
-    nblocks = (int)std::max<int64_t>(1, std::min<int64_t>(nblocks, (groups + gs::WARPS * 8 - 1) / (gs::WARPS * 8)));
+    const int64_t groups = (N + 31) / 32;  // warp trips of 32 observations
+    nblocks = (int)std::max<int64_t>(1, std::min<int64_t>(nblocks, (groups + gs::WARPS - 1) / gs::WARPS));
     const int64_t total_warps = (int64_t)nblocks * gs::WARPS;
-    const int64_t obs_per_warp = ((groups + total_warps - 1) / total_warps) * 4;
+    const int64_t obs_per_warp = ((groups + total_warps - 1) / total_warps) * 32;
     BLR_TRY(ensure_ws(ctx, (size_t)nblocks * (DP * DP + DP) * sizeof(double)));
     double* P = ctx->ws;
     double* Pr = ctx->ws + (size_t)nblocks * DP * DP;
     const bool colv = x->layout == BLR_COLVECS;
     const int64_t sd = colv ? 1 : x->ld, sn = colv ? x->ld : 1;
-    gram_small_kernel<MI><<<nblocks, gs::THREADS, 0, ctx->stream>>>(x->p, sd, sn, D, N, s, t, P, Pr, obs_per_warp);
+    if (FUSED && !mw_is_zero)
+        gram_small_kernel<MI, true, FUSED><<<nblocks, gs::THREADS, 0, ctx->stream>>>(
+            x->p, sd, sn, D, N, y, sigma2, sigma2_scalar, mw_dev, s, t, P, Pr, partial, obs_per_warp);
+    else
+        gram_small_kernel<MI, false, FUSED><<<nblocks, gs::THREADS, 0, ctx->stream>>>(
+            x->p, sd, sn, D, N, y, sigma2, sigma2_scalar, mw_dev, s, t, P, Pr, partial, obs_per_warp);
     BLR_CHECK_LAUNCH(ctx, "gram_small_kernel");
     BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     gram_small_reduce_kernel<<<(DP * DP + 255) / 256, 256, 0, ctx->stream>>>(P, Pr, DP, nblocks, D, st->G(), st->r(), st->scal(),
-                                                                            prep_partial, prep_blocks, (double)N);
+                                                                            partial, FUSED ? nblocks : partial_blocks, (double)N);
     BLR_CHECK_LAUNCH(ctx, "gram_small_reduce_kernel");
     return 0;
 }
 
-int gram_small(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double* s, const double* t, const double* prep_partial,
-               int prep_blocks) {
+bool gram_small_fused(int64_t D) { return D <= 16; }
+
+template <int DT>
+static int launch_tiny(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double* y, const double* sigma2,
+                       double sigma2_scalar, const double* mw_dev, bool mw_is_zero, double* partial) {
     const int D = (int)x->D;
-    if (D <= 8) return launch_small<1>(ctx, st, x, s, t, prep_partial, prep_blocks);
-    if (D <= 16) return launch_small<2>(ctx, st, x, s, t, prep_partial, prep_blocks);
-    if (D <= 32) return launch_small<4>(ctx, st, x, s, t, prep_partial, prep_blocks);
-    return launch_small<8>(ctx, st, x, s, t, prep_partial, prep_blocks);
+    const int64_t N = x->N;
+    constexpr int THREADS = gt::threads(DT);
+    const int nblocks =
+        (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * gt::ctas_per_sm(DT), (N + THREADS - 1) / THREADS));
+    BLR_TRY(ensure_ws(ctx, (size_t)nblocks * (64 + 8) * sizeof(double)));
+    double* P = ctx->ws;
+    double* Pr = ctx->ws + (size_t)nblocks * 64;
+    const bool colv = x->layout == BLR_COLVECS;
+    const int64_t sd = colv ? 1 : x->ld, sn = colv ? x->ld : 1;
+    const bool vec = colv && D == DT && x->ld == DT && (reinterpret_cast<uintptr_t>(x->p) & 15) == 0;
+#define BLR_TINY(HM, VC)                                                                                              \
+    gram_tiny_kernel<DT, HM, VC><<<nblocks, THREADS, 0, ctx->stream>>>(x->p, sd, sn, D, N, y, sigma2, sigma2_scalar, \
+                                                                          mw_dev, P, Pr, partial)
+    if (mw_is_zero) {
+        if (vec) BLR_TINY(false, true);
+        else BLR_TINY(false, false);
+    } else {
+        if (vec) BLR_TINY(true, true);
+        else BLR_TINY(true, false);
+    }
+#undef BLR_TINY
+    BLR_CHECK_LAUNCH(ctx, "gram_tiny_kernel");
+    BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    gram_small_reduce_kernel<<<1, 256, 0, ctx->stream>>>(P, Pr, 8, nblocks, D, st->G(), st->r(), st->scal(), partial, nblocks,
+                                                         (double)N);
+    BLR_CHECK_LAUNCH(ctx, "gram_small_reduce_kernel");
+    return 0;
+}
+
+int gram_small(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double* y, const double* sigma2, double sigma2_scalar,
+               const double* mw_dev, bool mw_is_zero, const double* s, const double* t, double* partial, int partial_blocks) {
+    const int D = (int)x->D;
+    if (D <= 2) return launch_tiny<2>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, partial);
+    if (D <= 4) return launch_tiny<4>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, partial);
+    if (D <= 8) return launch_tiny<8>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, partial);
+    if (D <= 16)
+        return launch_small<2, true>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, s, t, partial, partial_blocks);
+    if (D <= 32)
+        return launch_small<4, false>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, s, t, partial, partial_blocks);
+    return launch_small<8, false>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, s, t, partial, partial_blocks);
 }
 
 }  // namespace blr

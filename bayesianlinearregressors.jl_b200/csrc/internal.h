@@ -55,6 +55,7 @@ struct blr_ctx {
     double* small = nullptr;  // small device scratch (scalars, block partial sums)
     size_t small_bytes = 0;
     int* d_info = nullptr;
+    double* h_res = nullptr;  // page-locked result staging: [info | logpdf | m_post (SMALL_VEC)] -> one sync per inference
     int* d_flags = nullptr;  // wavefront-solve ready flags (one per 64-row block), compared against flag_epoch
     int flag_epoch = 0;
     cudaEvent_t ev[8] = {};
@@ -121,9 +122,11 @@ int ensure_dinv(blr_ctx* ctx, size_t bytes);
 int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_is_zero, const blr_x* x,
                     const double* y, const double* sigma2, double sigma2_scalar);
 
-// ---- gram_small.cu: D <= 64, any layout / alignment; adds this shard's statistics into st (uses prep's s, t)
-int gram_small(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double* s, const double* t, const double* prep_partial,
-               int prep_blocks);
+// ---- gram_small.cu: D <= 64, any layout / alignment; adds this shard's statistics into st.  D <= 16: K0 fused (reads
+// y, σ² itself, s / t unused, `partial` is scratch for 2 doubles per CTA); otherwise s, t, partial come from prep_kernel.
+bool gram_small_fused(int64_t D);
+int gram_small(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double* y, const double* sigma2, double sigma2_scalar,
+               const double* mw_dev, bool mw_is_zero, const double* s, const double* t, double* partial, int partial_blocks);
 
 // ---- chol.cu
 // In-place lower Cholesky of the column-major D x D matrix A (only the lower triangle is read);

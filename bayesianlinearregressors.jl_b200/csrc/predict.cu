@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(bg::THREADS) var_kernel(const double* __restri
 // into m8n8k4 B fragments (lane (k, g) reads feature 4*kk + k of point p + g: whole 32-byte sectors in both layouts),
 // α = W x stays in 2 accumulators per 8-row block, squares are folded by shuffles; the mean rides on the same fragments.
 template <int MI>
-__global__ void __launch_bounds__(256) var_small_kernel(const double* __restrict__ W, const double* __restrict__ mw, int D,
+__global__ void __launch_bounds__(256, 2) var_small_kernel(const double* __restrict__ W, const double* __restrict__ mw, int D,
                                                         const double* __restrict__ X, int64_t sd, int64_t sn, int64_t N,
                                                         const double* __restrict__ sigma2, double sigma2_scalar,
                                                         double* __restrict__ mean, double* __restrict__ var) {
@@ -142,50 +142,125 @@ __global__ void __launch_bounds__(256) var_small_kernel(const double* __restrict
     double a_mw[KK];
 #pragma unroll
     for (int kk = 0; kk < KK; ++kk) a_mw[kk] = mws[kk * 4 + kq];
-    for (int64_t grp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); grp < ngroups; grp += nwarps) {
-        const int64_t p0 = grp * 8, pt = p0 + g;
-        const bool pok = pt < N;
-        double b[KK];
+    // GB groups of 8 points per trip, loads first: like the small-D Gram kernel this is bound by bytes in flight
+    constexpr int GB = (MI == 1 ? 8 : (MI == 2 ? 4 : 1));
+    for (int64_t grp0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * GB; grp0 < ngroups; grp0 += nwarps * GB) {
+        double b[GB][KK];
 #pragma unroll
-        for (int kk = 0; kk < KK; ++kk) {
-            const int k = kk * 4 + kq;
-            b[kk] = (pok && k < D) ? X[(int64_t)k * sd + pt * sn] : 0.0;
-        }
-        double acc[MI][2];
+        for (int gb = 0; gb < GB; ++gb) {
+            const int64_t pt = (grp0 + gb) * 8 + g;
+            const bool pok = pt < N;
 #pragma unroll
-        for (int mi = 0; mi < MI; ++mi) acc[mi][0] = acc[mi][1] = 0.0;
-        double macc = 0.0;
-#pragma unroll
-        for (int kk = 0; kk < KK; ++kk) {
-            macc = fma(a_mw[kk], b[kk], macc);
-#pragma unroll
-            for (int mi = 0; mi < MI; ++mi) {
-                if (mi * 8 + 7 >= kk * 4) {  // W[m, k] = 0 for k > m: static triangular skip
-                    const double a = Ws[(kk * 4 + kq) * LDW + mi * 8 + g];
-                    dmma884(acc[mi], a, b[kk]);
-                }
+            for (int kk = 0; kk < KK; ++kk) {
+                const int k = kk * 4 + kq;
+                b[gb][kk] = (pok && k < D) ? X[(int64_t)k * sd + pt * sn] : 0.0;
             }
         }
-        double v0 = 0.0, v1 = 0.0;
 #pragma unroll
-        for (int mi = 0; mi < MI; ++mi) {
-            v0 = fma(acc[mi][0], acc[mi][0], v0);
-            v1 = fma(acc[mi][1], acc[mi][1], v1);
-        }
+        for (int gb = 0; gb < GB; ++gb) {
+            const int64_t p0 = (grp0 + gb) * 8, pt = p0 + g;
+            if (p0 >= N) break;
+            const bool pok = pt < N;
+            double acc[MI][2];
 #pragma unroll
-        for (int o = 4; o <= 16; o <<= 1) {
-            v0 += __shfl_xor_sync(0xffffffffu, v0, o);
-            v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+            for (int mi = 0; mi < MI; ++mi) acc[mi][0] = acc[mi][1] = 0.0;
+            double macc = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < KK; ++kk) {
+                macc = fma(a_mw[kk], b[gb][kk], macc);
+#pragma unroll
+                for (int mi = 0; mi < MI; ++mi) {
+                    if (mi * 8 + 7 >= kk * 4) {  // W[m, k] = 0 for k > m: static triangular skip
+                        const double a = Ws[(kk * 4 + kq) * LDW + mi * 8 + g];
+                        dmma884(acc[mi], a, b[gb][kk]);
+                    }
+                }
+            }
+            double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+            for (int mi = 0; mi < MI; ++mi) {
+                v0 = fma(acc[mi][0], acc[mi][0], v0);
+                v1 = fma(acc[mi][1], acc[mi][1], v1);
+            }
+#pragma unroll
+            for (int o = 4; o <= 16; o <<= 1) {
+                v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+                v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+            }
+            macc += __shfl_xor_sync(0xffffffffu, macc, 1);
+            macc += __shfl_xor_sync(0xffffffffu, macc, 2);
+            if (var && g == 0) {  // lane kq owns points p0 + 2 kq, p0 + 2 kq + 1
+                const int64_t q0 = p0 + kq * 2;
+                if (q0 < N) var[q0] = v0 + (sigma2 ? sigma2[q0] : sigma2_scalar);
+                if (q0 + 1 < N) var[q0 + 1] = v1 + (sigma2 ? sigma2[q0 + 1] : sigma2_scalar);
+            }
+            if (mean && kq == 0 && pok) mean[pt] = macc;
         }
-        macc += __shfl_xor_sync(0xffffffffu, macc, 1);
-        macc += __shfl_xor_sync(0xffffffffu, macc, 2);
-        if (var && g == 0) {  // lane kq owns points p0 + 2 kq, p0 + 2 kq + 1
-            const int64_t q0 = p0 + kq * 2;
-            if (q0 < N) var[q0] = v0 + (sigma2 ? sigma2[q0] : sigma2_scalar);
-            if (q0 + 1 < N) var[q0 + 1] = v1 + (sigma2 ? sigma2[q0 + 1] : sigma2_scalar);
-        }
-        if (mean && kq == 0 && pok) mean[pt] = macc;
     }
+}
+
+// D <= 8: one thread per test point (an m8n8k4 tile would be mostly padding and the warp-per-8-points schedule above is
+// bound by instruction issue): W (lower triangle) and mw live in registers, X is read once with coalesced loads
+// (16-byte vector loads for ColVecs with ld == D), D (D + 1) / 2 + 2 D DFMAs per point.
+template <int DT, bool VEC>
+__global__ void __launch_bounds__(DT == 8 ? 128 : 256, DT == 2 ? 4 : 3)
+    var_tiny_kernel(const double* __restrict__ W, const double* __restrict__ mw, int D, const double* __restrict__ X,
+                    int64_t sd, int64_t sn, int64_t N, const double* __restrict__ sigma2, double sigma2_scalar,
+                    double* __restrict__ mean, double* __restrict__ var) {
+    double w[DT * (DT + 1) / 2], m[DT];
+#pragma unroll
+    for (int i = 0; i < DT; ++i) {
+        m[i] = i < D ? mw[i] : 0.0;
+#pragma unroll
+        for (int k = 0; k <= i; ++k) w[i * (i + 1) / 2 + k] = (i < D) ? W[(int64_t)k * D + i] : 0.0;
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+#pragma unroll(DT == 8 ? 1 : 2)
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += stride) {
+        double x[DT];
+        if (VEC) {
+            const double2* col = reinterpret_cast<const double2*>(X + n * DT);
+#pragma unroll
+            for (int h = 0; h < DT / 2; ++h) {
+                const double2 v2 = col[h];
+                x[2 * h] = v2.x;
+                x[2 * h + 1] = v2.y;
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < DT; ++d) x[d] = (d < D) ? X[(int64_t)d * sd + n * sn] : 0.0;
+        }
+        double v = 0.0, mu = 0.0;
+#pragma unroll
+        for (int i = 0; i < DT; ++i) {
+            mu = fma(x[i], m[i], mu);
+            double al = 0.0;
+#pragma unroll
+            for (int k = 0; k <= i; ++k) al = fma(w[i * (i + 1) / 2 + k], x[k], al);
+            v = fma(al, al, v);
+        }
+        if (var) var[n] = v + (sigma2 ? sigma2[n] : sigma2_scalar);
+        if (mean) mean[n] = mu;
+    }
+}
+
+template <int DT>
+static int launch_var_tiny(blr_ctx* ctx, blr_post* p, const blr_x* x, const double* sigma2, double sigma2_scalar,
+                           double* mean_dev, double* var_dev) {
+    constexpr int THREADS = DT == 8 ? 128 : 256;
+    const bool colv = x->layout == BLR_COLVECS;
+    const int64_t sd = colv ? 1 : x->ld, sn = colv ? x->ld : 1;
+    const int grid = (int)std::max<int64_t>(
+        1, std::min<int64_t>((x->N + THREADS - 1) / THREADS, (int64_t)ctx->sm_count * (DT == 2 ? 4 : 3)));
+    const bool vec = colv && p->D == DT && x->ld == DT && (reinterpret_cast<uintptr_t>(x->p) & 15) == 0;
+    if (vec)
+        var_tiny_kernel<DT, true><<<grid, THREADS, 0, ctx->stream>>>(p->W, p->mw, (int)p->D, x->p, sd, sn, x->N, sigma2,
+                                                                    sigma2_scalar, mean_dev, var_dev);
+    else
+        var_tiny_kernel<DT, false><<<grid, THREADS, 0, ctx->stream>>>(p->W, p->mw, (int)p->D, x->p, sd, sn, x->N, sigma2,
+                                                                     sigma2_scalar, mean_dev, var_dev);
+    BLR_CHECK_LAUNCH(ctx, "var_tiny_kernel");
+    return 0;
 }
 
 template <int MI>
@@ -207,7 +282,9 @@ int predict_mean_var(blr_ctx* ctx, blr_post* p, const blr_x* x, const double* si
         return predict_mean_var_fast(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
     if (var_dev && p->D <= 64) {
         BLR_TRY(post_ensure_W(ctx, p));
-        if (p->D <= 8) return launch_var_small<1>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+        if (p->D <= 2) return launch_var_tiny<2>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+        if (p->D <= 4) return launch_var_tiny<4>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+        if (p->D <= 8) return launch_var_tiny<8>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
         if (p->D <= 16) return launch_var_small<2>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
         if (p->D <= 32) return launch_var_small<4>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
         return launch_var_small<8>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);

@@ -12,8 +12,8 @@
 //   B operand = 16 features of the 32 points, [point][k] in shared memory,
 // both filled by TMA bulk copies from a producer warp through a 3-stage mbarrier ring.  X is read from HBM exactly
 // once; W (2 MB at D = 512) streams from L2.
-// Triangular balance: warp w owns the 8-row blocks {w, w + 8, w + 16, ...}, so every warp loses sub-tiles at the
-// same rate as k advances; which sub-tile rows are live is a compile-time template parameter (run-time predication
+// Triangular balance: warp w owns the 8-row blocks {w, 15 - w, 16 + w, 31 - w, ...}, so every warp loses sub-tiles
+// at the same rate as k advances; which sub-tile rows are live is a compile-time template parameter (run-time predication
 // of mma.sync serialises the tensor pipe, see gram.cu).
 // D > 512 is handled in row passes of 512 rows (the point tile is re-streamed per pass).
 #include <math.h>
@@ -74,14 +74,16 @@ template <int MI, int M0>
 __device__ __forceinline__ void var_consume(double (&acc)[MI][4][2], const double* __restrict__ As,
                                             const double* __restrict__ Bs, int warp, int g, int kq) {
     using C = vk::Cfg<MI>;
-    const double* Ap = As + warp * 8 + g;
+    // row block of (warp, mi): 8 mi + warp for even mi, 8 mi + 7 - warp for odd mi (see var_tma_kernel)
+    const double* Ap0 = As + warp * 8 + g;
+    const double* Ap1 = As + (7 - warp) * 8 + g;
     const double* Bp = Bs + g * vk::LDB;
 #pragma unroll
     for (int kk = 0; kk < vk::KT / 4; ++kk) {
         const int kl = kk * 4 + kq;
         double a[MI], b[4];
 #pragma unroll
-        for (int mi = M0; mi < MI; ++mi) a[mi] = Ap[kl * C::LDA + mi * 64];
+        for (int mi = M0; mi < MI; ++mi) a[mi] = ((mi & 1) ? Ap1 : Ap0)[kl * C::LDA + mi * 64];
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) b[ni] = Bp[ni * 8 * vk::LDB + kl];
 #pragma unroll
@@ -206,9 +208,14 @@ __global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams
                 const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
                 mbar_wait(smem_u32(&sm.full[stg]), ph);
                 const typename C::Stage& S = sm.st[stg];
-                // row block (mi * 8 + warp) of this pass holds rows r_base + (mi*8 + warp)*8 .. +7; live iff last row >= k0
-                const int num = k0 - 7 - r_base - 8 * warp;
-                const int m0 = num <= 0 ? 0 : (num + 63) / 64;
+                // Warp w owns the 8-row blocks b(mi) = 8 mi + (mi odd ? 7 - w : w) of this pass (boustrophedon, so that
+                // every warp -- and every SM sub-partition -- loses sub-tiles at the same rate as k advances: with the
+                // plain 8 mi + w map warps 6, 7 carry 20 % more DMMAs than warps 0, 1).  Block b holds rows
+                // r_base + 8 b .. + 7 and is live iff its last row >= k0; b grows with mi, so the live set is mi >= m0.
+                int m0 = 0;
+#pragma unroll
+                for (int mi = 0; mi < MI; ++mi)
+                    m0 += (r_base + 8 * (8 * mi + ((mi & 1) ? 7 - warp : warp)) + 7 < k0) ? 1 : 0;
                 var_consume_dispatch<MI>(acc, S.a, S.b, warp, g, kq, m0);
                 if (ps == npass - 1) {  // the last row pass streams every feature k < D
                     const double mwk = S.mw[mk];

@@ -85,7 +85,7 @@ print(json.dumps(c.calibrate()))
     tests_fast)
       timeout 1500 python -m pytest tests -m gpu -q --timeout 600 --ignore tests/test_gpu_fullsize.py > "$OUT/tests.log" 2>&1; echo "tests exit $?"; tail -15 "$OUT/tests.log";;
     fullsize)
-      timeout 1500 python -m pytest tests/test_gpu_fullsize.py -m gpu -q --timeout 900 --durations=5 > "$OUT/fullsize.log" 2>&1; echo "fullsize exit $?"; tail -25 "$OUT/fullsize.log";;
+      timeout 1500 python -m pytest tests/test_gpu_fullsize.py -m gpu -q -s --timeout 900 --durations=5 > "$OUT/fullsize.log" 2>&1; echo "fullsize exit $?"; tail -25 "$OUT/fullsize.log";;
     cfg4_multi)
       NG=$(nvidia-smi -L | wc -l)
       if [ $NG -gt 1 ]; then
@@ -95,6 +95,8 @@ print(json.dumps(c.calibrate()))
         timeout 900 python tools/bench_cfg4.py > "$OUT/cfg4_g$NG.json" 2> "$OUT/cfg4_g$NG.err"
       fi
       echo "cfg4 exit $?"; cat "$OUT/cfg4_g$NG.json"; tail -3 "$OUT/cfg4_g$NG.err";;
+    small_d)
+      timeout 600 python tools/bench_small_d.py > "$OUT/small_d.jsonl" 2> "$OUT/small_d.err"; echo "small_d exit $?"; cat "$OUT/small_d.jsonl"; tail -3 "$OUT/small_d.err";;
     rff_multi)
       NG=$(nvidia-smi -L | wc -l)
       timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533 \
