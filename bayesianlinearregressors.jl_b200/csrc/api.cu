@@ -219,6 +219,7 @@ int blr_ctx_create(blr_ctx** out, int device) {
         if (atoi(k) == 16) ctx->gram_kt = 16;
         if (atoi(k) == 32) ctx->gram_kt = 32;
     }
+    if (const char* v = getenv("BLR_VAR_CFG")) ctx->var_cfg = atoi(v) == 0 ? 0 : 1;
     if (const char* w = getenv("BLR_DIAG_WEIGHT")) {
         const int v = atoi(w);
         if (v >= 8 && v <= 128) ctx->diag_weight = v;

@@ -67,6 +67,7 @@ struct blr_ctx {
     int sched_T = 0, sched_nseg = 0;
     int64_t gram_period_obs = 0;  // observations per L2 period of the Gram kernel (0 = single period; BLR_GRAM_PERIOD_OBS)
     int gram_stages = 0;   // ring depth override for gram_kt == 16 (BLR_GRAM_STAGES = 6)
+    int var_cfg = 1;       // marginals fast path: 1 = <4 x 64 rows, 64 points> (default), 0 = <8 x 64 rows, 32 points> (BLR_VAR_CFG=0)
     int gram_kt = 32;      // observations per pipeline stage of the Gram kernel: 16 or 32 (BLR_GRAM_KT)
     int diag_weight = 40;  // cost of a diagonal-tile stage relative to W_OFF = 64 (BLR_DIAG_WEIGHT overrides)
     // host-streaming path (blr_stats_accumulate_host): copy stream, two staging slots

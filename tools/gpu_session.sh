@@ -75,7 +75,7 @@ print(json.dumps(c.calibrate()))
       done 2>&1 | tee "$OUT/kt_sweep.log"
       BLR_GRAM_KT=32 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "statistics or posterior_and_logpdf" > "$OUT/tests_kt32.log" 2>&1; tail -3 "$OUT/tests_kt32.log";;
     period_sweep)
-      for po in 0 2048 4096 8192 1000000000; do
+      for po in ${PERIODS:-0 2048 4096 8192 1000000000}; do
         for cfg in "--n-obs 1048576 --dim 256" "--n-obs 2097152 --dim 1024"; do
           echo "PERIOD_OBS=$po cfg=$cfg"
           BLR_GRAM_PERIOD_OBS=$po timeout 600 python bench.py $cfg --steps 5 --warmup 3 --no-cpu --no-e2e --no-calibrate 2>> "$OUT/period.err" \
@@ -95,6 +95,18 @@ print(json.dumps(c.calibrate()))
         timeout 900 python tools/bench_cfg4.py > "$OUT/cfg4_g$NG.json" 2> "$OUT/cfg4_g$NG.err"
       fi
       echo "cfg4 exit $?"; cat "$OUT/cfg4_g$NG.json"; tail -3 "$OUT/cfg4_g$NG.err";;
+    var_ab)
+      for c in 0 1; do
+        echo "BLR_VAR_CFG=$c"
+        BLR_VAR_CFG=$c timeout 600 python tools/bench_cfg4.py --max-log2-per-gpu 23 --n-fit 262144 2>> "$OUT/var_ab.err" | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('mean_var', d['mean_and_var'], 'rand', d['rand']['ms'])"
+        BLR_VAR_CFG=$c timeout 900 python -m pytest tests -m gpu -q -k "mean_var or golden or cfg4 or reference_suite" --timeout 600 2>&1 | tail -2
+      done 2>&1 | tee "$OUT/var_ab.log";;
+    var_dbg)
+      for c in "0 0" "0 1" "1 0" "1 1" "0 0" "0 1"; do
+        set -- $c
+        echo "BLR_VAR_CFG=$1 BLR_VAR_DBG=$2"
+        BLR_VAR_CFG=$1 BLR_VAR_DBG=$2 timeout 600 python tools/bench_cfg4.py --max-log2-per-gpu 23 --n-fit 262144 2>> "$OUT/var_dbg.err" | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('mean_var ms', d['mean_and_var']['ms'], 'TF', d['mean_and_var']['tflops_per_gpu'])"
+      done 2>&1 | tee "$OUT/var_dbg.log";;
     small_d)
       timeout 600 python tools/bench_small_d.py > "$OUT/small_d.jsonl" 2> "$OUT/small_d.err"; echo "small_d exit $?"; cat "$OUT/small_d.jsonl"; tail -3 "$OUT/small_d.err";;
     rff_multi)
