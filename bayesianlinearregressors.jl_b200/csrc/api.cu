@@ -203,6 +203,12 @@ int blr_ctx_create(blr_ctx** out, int device) {
     if (e == cudaSuccess) e = cudaMalloc(&ctx->small, (size_t)SMALL_TOTAL * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_info, sizeof(int));
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_res, (size_t)(SMALL_VEC + 2) * sizeof(double));
+    // copy stream + hand-over events: host-streaming accumulation and the overlapped precision download
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_flags, 512 * sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(ctx->d_flags, 0, 512 * sizeof(int));
     if (e != cudaSuccess || ctx->sm_count * 16 > SMALL_SC) {
@@ -219,6 +225,7 @@ int blr_ctx_create(blr_ctx** out, int device) {
         if (atoi(k) == 16) ctx->gram_kt = 16;
         if (atoi(k) == 32) ctx->gram_kt = 32;
     }
+    if (const char* v = getenv("BLR_GRAM_CS")) ctx->gram_cs = atoi(v) != 0 ? 1 : 0;
     if (const char* v = getenv("BLR_VAR_CFG")) ctx->var_cfg = atoi(v) == 0 ? 0 : 1;
     if (const char* w = getenv("BLR_DIAG_WEIGHT")) {
         const int v = atoi(w);
@@ -643,13 +650,6 @@ int blr_stats_accumulate_host(blr_ctx* ctx, blr_stats* s, const double* mw_host,
     const int64_t ldx = (layout == BLR_COLVECS) ? D + (D & 1) : chunk;
     const size_t x_elems = (size_t)((layout == BLR_COLVECS) ? ldx * chunk : chunk * D);
     const size_t slot_bytes = (x_elems + 2 * (size_t)chunk) * sizeof(double);
-    if (!ctx->copy_stream) {
-        BLR_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            BLR_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
-            BLR_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming));
-        }
-    }
     if (ctx->stage_bytes < slot_bytes) {
         BLR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
         BLR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->copy_stream));

@@ -19,6 +19,8 @@
 // a tile in a FIXED order, so results are bit-reproducible run to run.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -223,7 +225,66 @@ __device__ __forceinline__ void run_segment(double (&acc)[8][4][2], double& racc
     }
 }
 
-template <int KT, int STAGES, bool ROW = false>
+// ---------------------------------------------------------------------------------------------------------------------
+// "Column-strip" consumer tiling (ColVecs ring only): the 8 consumer warps sit 1 (m) x 8 (n), warp tile 128 x 16.
+// Each B fragment is then scaled by exactly ONE warp -- 2 DMUL per 32 DMMA instead of 4 (the DMULs share the fp64 pipe
+// with the DMMAs: the 2 x 4 mix tops out at 95.7 % of the pure-DMMA rate, this one at 97.9 %, `blr_calibrate_gram_inner`
+// with BLR_PROBE_VARIANT) -- and fragments are fetched with 16-byte loads: lane g of an A fragment pair holds rows
+// 16 p + 2 g and 16 p + 2 g + 1 (one LDS.128), lane g of the B pair holds columns 16 wn + 2 g, + 1.  The accumulator of
+// (pair p, e; b; c) is element (row 16 p + 2 g + e, col 16 wn + 4 kq + 2 c + b): a thread owns 2 x 4 blocks, flushed as
+// two 16-byte stores per row.  Diagonal tiles: the 16-row band p is needed by column strip wn iff p >= wn (compile-time
+// P0 = wn; 36 live 8 x 8 sub-tiles per SM sub-partition with the warp -> strip map {0,1,2,3,7,6,5,4}).
+template <int P0, int KT>
+__device__ __forceinline__ void consume_stage_cs(double (&acc)[16][2][2], const double* __restrict__ Asrc,
+                                                 const double* __restrict__ Bsrc, const double* __restrict__ Ssrc, int wn,
+                                                 int g, int kq) {
+    using namespace gk;
+    const double* Ap = Asrc + 2 * g;
+    const double* Bp = Bsrc + wn * 16 + 2 * g;
+#pragma unroll
+    for (int kk = 0; kk < KT / 4; ++kk) {
+        const int kl = kk * 4 + kq;
+        const double sk = Ssrc[kl];
+        double a[16], b[2];
+#pragma unroll
+        for (int pr = P0; pr < 8; ++pr) {
+            const double2 v = *reinterpret_cast<const double2*>(Ap + kl * LDT + pr * 16);
+            a[2 * pr] = v.x;
+            a[2 * pr + 1] = v.y;
+        }
+        const double2 bv = *reinterpret_cast<const double2*>(Bp + kl * LDT);
+        b[0] = bv.x * sk;
+        b[1] = bv.y * sk;
+#pragma unroll
+        for (int mi = 2 * P0; mi < 16; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
+    }
+}
+
+template <int P0, int KT, int STAGES>
+__device__ __forceinline__ void run_segment_cs(double (&acc)[16][2][2], double& racc, gk::Smem<KT, STAGES, false>& sm, int& it,
+                                               int nst, bool diag, int wn, int g, int kq, int rm, int rhalf, int lane) {
+    using namespace gk;
+    for (int i = 0; i < nst; ++i, ++it) {
+        const int stg = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(smem_u32(&sm.full[stg]), ph);
+        const Stage<KT, false>& S = sm.st[stg];
+        consume_stage_cs<P0, KT>(acc, S.a, diag ? S.a : S.b, S.s, wn, g, kq);
+        if (diag) {
+#pragma unroll
+            for (int k = 0; k < KT / 2; ++k) {  // r block of this row panel: r[m] += Σ_k X[m,k] t_k
+                const int kl = rhalf * (KT / 2) + k;
+                racc = fma(S.a[kl * LDT + rm], S.t[kl], racc);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sm.empty[stg]));
+    }
+}
+
+template <int KT, int STAGES, bool ROW = false, bool CS = false>
 __global__ void __launch_bounds__(ROW ? gk::THREADS_ROW : gk::THREADS, 1) gram_tma_kernel(const GramParams p) {
     using namespace gk;
     using Stage = gk::Stage<KT, ROW>;
@@ -253,6 +314,7 @@ __global__ void __launch_bounds__(ROW ? gk::THREADS_ROW : gk::THREADS, 1) gram_t
     __syncthreads();
 
     if (warp >= CONSUMER_WARPS) {
+        if constexpr (CS) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");  // hand registers to the consumer warpgroups
         // ------------------------------------------------------------ producer warps (TMA): 0 -> panel I + s, 1 -> panel J + t
         // (feature-major: warps 0, 1 -> halves of panel I, warps 2, 3 -> halves of panel J)
         const int pwr = warp - CONSUMER_WARPS;
@@ -338,6 +400,103 @@ __global__ void __launch_bounds__(ROW ? gk::THREADS_ROW : gk::THREADS, 1) gram_t
     // ---------------------------------------------------------------- consumer warps (DMMA)
     const int g = lane >> 2, kq = lane & 3;
     const int rm = tid & (TM - 1), rhalf = tid >> 7;
+    if constexpr (CS) {
+        // Hybrid tiling: off-diagonal tiles (86 % of the work at D = 1024, 97 % at D = 4096) run the column-strip consumer
+        // (consume_stage_cs: half the DMULs); diagonal tiles keep the 2 x 4 tiling below, whose compile-time sub-tile
+        // skipping leaves every SM sub-partition a second warp to overlap with (measured: a column-strip diagonal tile,
+        // where the heavy strips run nearly alone on their sub-partition, costs more than a full tile).  Consumer
+        // warpgroups take the producers' registers: 128 x 40 + 256 x 232 = 384 x 168.
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        const int wn_cs = warp < 4 ? warp : 11 - warp;
+        const int dmap = (0x7132'6054 >> (4 * warp)) & 0xf;  // diagonal tiles: see the 2 x 4 path below
+        const int wm_dg = dmap >> 2, wn_dg = dmap & 3;
+        const int thr_dg = wn_dg * 4 - wm_dg * 8;
+        int it = 0;
+        const bool single = (seg_end - seg_begin) == 1;
+        double acc[16][2][2];  // column-strip view; the diagonal path uses the same 64 registers as [8][4][2]
+        auto& acc_dg = reinterpret_cast<double (&)[8][4][2]>(acc);
+#pragma unroll
+        for (int mi = 0; mi < 16; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        double racc = 0.0;
+        auto flush = [&](int sg, bool diag, bool add) {
+            double* Pt = p.P + (int64_t)sg * (TM * TM);
+            if (!diag) {
+#pragma unroll
+                for (int mi = 0; mi < 16; ++mi) {
+                    const int row = (mi >> 1) * 16 + 2 * g + (mi & 1);
+                    double2* dst = reinterpret_cast<double2*>(Pt + row * TM + wn_cs * 16 + 4 * kq);
+                    double2 v0 = make_double2(acc[mi][0][0], acc[mi][1][0]);  // cols 4 kq + 0, + 1
+                    double2 v1 = make_double2(acc[mi][0][1], acc[mi][1][1]);  // cols 4 kq + 2, + 3
+                    if (add) {
+                        const double2 o0 = dst[0], o1 = dst[1];
+                        v0.x += o0.x;
+                        v0.y += o0.y;
+                        v1.x += o1.x;
+                        v1.y += o1.y;
+                    }
+                    dst[0] = v0;
+                    dst[1] = v1;
+                }
+                return;
+            }
+#pragma unroll
+            for (int mi = 0; mi < 8; ++mi) {
+                const int row = wm_dg * 64 + mi * 8 + g;
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    const int col = wn_dg * 32 + ni * 8 + kq * 2;
+                    if ((mi - ni) >= thr_dg) {
+                        double2* dst = reinterpret_cast<double2*>(Pt + row * TM + col);
+                        double2 v = make_double2(acc_dg[mi][ni][0], acc_dg[mi][ni][1]);
+                        if (add) {
+                            const double2 o = *dst;
+                            v.x += o.x;
+                            v.y += o.y;
+                        }
+                        *dst = v;
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // rred may still be read by the previous flush
+            if (rhalf == 1) sm.rred[rm] = racc;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (rhalf == 0) {
+                double* dst = p.Pr + (int64_t)sg * TM + rm;
+                *dst = (add ? *dst : 0.0) + (racc + sm.rred[rm]);
+            }
+        };
+        for (int per = 0; per < p.NP; ++per) {
+            const int base = per * p.PS;
+            for (int sg = seg_begin; sg < seg_end; ++sg) {
+                int ti, tj;
+                tile_from_index(p.seg_tile[sg], ti, tj);
+                const bool diag = (ti == tj);
+                const int nst = max(0, min(base + sched_stage(p.seg_g1[sg], per, p.fix_bits), p.n_stages) - (base + sched_stage(p.seg_g0[sg], per, p.fix_bits)));
+                // warp-uniform dispatch to a fully unrolled, unpredicated instruction stream
+                if (!diag) run_segment_cs<0, KT, STAGES>(acc, racc, sm, it, nst, false, wn_cs, g, kq, rm, rhalf, lane);
+                else if (thr_dg <= -3) run_segment<1, KT, STAGES, false>(acc_dg, racc, sm, it, nst, wm_dg, wn_dg, g, kq, rm, rhalf, lane);
+                else if (thr_dg == 0) run_segment<2, KT, STAGES, false>(acc_dg, racc, sm, it, nst, wm_dg, wn_dg, g, kq, rm, rhalf, lane);
+                else if (thr_dg == 4) run_segment<3, KT, STAGES, false>(acc_dg, racc, sm, it, nst, wm_dg, wn_dg, g, kq, rm, rhalf, lane);
+                else run_segment<4, KT, STAGES, false>(acc_dg, racc, sm, it, nst, wm_dg, wn_dg, g, kq, rm, rhalf, lane);
+                if (!single) {
+                    flush(sg, diag, per > 0);
+#pragma unroll
+                    for (int mi = 0; mi < 16; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+                    racc = 0.0;
+                }
+            }
+        }
+        if (single) {
+            int ti, tj;
+            tile_from_index(p.seg_tile[seg_begin], ti, tj);
+            flush(seg_begin, ti == tj, false);
+        }
+        return;
+    }
     // off-diagonal tiles: warp -> (wm, wn) row-major.  Diagonal tiles: remapped so that the surviving sub-tile counts
     // {26, 10, 0, 0, 32, 32, 26, 10} pair up evenly over the four SM sub-partitions (warp % 4): 32, 32, 36, 36.
     const int wm_off = warp >> 2, wn_off = warp & 3;
@@ -447,19 +606,111 @@ __global__ void __launch_bounds__(256, 1) gram_inner_probe_kernel(double* __rest
     out[(int64_t)blockIdx.x * 256 + threadIdx.x] = sum;
 }
 
+// Alternative consumer mixes for the same probe (BLR_PROBE_VARIANT): what would a different warp tiling buy?
+//   1: warps 1 (m) x 8 (n), warp tile 128 x 16: 16 A fragments fetched as 8 LDS.128 (row pairs 16 p + 2 g, + 1),
+//      2 B fragments as one LDS.128, 2 DMUL per 32 DMMA (each B fragment is scaled by exactly one warp)
+//   2: the current 2 x 4 tiling without the DMULs (not a valid kernel: isolates what the scaling costs)
+//   3: variant 1 without the DMULs
+template <int KT, int VARIANT>
+__global__ void __launch_bounds__(256, 1) gram_inner_probe_alt_kernel(double* __restrict__ out, int iters) {
+    using namespace gk;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Stage<KT>& S = *reinterpret_cast<Stage<KT>*>(smem_raw);
+    for (int i = threadIdx.x; i < (int)(sizeof(Stage<KT>) / sizeof(double)); i += 256)
+        reinterpret_cast<double*>(&S)[i] = 1.0 + 1e-9 * i;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, kq = lane & 3;
+    double sum = 0.0;
+    if (VARIANT == 2) {
+        double acc[8][4][2];
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        const int wm = warp >> 2, wn = warp & 3;
+        const double* Ap = S.a + wm * 64 + g;
+        const double* Bp = S.b + wn * 32 + g;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int kk = 0; kk < KT / 4; ++kk) {
+                const int kl = kk * 4 + kq;
+                double a[8], b[4];
+#pragma unroll
+                for (int mi = 0; mi < 8; ++mi) a[mi] = Ap[kl * LDT + mi * 8];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) b[ni] = Bp[kl * LDT + ni * 8];
+#pragma unroll
+                for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
+            }
+        }
+#pragma unroll
+        for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) sum += acc[mi][ni][0] + acc[mi][ni][1];
+    } else {
+        double acc[16][2][2];
+#pragma unroll
+        for (int mi = 0; mi < 16; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        const double* Ap = S.a + 2 * g;
+        const double* Bp = S.b + warp * 16 + 2 * g;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int kk = 0; kk < KT / 4; ++kk) {
+                const int kl = kk * 4 + kq;
+                const double sk = S.s[kl];
+                double a[16], b[2];
+#pragma unroll
+                for (int pr = 0; pr < 8; ++pr) {
+                    const double2 v = *reinterpret_cast<const double2*>(Ap + kl * LDT + pr * 16);
+                    a[2 * pr] = v.x;
+                    a[2 * pr + 1] = v.y;
+                }
+                const double2 bv = *reinterpret_cast<const double2*>(Bp + kl * LDT);
+                if (VARIANT == 1) {
+                    b[0] = bv.x * sk;
+                    b[1] = bv.y * sk;
+                } else {
+                    b[0] = bv.x;
+                    b[1] = bv.y;
+                }
+#pragma unroll
+                for (int mi = 0; mi < 16; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 2; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
+            }
+        }
+#pragma unroll
+        for (int mi = 0; mi < 16; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) sum += acc[mi][ni][0] + acc[mi][ni][1];
+    }
+    out[(int64_t)blockIdx.x * 256 + threadIdx.x] = sum;
+}
+
 int calib_gram_inner(blr_ctx* ctx, double* tflops) {
     constexpr int KT = 32;
     const int blocks = ctx->sm_count, iters = 2000;
+    const int variant = getenv("BLR_PROBE_VARIANT") ? atoi(getenv("BLR_PROBE_VARIANT")) : 0;
     BLR_TRY(ensure_ws(ctx, (size_t)blocks * 256 * sizeof(double)));
-    BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_inner_probe_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(gk::Stage<KT>)));
+    const int smem = (int)sizeof(gk::Stage<KT>);
+    BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_inner_probe_kernel<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_inner_probe_alt_kernel<KT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_inner_probe_alt_kernel<KT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_inner_probe_alt_kernel<KT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     cudaEvent_t e0, e1;
     BLR_CUDA_OK(ctx, cudaEventCreate(&e0));
     BLR_CUDA_OK(ctx, cudaEventCreate(&e1));
     float best = 1e30f;
     for (int r = 0; r < 4; ++r) {
         BLR_CUDA_OK(ctx, cudaEventRecord(e0, ctx->stream));
-        gram_inner_probe_kernel<KT><<<blocks, 256, sizeof(gk::Stage<KT>), ctx->stream>>>(ctx->ws, iters);
+        if (variant == 1) gram_inner_probe_alt_kernel<KT, 1><<<blocks, 256, smem, ctx->stream>>>(ctx->ws, iters);
+        else if (variant == 2) gram_inner_probe_alt_kernel<KT, 2><<<blocks, 256, smem, ctx->stream>>>(ctx->ws, iters);
+        else if (variant == 3) gram_inner_probe_alt_kernel<KT, 3><<<blocks, 256, smem, ctx->stream>>>(ctx->ws, iters);
+        else gram_inner_probe_kernel<KT><<<blocks, 256, smem, ctx->stream>>>(ctx->ws, iters);
         ctx->launches++;
         BLR_CUDA_OK(ctx, cudaEventRecord(e1, ctx->stream));
         BLR_CUDA_OK(ctx, cudaEventSynchronize(e1));
@@ -469,6 +720,7 @@ int calib_gram_inner(blr_ctx* ctx, double* tflops) {
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    BLR_CUDA_OK(ctx, cudaGetLastError());
     // hardware flops of the DMMAs only: per block per iteration 128 x 128 x KT FMAs
     *tflops = (double)blocks * iters * 128.0 * 128.0 * KT * 2.0 / (best * 1e-3) / 1e12;
     return 0;
@@ -688,10 +940,12 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
         if (n_stages <= PS + PS / 2) PS = n_stages;  // short inputs: one period (plain stream-K)
         const int64_t NP = (n_stages + PS - 1) / PS;
         const int64_t flush_cost = NP > 1 ? gk::W_OFF / 2 : 0;  // ~half a stage per tile switch
+        const bool hybrid = KT == 32 && ctx->gram_cs && !row_native;
+        const int diag_weight = ctx->diag_weight > 0 ? ctx->diag_weight : (hybrid ? 42 : 40);
         if (ctx->sched_key[0] != nt || ctx->sched_key[1] != PS || ctx->sched_key[2] != G ||
-            ctx->sched_key[3] != ctx->diag_weight * 1000 + flush_cost) {
+            ctx->sched_key[3] != diag_weight * 1000 + flush_cost) {
             Schedule sc;
-            build_schedule(sc, nt, PS, G, ctx->diag_weight, flush_cost);
+            build_schedule(sc, nt, PS, G, diag_weight, flush_cost);
             const size_t bytes = sc.table.size() * sizeof(int);
             if (ctx->sched_bytes < bytes) {
                 BLR_CUDA_OK(ctx, cudaStreamSynchronize(sm));
@@ -706,7 +960,7 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
             ctx->sched_key[0] = nt;
             ctx->sched_key[1] = PS;
             ctx->sched_key[2] = G;
-            ctx->sched_key[3] = ctx->diag_weight * 1000 + flush_cost;
+            ctx->sched_key[3] = diag_weight * 1000 + flush_cost;
             ctx->sched_T = sc.T;
             ctx->sched_nseg = sc.nseg;
         }
@@ -740,6 +994,12 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
             BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_tma_kernel<32, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   (int)sizeof(SM)));
             BLR_CUDA_OK(ctx, cudaLaunchCooperativeKernel((void*)gram_tma_kernel<32, 3, true>, dim3(G), dim3(gk::THREADS_ROW),
+                                                         args, sizeof(SM), sm));
+        } else if (hybrid) {
+            using SM = gk::Smem<32, 3>;
+            BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_tma_kernel<32, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)sizeof(SM)));
+            BLR_CUDA_OK(ctx, cudaLaunchCooperativeKernel((void*)gram_tma_kernel<32, 3, false, true>, dim3(G), dim3(gk::THREADS),
                                                          args, sizeof(SM), sm));
         } else if (KT == 32) {
             using SM = gk::Smem<32, 3>;

@@ -128,6 +128,41 @@ def test_periodic_schedule_many_periods(D, N, period, monkeypatch):
     assert lp2 == lp and np.array_equal(post.mw, post2.mw)
 
 
+@pytest.mark.parametrize("D,N,period", [(256, 20011, 0), (130, 5000, 0), (320, 7777, 0), (1024, 6000, 0), (384, 9000, 256)])
+@pytest.mark.parametrize("cs", [0, 1])
+def test_gram_consumer_tilings(D, N, period, cs, monkeypatch):
+    """Both consumer tilings of the Gram fast path (2 x 4 warps with 64 x 32 warp tiles; column strips = 1 x 8 warps with
+    128 x 16 warp tiles, half the B-fragment scalings) against the oracle, including a D tail inside a tile, a narrow last
+    tile row and the periodic schedule's read-modify-write flushes; results are bit-reproducible for either."""
+    X, mw, _, σ2, y = problem(D, N, seed=3 * D + cs)
+    monkeypatch.setenv("BLR_GRAM_CS", str(cs))
+    if period:
+        monkeypatch.setenv("BLR_GRAM_PERIOD_OBS", str(period))
+    ctx = blr.Context(0)  # reads the environment at creation
+    monkeypatch.delenv("BLR_GRAM_CS")
+    if period:
+        monkeypatch.delenv("BLR_GRAM_PERIOD_OBS")
+    Xd = blr.DeviceMatrix.upload(ctx, X, 0)
+    yd = blr.DeviceVector.upload(ctx, y)
+    sd = blr.DeviceVector.upload(ctx, σ2)
+    from blr_b200 import _lib as L
+    import ctypes as C
+
+    noise = L.Noise(L.NOISE_VECTOR, 0.0, sd.handle, None, 0)
+    outs = []
+    for rep in range(2):
+        st = blr.Stats(ctx, D)
+        ctx.check(ctx.lib.blr_stats_accumulate(ctx.handle, st.handle, np.ascontiguousarray(mw).ctypes.data_as(C.c_void_p), Xd.handle,
+                                               yd.handle, C.byref(noise)))
+        outs.append(st.unpack())
+    G, r, q, ℓ, n = outs[0]
+    Go, ro, qo, ℓo = ref.gram_stats(X, y, σ2, mw, chunk=4096)
+    assert n == N and np.array_equal(G, G.T)
+    assert relerr(G, Go) < 1e-12 and relerr(r, ro) < 1e-11
+    assert abs(q - qo) <= 1e-11 * abs(qo) and abs(ℓ - ℓo) <= 1e-11 * max(abs(ℓo), 1.0)
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
 # ------------------------------------------------------------------------------------------------ posterior + logpdf
 INFER_CASES = [
     # D, N, dense prior, zero mean, scalar noise
@@ -188,6 +223,25 @@ def test_device_resident_inputs(D, N):
     if N <= (1 << 16):  # a single host chunk sees the same kernel launch as the resident path
         assert lp_h == lp_d and np.array_equal(post_h.mw, post_d.mw)
     assert relerr(post_d.mw, ref.posterior(fxo, y).mw) < RTOL
+
+
+def test_resident_then_streamed_on_one_context():
+    """A device-resident inference at D >= 1024 (precision download overlapped on the copy stream) followed by a host-
+    streamed one on the same context: both share the copy stream and its hand-over events."""
+    D, N = 1024, 3000
+    X, mw, _, σ2, y = problem(D, N, seed=21, dense=False)
+    ctx = blr.Context(0)
+    f = blr.BayesianLinearRegressor(mw, blr.Diagonal(np.ones(D)))
+    fx = f(blr.ColVecs(blr.DeviceMatrix.upload(ctx, X, 0)), blr.DeviceVector.upload(ctx, σ2))
+    fx.ctx = ctx
+    post_d, lp_d = blr.posterior_and_logpdf(fx, blr.DeviceVector.upload(ctx, y))
+    post_s, lp_s = blr.posterior_and_logpdf_streamed(f, X, y, σ2, chunk=1024, ctx=ctx)
+    post_d2, lp_d2 = blr.posterior_and_logpdf(fx, blr.DeviceVector.upload(ctx, y))
+    lpo, mo, To = ref.infer_streaming(mw, ref.Diagonal(np.ones(D)), X, y, σ2)
+    for post, lp in ((post_d, lp_d), (post_s, lp_s), (post_d2, lp_d2)):
+        assert abs(lp - lpo) <= RTOL * abs(lpo)
+        assert relerr(post.mw, mo) < RTOL and relerr(post.Λw.dense(), To.T @ To) < RTOL
+    assert lp_d2 == lp_d and np.array_equal(post_d.Λw.dense(), post_d2.Λw.dense())
 
 
 def test_large_rowvecs_blockwise_staging():

@@ -107,6 +107,43 @@ print(json.dumps(c.calibrate()))
         echo "BLR_VAR_CFG=$1 BLR_VAR_DBG=$2"
         BLR_VAR_CFG=$1 BLR_VAR_DBG=$2 timeout 600 python tools/bench_cfg4.py --max-log2-per-gpu 23 --n-fit 262144 2>> "$OUT/var_dbg.err" | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('mean_var ms', d['mean_and_var']['ms'], 'TF', d['mean_and_var']['tflops_per_gpu'])"
       done 2>&1 | tee "$OUT/var_dbg.log";;
+    ncu_solve)
+      for d in 256 1024; do
+        timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 300 --csv --log-file "$OUT/solve_launches_D$d.csv" \
+          python bench.py --n-obs 262144 --dim $d --steps 1 --warmup 1 --no-cpu --no-calibrate --no-e2e > "$OUT/ncu_solve_D$d.log" 2>&1; echo "ncu_solve D=$d exit $?"
+      done;;
+    probe_mix)
+      for v in 0 1 2 3 0 1; do
+        BLR_PROBE_VARIANT=$v timeout 300 python -c "
+import blr_b200 as b, ctypes as C
+c = b.Context(0)
+v = C.c_double(); c.check(c.lib.blr_calibrate_gram_inner(c.handle, C.byref(v)))
+p = C.c_double(); c.check(c.lib.blr_calibrate_dmma(c.handle, C.byref(p)))
+print('variant $v mix TF', round(v.value, 3), 'pure DMMA TF', round(p.value, 3), 'frac', round(v.value / p.value, 4))
+"
+      done 2>&1 | tee "$OUT/probe_mix.log";;
+    cs_ab)
+      timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "consumer_tilings" --timeout 600 2>&1 | tail -5
+      for c in 0 1 0 1; do
+        for cfg in "--n-obs 1048576 --dim 256" "--n-obs 2097152 --dim 1024" "--n-obs 262144 --dim 4096"; do
+          echo "BLR_GRAM_CS=$c cfg=$cfg"
+          BLR_GRAM_CS=$c timeout 600 python bench.py $cfg --steps 5 --warmup 3 --no-cpu --no-e2e --no-calibrate 2>> "$OUT/cs.err" \
+            | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['achieved'], d['clocks'].get('power_w_max'))"
+        done
+      done 2>&1 | tee "$OUT/cs_ab.log";;
+    cs_weight)
+      for w in ${WEIGHTS:-40 41 42 43}; do
+        for cfg in "--n-obs 1048576 --dim 256" "--n-obs 2097152 --dim 1024" "--n-obs 1048576 --dim 2048"; do
+          echo "BLR_GRAM_CS=1 BLR_DIAG_WEIGHT=$w cfg=$cfg"
+          BLR_GRAM_CS=1 BLR_DIAG_WEIGHT=$w timeout 600 python bench.py $cfg --steps 5 --warmup 3 --no-cpu --no-e2e --no-calibrate 2>> "$OUT/csw.err" \
+            | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['achieved'])"
+        done
+      done 2>&1 | tee "$OUT/cs_weight.log"
+      for cfg in "--n-obs 1048576 --dim 2048"; do
+        echo "BLR_GRAM_CS=0 cfg=$cfg"
+        BLR_GRAM_CS=0 timeout 600 python bench.py $cfg --steps 5 --warmup 3 --no-cpu --no-e2e --no-calibrate 2>> "$OUT/csw.err" \
+          | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['achieved'])"
+      done 2>&1 | tee -a "$OUT/cs_weight.log";;
     small_d)
       timeout 600 python tools/bench_small_d.py > "$OUT/small_d.jsonl" 2> "$OUT/small_d.err"; echo "small_d exit $?"; cat "$OUT/small_d.jsonl"; tail -3 "$OUT/small_d.err";;
     rff_multi)
