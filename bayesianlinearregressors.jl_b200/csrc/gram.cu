@@ -284,7 +284,82 @@ __device__ __forceinline__ void run_segment_cs(double (&acc)[16][2][2], double& 
     }
 }
 
-template <int KT, int STAGES, bool ROW = false, bool CS = false>
+// Diagonal tiles of the hybrid kernel: warp w owns the 8-row blocks w and 15 - w of the 16 x 16 grid of 8 x 8 sub-tiles.
+// Block row R has R + 1 sub-tiles on or below the diagonal, so every warp carries exactly 17 of the 136 live sub-tiles and
+// the two warps of an SM sub-partition always have equal work to overlap.  Measured on the alternatives: maps that leave a
+// sub-partition one heavy and one light (or idle) warp run the heavy warp's DMMA stream at 1 per 21-32 cycles instead of 16
+// -- a diagonal tile then costs as much as a full one.  Only the two A fragments are scaled by s_k (2 DMUL per 17 DMMA).
+// acc[c] (c <= R0) is sub-tile (R0, c); acc[R0 + 1 + c] (c <= R1) is sub-tile (R1, c).
+template <int W, int KT, int DU>
+__device__ __forceinline__ void consume_stage_rp(double (&acc)[17][2], const gk::Stage<KT, false>& S, int g, int kq) {
+    using namespace gk;
+    constexpr int R0 = W, R1 = 15 - W;          // block rows of this warp (R0 < R1)
+    constexpr int N0 = R0 + 1, N1 = R1 + 1;     // live sub-tiles in each (columns 0 .. R)
+    const double* Ap = S.a + g;
+    // DU = k4 steps per loop trip.  Eight warps run eight different instruction streams here; fully unrolled (DU = 8:
+    // 56 KB for the eight variants) they miss the instruction cache once most SMs of the chip run diagonal tiles at the
+    // same time (D <= 512: 37 % of the stall samples were `no_instructions`, a diagonal tile cost as much as a full one),
+    // while at larger D, where few CTAs are on diagonal tiles, the full unroll is the faster one (35.2 vs 34.8 TF at D = 1024).
+#pragma unroll(DU)
+    for (int kk = 0; kk < KT / 4; ++kk) {
+        const int kl = kk * 4 + kq;
+        const double sk = S.s[kl];
+        const double a0 = Ap[kl * LDT + R0 * 8] * sk, a1 = Ap[kl * LDT + R1 * 8] * sk;
+        double b[N1];
+#pragma unroll
+        for (int c = 0; c < N1; ++c) b[c] = Ap[kl * LDT + c * 8];
+#pragma unroll
+        for (int c = 0; c < N1; ++c) {
+            if (c < N0) dmma884(acc[c], a0, b[c]);
+            dmma884(acc[N0 + c], a1, b[c]);
+        }
+    }
+}
+
+template <int W, int KT, int STAGES, int DU>
+__device__ __forceinline__ void run_segment_rp(double (&acc)[17][2], double& racc, gk::Smem<KT, STAGES, false>& sm, int& it,
+                                               int nst, int g, int kq, int rm, int rhalf, int lane) {
+    using namespace gk;
+    for (int i = 0; i < nst; ++i, ++it) {
+        const int stg = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(smem_u32(&sm.full[stg]), ph);
+        const Stage<KT, false>& S = sm.st[stg];
+        consume_stage_rp<W, KT, DU>(acc, S, g, kq);
+#pragma unroll
+        for (int k = 0; k < KT / 2; ++k) {  // r block of this row panel: r[m] += Σ_k X[m,k] t_k
+            const int kl = rhalf * (KT / 2) + k;
+            racc = fma(S.a[kl * LDT + rm], S.t[kl], racc);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sm.empty[stg]));
+    }
+}
+
+template <int W>
+__device__ __forceinline__ void flush_rp(const double (&acc)[17][2], double* __restrict__ Pt, int g, int kq, bool add) {
+    using namespace gk;
+    constexpr int R0 = W, R1 = 15 - W, N0 = R0 + 1, N1 = R1 + 1;
+#pragma unroll
+    for (int c = 0; c < N1; ++c) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (h == 0 && c >= N0) continue;
+            const int R = h == 0 ? R0 : R1;
+            const double(&v)[2] = acc[h == 0 ? c : N0 + c];
+            double2* dst = reinterpret_cast<double2*>(Pt + (R * 8 + g) * TM + c * 8 + kq * 2);
+            double2 o = make_double2(v[0], v[1]);
+            if (add) {
+                const double2 old = *dst;
+                o.x += old.x;
+                o.y += old.y;
+            }
+            *dst = o;
+        }
+    }
+}
+
+template <int KT, int STAGES, bool ROW = false, bool CS = false, int DU = 8>
 __global__ void __launch_bounds__(ROW ? gk::THREADS_ROW : gk::THREADS, 1) gram_tma_kernel(const GramParams p) {
     using namespace gk;
     using Stage = gk::Stage<KT, ROW>;
@@ -353,8 +428,11 @@ __global__ void __launch_bounds__(ROW ? gk::THREADS_ROW : gk::THREADS, 1) gram_t
                     Stage& S = sm.st[stg];
                     const uint32_t bar = smem_u32(&sm.full[stg]);
                     if (narrow) {  // rare (only tiles in the last block row when D % 128 != 0): clear my part first
-                        double* z = (pw == 0 ? S.a : S.b) + half * (Stage::PANEL / 2);
-                        for (int i = lane; i < Stage::PANEL / 2; i += 32) z[i] = 0.0;
+                        // (the part this warp is about to fill: a quarter of panel I on a ColVecs diagonal tile, see below)
+                        const bool quarter = !ROW && diag;
+                        double* z = quarter ? S.a + pwr * (Stage::PANEL / 4) : (pw == 0 ? S.a : S.b) + half * (Stage::PANEL / 2);
+                        const int nz = quarter ? Stage::PANEL / 4 : Stage::PANEL / 2;
+                        for (int i = lane; i < nz; i += 32) z[i] = 0.0;
                         fence_proxy_async();
                         __syncwarp();
                     }
@@ -378,16 +456,21 @@ __global__ void __launch_bounds__(ROW ? gk::THREADS_ROW : gk::THREADS, 1) gram_t
                         }
                         if (lane == 0 && half == 0) bulk_g2s(smem_u32(pw == 0 ? S.s : S.t), (pw == 0 ? p.s : p.t) + k0, KT * 8u, bar);
                     } else {
-                        // one copy per observation (its rows-long slice); this warp owns observations
-                        // [KT/2 half, KT/2 half + KT/2) of the stage
-                        const int my_k = have_panel ? max(0, min(KT / 2, kc - half * (KT / 2))) : 0;
+                        // one copy per observation (its rows-long slice).  Off-diagonal tile: this warp owns observations
+                        // [KT/2 half, KT/2 half + KT/2) of its panel.  Diagonal tile (panel I only): all four warps share
+                        // it, KT/4 observations each -- the per-lane copies of a warp issue one after another (~100 cycles
+                        // apiece), and with two warps a diagonal stage took as long to ISSUE as to consume.
+                        const int kbeg = diag ? pwr * (KT / 4) : half * (KT / 2);
+                        const int kcnt = diag ? KT / 4 : KT / 2;
+                        const int my_k = (diag || have_panel) ? max(0, min(kcnt, kc - kbeg)) : 0;
+                        const int rws = diag ? rowsA : rows;
                         if (lane == 0)
-                            mbar_arrive_expect_tx(bar, (uint32_t)my_k * (uint32_t)rows * 8u + (half == 0 ? KT * 8u : 0u));
+                            mbar_arrive_expect_tx(bar, (uint32_t)my_k * (uint32_t)rws * 8u + (half == 0 ? KT * 8u : 0u));
                         __syncwarp();
-                        const int kl = half * (KT / 2) + lane;
+                        const int kl = kbeg + lane;
                         if (lane < my_k)
-                            bulk_g2s(smem_u32((pw == 0 ? S.a : S.b) + kl * LDT), p.X + (k0 + kl) * p.ld + (pw == 0 ? i0 : j0),
-                                     (uint32_t)rows * 8u, bar);
+                            bulk_g2s(smem_u32(((diag || pw == 0) ? S.a : S.b) + kl * LDT),
+                                     p.X + (k0 + kl) * p.ld + ((diag || pw == 0) ? i0 : j0), (uint32_t)rws * 8u, bar);
                         if (lane == 0 && half == 0) bulk_g2s(smem_u32(pw == 0 ? S.s : S.t), (pw == 0 ? p.s : p.t) + k0, KT * 8u, bar);
                     }
                 }
@@ -408,13 +491,11 @@ __global__ void __launch_bounds__(ROW ? gk::THREADS_ROW : gk::THREADS, 1) gram_t
         // warpgroups take the producers' registers: 128 x 40 + 256 x 232 = 384 x 168.
         asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         const int wn_cs = warp < 4 ? warp : 11 - warp;
-        const int dmap = (0x7132'6054 >> (4 * warp)) & 0xf;  // diagonal tiles: see the 2 x 4 path below
-        const int wm_dg = dmap >> 2, wn_dg = dmap & 3;
-        const int thr_dg = wn_dg * 4 - wm_dg * 8;
+
         int it = 0;
         const bool single = (seg_end - seg_begin) == 1;
         double acc[16][2][2];  // column-strip view; the diagonal path uses the same 64 registers as [8][4][2]
-        auto& acc_dg = reinterpret_cast<double (&)[8][4][2]>(acc);
+        auto& acc_dg = reinterpret_cast<double (&)[17][2]>(acc);  // diagonal tiles: see consume_stage_rp
 #pragma unroll
         for (int mi = 0; mi < 16; ++mi)
 #pragma unroll
@@ -441,24 +522,14 @@ __global__ void __launch_bounds__(ROW ? gk::THREADS_ROW : gk::THREADS, 1) gram_t
                 }
                 return;
             }
-#pragma unroll
-            for (int mi = 0; mi < 8; ++mi) {
-                const int row = wm_dg * 64 + mi * 8 + g;
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni) {
-                    const int col = wn_dg * 32 + ni * 8 + kq * 2;
-                    if ((mi - ni) >= thr_dg) {
-                        double2* dst = reinterpret_cast<double2*>(Pt + row * TM + col);
-                        double2 v = make_double2(acc_dg[mi][ni][0], acc_dg[mi][ni][1]);
-                        if (add) {
-                            const double2 o = *dst;
-                            v.x += o.x;
-                            v.y += o.y;
-                        }
-                        *dst = v;
-                    }
-                }
-            }
+            if (warp == 0) flush_rp<0>(acc_dg, Pt, g, kq, add);
+            else if (warp == 1) flush_rp<1>(acc_dg, Pt, g, kq, add);
+            else if (warp == 2) flush_rp<2>(acc_dg, Pt, g, kq, add);
+            else if (warp == 3) flush_rp<3>(acc_dg, Pt, g, kq, add);
+            else if (warp == 4) flush_rp<4>(acc_dg, Pt, g, kq, add);
+            else if (warp == 5) flush_rp<5>(acc_dg, Pt, g, kq, add);
+            else if (warp == 6) flush_rp<6>(acc_dg, Pt, g, kq, add);
+            else flush_rp<7>(acc_dg, Pt, g, kq, add);
             asm volatile("bar.sync 1, 256;" ::: "memory");  // rred may still be read by the previous flush
             if (rhalf == 1) sm.rred[rm] = racc;
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -476,10 +547,14 @@ __global__ void __launch_bounds__(ROW ? gk::THREADS_ROW : gk::THREADS, 1) gram_t
                 const int nst = max(0, min(base + sched_stage(p.seg_g1[sg], per, p.fix_bits), p.n_stages) - (base + sched_stage(p.seg_g0[sg], per, p.fix_bits)));
                 // warp-uniform dispatch to a fully unrolled, unpredicated instruction stream
                 if (!diag) run_segment_cs<0, KT, STAGES>(acc, racc, sm, it, nst, false, wn_cs, g, kq, rm, rhalf, lane);
-                else if (thr_dg <= -3) run_segment<1, KT, STAGES, false>(acc_dg, racc, sm, it, nst, wm_dg, wn_dg, g, kq, rm, rhalf, lane);
-                else if (thr_dg == 0) run_segment<2, KT, STAGES, false>(acc_dg, racc, sm, it, nst, wm_dg, wn_dg, g, kq, rm, rhalf, lane);
-                else if (thr_dg == 4) run_segment<3, KT, STAGES, false>(acc_dg, racc, sm, it, nst, wm_dg, wn_dg, g, kq, rm, rhalf, lane);
-                else run_segment<4, KT, STAGES, false>(acc_dg, racc, sm, it, nst, wm_dg, wn_dg, g, kq, rm, rhalf, lane);
+                else if (warp == 0) run_segment_rp<0, KT, STAGES, DU>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
+                else if (warp == 1) run_segment_rp<1, KT, STAGES, DU>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
+                else if (warp == 2) run_segment_rp<2, KT, STAGES, DU>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
+                else if (warp == 3) run_segment_rp<3, KT, STAGES, DU>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
+                else if (warp == 4) run_segment_rp<4, KT, STAGES, DU>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
+                else if (warp == 5) run_segment_rp<5, KT, STAGES, DU>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
+                else if (warp == 6) run_segment_rp<6, KT, STAGES, DU>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
+                else run_segment_rp<7, KT, STAGES, DU>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
                 if (!single) {
                     flush(sg, diag, per > 0);
 #pragma unroll
@@ -941,7 +1016,7 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
         const int64_t NP = (n_stages + PS - 1) / PS;
         const int64_t flush_cost = NP > 1 ? gk::W_OFF / 2 : 0;  // ~half a stage per tile switch
         const bool hybrid = KT == 32 && ctx->gram_cs && !row_native;
-        const int diag_weight = ctx->diag_weight > 0 ? ctx->diag_weight : (hybrid ? 42 : 40);
+        const int diag_weight = ctx->diag_weight > 0 ? ctx->diag_weight : (hybrid ? 38 : 40);
         if (ctx->sched_key[0] != nt || ctx->sched_key[1] != PS || ctx->sched_key[2] != G ||
             ctx->sched_key[3] != diag_weight * 1000 + flush_cost) {
             Schedule sc;
@@ -997,10 +1072,10 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
                                                          args, sizeof(SM), sm));
         } else if (hybrid) {
             using SM = gk::Smem<32, 3>;
-            BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_tma_kernel<32, 3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  (int)sizeof(SM)));
-            BLR_CUDA_OK(ctx, cudaLaunchCooperativeKernel((void*)gram_tma_kernel<32, 3, false, true>, dim3(G), dim3(gk::THREADS),
-                                                         args, sizeof(SM), sm));
+            // diagonal-tile code: partially unrolled when a large share of the SMs runs diagonal tiles (see consume_stage_rp)
+            void* kern = nt <= 4 ? (void*)gram_tma_kernel<32, 3, false, true, 4> : (void*)gram_tma_kernel<32, 3, false, true, 8>;
+            BLR_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
+            BLR_CUDA_OK(ctx, cudaLaunchCooperativeKernel(kern, dim3(G), dim3(gk::THREADS), args, sizeof(SM), sm));
         } else if (KT == 32) {
             using SM = gk::Smem<32, 3>;
             BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_tma_kernel<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,

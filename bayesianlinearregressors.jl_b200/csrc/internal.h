@@ -70,7 +70,7 @@ struct blr_ctx {
     int var_cfg = 1;       // marginals fast path: 1 = <4 x 64 rows, 64 points> (default), 0 = <8 x 64 rows, 32 points> (BLR_VAR_CFG=0)
     int gram_cs = 1;       // Gram consumer tiling: 1 = hybrid (column strips, 1 x 8 warps, on off-diagonal tiles), 0 = 2 x 4 (BLR_GRAM_CS)
     int gram_kt = 32;      // observations per pipeline stage of the Gram kernel: 16 or 32 (BLR_GRAM_KT)
-    int diag_weight = 0;   // cost of a diagonal-tile stage relative to W_OFF = 64; 0 = auto: 42 for the hybrid tiling, 40 for
+    int diag_weight = 0;   // cost of a diagonal-tile stage relative to W_OFF = 64; 0 = auto: 38 for the hybrid tiling, 40 for
                            // 2 x 4 (both measured best; BLR_DIAG_WEIGHT overrides)
     // host-streaming path (blr_stats_accumulate_host): copy stream, two staging slots
     cudaStream_t copy_stream = nullptr;

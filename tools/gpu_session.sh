@@ -144,6 +144,32 @@ print('variant $v mix TF', round(v.value, 3), 'pure DMMA TF', round(p.value, 3),
         BLR_GRAM_CS=0 timeout 600 python bench.py $cfg --steps 5 --warmup 3 --no-cpu --no-e2e --no-calibrate 2>> "$OUT/csw.err" \
           | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['achieved'])"
       done 2>&1 | tee -a "$OUT/cs_weight.log";;
+    diag_probe)
+      for c in 0 1; do
+        echo "BLR_GRAM_CS=$c D=128"
+        BLR_GRAM_CS=$c timeout 600 python bench.py --n-obs 4194304 --dim 128 --steps 5 --warmup 3 --no-cpu --no-e2e --no-calibrate 2>> "$OUT/dp.err" \
+          | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['achieved'])"
+      done 2>&1 | tee "$OUT/diag_probe.log"
+      BLR_GRAM_CS=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gram_tma -s 1 -c 1 -o "$OUT/prof_diag" -f \
+        python bench.py --n-obs 1048576 --dim 128 --steps 1 --warmup 1 --no-cpu --no-calibrate --no-e2e > "$OUT/ncu_diag.log" 2>&1; echo "ncu exit $?";;
+    l2pf_sweep)
+      for pf in ${PFS:-0 2 4 8}; do
+        for w in ${WEIGHTS:-36 40}; do
+          for cfg in "--n-obs 4194304 --dim 128" "--n-obs 1048576 --dim 256" "--n-obs 2097152 --dim 1024"; do
+            echo "L2PF=$pf DIAG_WEIGHT=$w cfg=$cfg"
+            BLR_GRAM_L2PF=$pf BLR_DIAG_WEIGHT=$w timeout 600 python bench.py $cfg --steps 5 --warmup 3 --no-cpu --no-e2e --no-calibrate 2>> "$OUT/pf.err" \
+              | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['achieved'])"
+          done
+        done
+      done 2>&1 | tee "$OUT/l2pf_sweep.log";;
+    shape_sweep)
+      for cfg in "--n-obs 4194304 --dim 128" "--n-obs 1048576 --dim 256" "--n-obs 1048576 --dim 384" "--n-obs 1048576 --dim 512" "--n-obs 1048576 --dim 640" "--n-obs 1048576 --dim 768" "--n-obs 2097152 --dim 1024" "--n-obs 1048576 --dim 2048" "--n-obs 262144 --dim 4096"; do
+        for c in ${CSS:-0 1}; do
+          echo "BLR_GRAM_CS=$c cfg=$cfg"
+          BLR_GRAM_CS=$c timeout 600 python bench.py $cfg --steps 5 --warmup 3 --no-cpu --no-e2e --no-calibrate 2>> "$OUT/shape.err" \
+            | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['achieved'])"
+        done
+      done 2>&1 | tee "$OUT/shape_sweep.log";;
     small_d)
       timeout 600 python tools/bench_small_d.py > "$OUT/small_d.jsonl" 2> "$OUT/small_d.err"; echo "small_d exit $?"; cat "$OUT/small_d.jsonl"; tail -3 "$OUT/small_d.err";;
     rff_multi)
