@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams
     const int npass = (int)(p.ldw / C::R);
 
     if (warp >= CONSUMER_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");  // producers hand their registers to the consumer warpgroups
         // ------------------------------------------------------------ producer warps (TMA)
         const int pw = warp - CONSUMER_WARPS;
         int it = 0;
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams
     }
 
     // ---------------------------------------------------------------- consumer warps (DMMA)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");  // 128 x 40 + 256 x 232 = 384 x 168
     const int g = lane >> 2, kq = lane & 3;
     constexpr int PP = NP / 16;               // mean: points per thread
     const int mk = tid & 15, mpg = tid >> 4;  // mean: feature within the stage, point group (conflict-free smem reads)
@@ -404,6 +406,7 @@ __global__ void __launch_bounds__(rk::THREADS, 1) rand_tma_kernel(const RandPara
     const int nsb = (p.S + TS - 1) / TS;
 
     if (warp >= CONSUMER_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         const int pw = warp - CONSUMER_WARPS;  // producer pw: points 32 pw .. 32 pw + 31 and W rows 8 pw .. 8 pw + 7
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -435,6 +438,7 @@ __global__ void __launch_bounds__(rk::THREADS, 1) rand_tma_kernel(const RandPara
         return;
     }
 
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, kq = lane & 3;
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
