@@ -74,6 +74,8 @@ SIGNATURES = {
          C.c_double, C.c_void_p, C.c_int64],
     ),
     "blr_stats_allreduce": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "blr_stats_allreduce_all": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int]),
+    "blr_comm_init_all": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "blr_stats_device_ptr": (C.c_int, [C.c_void_p, C.c_void_p, c_void_pp, C.POINTER(C.c_int64)]),
     "blr_stats_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "blr_stats_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -50,6 +50,8 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     std::string why;
@@ -71,6 +73,8 @@ static NcclApi* nccl_api() {
     api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
     api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
     api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+    api.GroupStart = (decltype(api.GroupStart))dlsym(api.handle, "ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))dlsym(api.handle, "ncclGroupEnd");
     api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
     api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
     if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.GetErrorString) {
@@ -333,6 +337,57 @@ int blr_comm_init_rank(blr_ctx* ctx, const void* id128, int nranks, int rank) {
     ctx->nccl_comm = (void*)comm;
     ctx->nranks = nranks;
     ctx->rank = rank;
+    return 0;
+}
+// One process driving several GPUs (one context per device -- a Julia session): rank i = ctxs[i].  The n
+// ncclCommInitRank calls must be in flight together, hence the group.
+int blr_comm_init_all(blr_ctx** ctxs, int n) {
+    if (!ctxs || n < 1) return BLR_E_INVALID;
+    for (int i = 0; i < n; ++i)
+        if (!ctxs[i]) return BLR_E_INVALID;
+    NcclApi* a = nccl_api();
+    if (!a->handle || !a->GroupStart || !a->GroupEnd) return set_err(ctxs[0], BLR_E_NCCL, a->handle ? "libnccl lacks group calls" : a->why);
+    for (int i = 0; i < n; ++i) blr_comm_destroy(ctxs[i]);
+    if (n == 1) return 0;
+    ncclUniqueId id;
+    ncclResult_t r = a->GetUniqueId(&id);
+    if (r != ncclSuccess) return nccl_fail(ctxs[0], r, "ncclGetUniqueId");
+    std::vector<ncclComm_t> comms((size_t)n, nullptr);
+    r = a->GroupStart();
+    for (int i = 0; i < n && r == ncclSuccess; ++i) {
+        cudaSetDevice(ctxs[i]->device);
+        r = a->CommInitRank(&comms[(size_t)i], n, id, i);
+    }
+    const ncclResult_t re = a->GroupEnd();
+    if (r == ncclSuccess) r = re;
+    if (r != ncclSuccess) return nccl_fail(ctxs[0], r, "ncclCommInitRank (group)");
+    for (int i = 0; i < n; ++i) {
+        ctxs[i]->nccl_comm = (void*)comms[(size_t)i];
+        ctxs[i]->nranks = n;
+        ctxs[i]->rank = i;
+    }
+    return 0;
+}
+// Grouped in-place sum of stats[i] (resident on ctxs[i]'s device) over the contexts of a blr_comm_init_all communicator.
+int blr_stats_allreduce_all(blr_ctx** ctxs, blr_stats** stats, int n) {
+    if (!ctxs || !stats || n < 1) return BLR_E_INVALID;
+    if (n == 1) return 0;
+    NcclApi* a = nccl_api();
+    if (!a->handle || !a->GroupStart || !a->GroupEnd) return set_err(ctxs[0], BLR_E_NCCL, a->handle ? "libnccl lacks group calls" : a->why);
+    for (int i = 0; i < n; ++i) {
+        if (!ctxs[i] || !stats[i] || !ctxs[i]->nccl_comm || ctxs[i]->nranks != n)
+            return set_err(ctxs[0], BLR_E_INVALID, "contexts are not the n ranks of one communicator");
+        if (stats[i]->len() != stats[0]->len()) return set_err(ctxs[0], BLR_E_DIM, "statistics of different dimension");
+    }
+    ncclResult_t r = a->GroupStart();
+    for (int i = 0; i < n && r == ncclSuccess; ++i) {
+        cudaSetDevice(ctxs[i]->device);
+        r = a->AllReduce(stats[i]->p, stats[i]->p, (size_t)stats[i]->len(), ncclFloat64, ncclSum, (ncclComm_t)ctxs[i]->nccl_comm,
+                         ctxs[i]->stream);
+    }
+    const ncclResult_t re = a->GroupEnd();
+    if (r == ncclSuccess) r = re;
+    if (r != ncclSuccess) return nccl_fail(ctxs[0], r, "ncclAllReduce (group)");
     return 0;
 }
 int blr_comm_destroy(blr_ctx* ctx) {

@@ -113,6 +113,14 @@ class Context:
         dist.broadcast_object_list(box, src=0)
         self.init_comm(world, rank, box[0])
 
+    @staticmethod
+    def init_comm_all(ctxs):
+        """One process, several GPUs: make `ctxs` (one Context per device) the ranks 0..n-1 of one communicator."""
+        arr = (C.c_void_p * len(ctxs))(*[c.handle for c in ctxs])
+        ctxs[0].check(ctxs[0].lib.blr_comm_init_all(arr, len(ctxs)))
+        for i, c in enumerate(ctxs):
+            c.rank, c.world = i, len(ctxs)
+
     # ---- calibration ---------------------------------------------------------------------------
     def calibrate(self) -> dict:
         out = {}
@@ -245,6 +253,13 @@ class Stats:
 
     def allreduce(self):
         self.ctx.check(self.ctx.lib.blr_stats_allreduce(self.ctx.handle, self.handle))
+
+    @staticmethod
+    def allreduce_all(stats):
+        """Grouped in-place sum over the per-device statistics of a single-process communicator (Context.init_comm_all)."""
+        ctxs = (C.c_void_p * len(stats))(*[s.ctx.handle for s in stats])
+        hs = (C.c_void_p * len(stats))(*[s.handle for s in stats])
+        stats[0].ctx.check(stats[0].ctx.lib.blr_stats_allreduce_all(ctxs, hs, len(stats)))
 
     def download(self) -> np.ndarray:
         out = np.empty(len(self), dtype=np.float64)

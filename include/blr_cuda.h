@@ -94,6 +94,9 @@ int blr_host_free(blr_ctx* ctx, void* p);
  * (SURVEY.md section 8e).  NCCL is dlopen'ed on first use. */
 int blr_nccl_unique_id(void* out128);
 int blr_comm_init_rank(blr_ctx* ctx, const void* id128, int nranks, int rank);
+/* One process driving n GPUs (one context per device, e.g. a Julia session): rank i = ctxs[i]; the communicators are
+ * created inside one NCCL group.  blr_stats_allreduce_all is the matching grouped in-place sum of stats[i] on ctxs[i]. */
+int blr_comm_init_all(blr_ctx** ctxs, int n);
 int blr_comm_destroy(blr_ctx* ctx);
 
 /* ------------------------------------------------------------------ data handles */
@@ -141,6 +144,7 @@ int blr_stats_accumulate_host(blr_ctx* ctx, blr_stats* s, const double* mw_host,
                               const double* sigma2_host, int64_t chunk);
 /* in-place NCCL sum over ranks; no-op without a communicator. */
 int blr_stats_allreduce(blr_ctx* ctx, blr_stats* s);
+int blr_stats_allreduce_all(blr_ctx** ctxs, blr_stats** stats, int n);
 int blr_stats_device_ptr(blr_ctx* ctx, const blr_stats* s, double** dev_out, int64_t* len_out);
 int blr_stats_download(blr_ctx* ctx, const blr_stats* s, double* host);
 int blr_stats_upload(blr_ctx* ctx, blr_stats* s, const double* host);

@@ -185,3 +185,57 @@ function apply_weights(ctx::Context, x::DeviceX, w::Vector{Float64})
 end
 
 end # module
+
+
+# ------------------------------------------------------------------------------------------------ several GPUs, one process
+# One Context per device; observations are sharded over them (contiguous column blocks), each device accumulates the
+# statistics of its shard, ONE grouped all-reduce sums them, every device then holds the same posterior
+# (SURVEY.md section 8e).  UNEXECUTED -- see INTEGRATION.md.
+struct MultiContext
+    ctxs::Vector{Context}
+end
+
+function MultiContext(devices::AbstractVector{<:Integer})
+    ctxs = [Context(Cint(d)) for d in devices]
+    ptrs = [c.ptr for c in ctxs]
+    rc = ccall((:blr_comm_init_all, libblr), Cint, (Ptr{Ptr{Cvoid}}, Cint), ptrs, length(ptrs))
+    check(ctxs[1], rc)
+    return MultiContext(ctxs)
+end
+
+"contiguous shard of 1:N owned by rank r (0-based) of P -- the same split as sharding.py / bench.py"
+function shard_bounds(N::Integer, P::Integer, r::Integer)
+    q, rem = divrem(N, P)
+    lo = r * q + min(r, rem)
+    return lo + 1, lo + q + (r < rem ? 1 : 0)
+end
+
+"posterior + logpdf of ColVecs data X (D x N) sharded over the devices of `mc`; returns (logpdf, m′, Λ′) from device 1"
+function infer_sharded(mc::MultiContext, prior::Prior, X::StridedMatrix{Float64}, y::Vector{Float64}, σ²::Vector{Float64},
+                       mw::Vector{Float64})
+    D, N = size(X)
+    P = length(mc.ctxs)
+    stats = Vector{Ptr{Cvoid}}(undef, P)
+    for (r, ctx) in enumerate(mc.ctxs)
+        lo, hi = shard_bounds(N, P, r - 1)
+        st = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ctx, ccall((:blr_stats_create, libblr), Cint, (Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}), ctx.ptr, D, st))
+        Xr, yr, sr = view(X, :, lo:hi), view(y, lo:hi), view(σ², lo:hi)
+        GC.@preserve X y σ² mw check(ctx, ccall((:blr_stats_accumulate_host, libblr), Cint,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Int64, Cint, Ptr{Float64}, Cint, Float64,
+             Ptr{Float64}, Int64),
+            ctx.ptr, st[], mw, Xr, D, hi - lo + 1, stride(X, 2), COLVECS, yr, NOISE_VECTOR, 0.0, sr, 1 << 16))
+        stats[r] = st[]
+    end
+    ptrs = [c.ptr for c in mc.ctxs]
+    check(mc.ctxs[1], ccall((:blr_stats_allreduce_all, libblr), Cint, (Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Cint), ptrs, stats, P))
+    lp = Ref{Float64}(NaN); m = Vector{Float64}(undef, D); Λ = Matrix{Float64}(undef, D, D)
+    ctx = mc.ctxs[1]
+    check(ctx, ccall((:blr_infer_from_stats, libblr), Cint,
+        (Ptr{Cvoid}, Ref{Prior}, Ptr{Cvoid}, Ref{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cvoid}),
+        ctx.ptr, prior, stats[1], lp, m, C_NULL, Λ, C_NULL))
+    for (r, c) in enumerate(mc.ctxs)
+        ccall((:blr_stats_free, libblr), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), c.ptr, stats[r])
+    end
+    return lp[], m, Λ
+end

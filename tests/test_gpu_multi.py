@@ -66,3 +66,50 @@ def test_two_rank_sharded_inference(tmp_path):
     assert abs(r0["lp"] - lp) <= 1e-9 * abs(lp)
     assert np.linalg.norm(r0["m"] - post.mw) <= 1e-9 * np.linalg.norm(post.mw)
     assert np.linalg.norm(r0["L"] - ref.dense(post.Λw)) <= 1e-9 * np.linalg.norm(ref.dense(post.Λw))
+
+
+def test_single_process_two_devices():
+    """One process driving two GPUs (the shape of a Julia session): blr_comm_init_all + blr_stats_allreduce_all.
+    Each context accumulates its shard, the grouped all-reduce sums them, every device solves the same posterior."""
+    import ctypes as C
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import blr_b200 as blr
+    from blr_b200 import _lib as L
+    from oracle import blr_oracle as ref
+
+    rng = np.random.default_rng(5)
+    D, N = 256, 30011
+    X = rng.standard_normal((D, N))
+    s2 = np.exp(rng.standard_normal(N))
+    mw = rng.standard_normal(D)
+    y = X.T @ rng.standard_normal(D) + np.sqrt(s2) * rng.standard_normal(N)
+    ctxs = [blr.Context(0), blr.Context(1)]
+    blr.Context.init_comm_all(ctxs)
+    stats, keep = [], []
+    for r, ctx in enumerate(ctxs):
+        lo, hi = blr.ShardPlan(N, 2).bounds(r)
+        Xd = blr.DeviceMatrix.upload(ctx, X[:, lo:hi], 0)
+        yd, sd = blr.DeviceVector.upload(ctx, y[lo:hi]), blr.DeviceVector.upload(ctx, s2[lo:hi])
+        st = blr.Stats(ctx, D)
+        noise = L.Noise(L.NOISE_VECTOR, 0.0, sd.handle, None, 0)
+        ctx.check(ctx.lib.blr_stats_accumulate(ctx.handle, st.handle, np.ascontiguousarray(mw).ctypes.data_as(C.c_void_p), Xd.handle,
+                                               yd.handle, C.byref(noise)))
+        stats.append(st)
+        keep.append((Xd, yd, sd))
+    blr.Stats.allreduce_all(stats)
+    f = blr.BayesianLinearRegressor(mw, blr.Diagonal(np.ones(D)))
+    outs = []
+    for ctx, st in zip(ctxs, stats):
+        prior, kp = f._prior_struct()
+        lp = C.c_double()
+        m = np.empty(D)
+        ctx.check(ctx.lib.blr_infer_from_stats(ctx.handle, C.byref(prior), st.handle, C.byref(lp), m.ctypes.data_as(C.c_void_p), None, None, None))
+        outs.append((lp.value, m))
+    lpo, mo, _ = ref.infer_streaming(mw, ref.Diagonal(np.ones(D)), X, y, s2)
+    assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1])
+    assert abs(outs[0][0] - lpo) <= 1e-9 * abs(lpo)
+    assert np.linalg.norm(outs[0][1] - mo) / np.linalg.norm(mo) < 1e-9
