@@ -229,6 +229,7 @@ int blr_ctx_create(blr_ctx** out, int device) {
         if (atoi(k) == 16) ctx->gram_kt = 16;
         if (atoi(k) == 32) ctx->gram_kt = 32;
     }
+    if (const char* v = getenv("BLR_GRAM_UNIT")) ctx->gram_unit = atoi(v) != 0 ? 1 : 0;
     if (const char* v = getenv("BLR_GRAM_CS")) ctx->gram_cs = atoi(v) != 0 ? 1 : 0;
     if (const char* v = getenv("BLR_VAR_CFG")) ctx->var_cfg = atoi(v) == 0 ? 0 : 1;
     if (const char* w = getenv("BLR_DIAG_WEIGHT")) {

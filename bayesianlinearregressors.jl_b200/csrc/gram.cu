@@ -153,6 +153,7 @@ struct GramParams {
     unsigned int* period_counter;  // soft barrier: number of (CTA, period) pairs whose loads have all been issued
 };
 
+
 // integer stage of a fixed-point boundary in period `per` (dither θ_per shared by all CTAs, θ_0 = 0)
 __device__ __forceinline__ int sched_stage(int fix, int per, int bits) {
     const unsigned int theta = per == 0 ? 0u : (((unsigned int)per * 40503u) & 0xffffu) >> (16 - bits);
@@ -234,7 +235,7 @@ __device__ __forceinline__ void run_segment(double (&acc)[8][4][2], double& racc
 // (pair p, e; b; c) is element (row 16 p + 2 g + e, col 16 wn + 4 kq + 2 c + b): a thread owns 2 x 4 blocks, flushed as
 // two 16-byte stores per row.  Diagonal tiles: the 16-row band p is needed by column strip wn iff p >= wn (compile-time
 // P0 = wn; 36 live 8 x 8 sub-tiles per SM sub-partition with the warp -> strip map {0,1,2,3,7,6,5,4}).
-template <int P0, int KT>
+template <int P0, int KT, bool UNIT>
 __device__ __forceinline__ void consume_stage_cs(double (&acc)[16][2][2], const double* __restrict__ Asrc,
                                                  const double* __restrict__ Bsrc, const double* __restrict__ Ssrc, int wn,
                                                  int g, int kq) {
@@ -253,8 +254,8 @@ __device__ __forceinline__ void consume_stage_cs(double (&acc)[16][2][2], const 
             a[2 * pr + 1] = v.y;
         }
         const double2 bv = *reinterpret_cast<const double2*>(Bp + kl * LDT);
-        b[0] = bv.x * sk;
-        b[1] = bv.y * sk;
+        b[0] = UNIT ? bv.x : bv.x * sk;  // UNIT: homoscedastic noise, the common factor 1/σ² is applied by the reduction
+        b[1] = UNIT ? bv.y : bv.y * sk;
 #pragma unroll
         for (int mi = 2 * P0; mi < 16; ++mi)
 #pragma unroll
@@ -262,7 +263,7 @@ __device__ __forceinline__ void consume_stage_cs(double (&acc)[16][2][2], const 
     }
 }
 
-template <int P0, int KT, int STAGES>
+template <int P0, int KT, int STAGES, bool UNIT>
 __device__ __forceinline__ void run_segment_cs(double (&acc)[16][2][2], double& racc, gk::Smem<KT, STAGES, false>& sm, int& it,
                                                int nst, bool diag, int wn, int g, int kq, int rm, int rhalf, int lane) {
     using namespace gk;
@@ -271,7 +272,7 @@ __device__ __forceinline__ void run_segment_cs(double (&acc)[16][2][2], double& 
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(smem_u32(&sm.full[stg]), ph);
         const Stage<KT, false>& S = sm.st[stg];
-        consume_stage_cs<P0, KT>(acc, S.a, diag ? S.a : S.b, S.s, wn, g, kq);
+        consume_stage_cs<P0, KT, UNIT>(acc, S.a, diag ? S.a : S.b, S.s, wn, g, kq);
         if (diag) {
 #pragma unroll
             for (int k = 0; k < KT / 2; ++k) {  // r block of this row panel: r[m] += Σ_k X[m,k] t_k
@@ -290,7 +291,7 @@ __device__ __forceinline__ void run_segment_cs(double (&acc)[16][2][2], double& 
 // sub-partition one heavy and one light (or idle) warp run the heavy warp's DMMA stream at 1 per 21-32 cycles instead of 16
 // -- a diagonal tile then costs as much as a full one.  Only the two A fragments are scaled by s_k (2 DMUL per 17 DMMA).
 // acc[c] (c <= R0) is sub-tile (R0, c); acc[R0 + 1 + c] (c <= R1) is sub-tile (R1, c).
-template <int W, int KT, int DU>
+template <int W, int KT, int DU, bool UNIT>
 __device__ __forceinline__ void consume_stage_rp(double (&acc)[17][2], const gk::Stage<KT, false>& S, int g, int kq) {
     using namespace gk;
     constexpr int R0 = W, R1 = 15 - W;          // block rows of this warp (R0 < R1)
@@ -304,7 +305,8 @@ __device__ __forceinline__ void consume_stage_rp(double (&acc)[17][2], const gk:
     for (int kk = 0; kk < KT / 4; ++kk) {
         const int kl = kk * 4 + kq;
         const double sk = S.s[kl];
-        const double a0 = Ap[kl * LDT + R0 * 8] * sk, a1 = Ap[kl * LDT + R1 * 8] * sk;
+        const double a0 = UNIT ? Ap[kl * LDT + R0 * 8] : Ap[kl * LDT + R0 * 8] * sk;
+        const double a1 = UNIT ? Ap[kl * LDT + R1 * 8] : Ap[kl * LDT + R1 * 8] * sk;
         double b[N1];
 #pragma unroll
         for (int c = 0; c < N1; ++c) b[c] = Ap[kl * LDT + c * 8];
@@ -316,7 +318,7 @@ __device__ __forceinline__ void consume_stage_rp(double (&acc)[17][2], const gk:
     }
 }
 
-template <int W, int KT, int STAGES, int DU>
+template <int W, int KT, int STAGES, int DU, bool UNIT>
 __device__ __forceinline__ void run_segment_rp(double (&acc)[17][2], double& racc, gk::Smem<KT, STAGES, false>& sm, int& it,
                                                int nst, int g, int kq, int rm, int rhalf, int lane) {
     using namespace gk;
@@ -325,7 +327,7 @@ __device__ __forceinline__ void run_segment_rp(double (&acc)[17][2], double& rac
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(smem_u32(&sm.full[stg]), ph);
         const Stage<KT, false>& S = sm.st[stg];
-        consume_stage_rp<W, KT, DU>(acc, S, g, kq);
+        consume_stage_rp<W, KT, DU, UNIT>(acc, S, g, kq);
 #pragma unroll
         for (int k = 0; k < KT / 2; ++k) {  // r block of this row panel: r[m] += Σ_k X[m,k] t_k
             const int kl = rhalf * (KT / 2) + k;
@@ -359,7 +361,7 @@ __device__ __forceinline__ void flush_rp(const double (&acc)[17][2], double* __r
     }
 }
 
-template <int KT, int STAGES, bool ROW = false, bool CS = false, int DU = 8>
+template <int KT, int STAGES, bool ROW = false, bool CS = false, int DU = 8, bool UNIT = false>
 __global__ void __launch_bounds__(ROW ? gk::THREADS_ROW : gk::THREADS, 1) gram_tma_kernel(const GramParams p) {
     using namespace gk;
     using Stage = gk::Stage<KT, ROW>;
@@ -427,7 +429,8 @@ __global__ void __launch_bounds__(ROW ? gk::THREADS_ROW : gk::THREADS, 1) gram_t
                     const int kc = (int)min((int64_t)KT, p.N - k0);
                     Stage& S = sm.st[stg];
                     const uint32_t bar = smem_u32(&sm.full[stg]);
-                    if (narrow) {  // rare (only tiles in the last block row when D % 128 != 0): clear my part first
+                    // UNIT: observations beyond N are not neutralised by s = 0, so the one partial stage clears its slot too
+                    if (narrow || (UNIT && kc < KT)) {  // rare (tiles in the last block row when D % 128 != 0): clear my part first
                         // (the part this warp is about to fill: a quarter of panel I on a ColVecs diagonal tile, see below)
                         const bool quarter = !ROW && diag;
                         double* z = quarter ? S.a + pwr * (Stage::PANEL / 4) : (pw == 0 ? S.a : S.b) + half * (Stage::PANEL / 2);
@@ -546,15 +549,15 @@ __global__ void __launch_bounds__(ROW ? gk::THREADS_ROW : gk::THREADS, 1) gram_t
                 const bool diag = (ti == tj);
                 const int nst = max(0, min(base + sched_stage(p.seg_g1[sg], per, p.fix_bits), p.n_stages) - (base + sched_stage(p.seg_g0[sg], per, p.fix_bits)));
                 // warp-uniform dispatch to a fully unrolled, unpredicated instruction stream
-                if (!diag) run_segment_cs<0, KT, STAGES>(acc, racc, sm, it, nst, false, wn_cs, g, kq, rm, rhalf, lane);
-                else if (warp == 0) run_segment_rp<0, KT, STAGES, DU>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
-                else if (warp == 1) run_segment_rp<1, KT, STAGES, DU>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
-                else if (warp == 2) run_segment_rp<2, KT, STAGES, DU>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
-                else if (warp == 3) run_segment_rp<3, KT, STAGES, DU>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
-                else if (warp == 4) run_segment_rp<4, KT, STAGES, DU>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
-                else if (warp == 5) run_segment_rp<5, KT, STAGES, DU>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
-                else if (warp == 6) run_segment_rp<6, KT, STAGES, DU>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
-                else run_segment_rp<7, KT, STAGES, DU>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
+                if (!diag) run_segment_cs<0, KT, STAGES, UNIT>(acc, racc, sm, it, nst, false, wn_cs, g, kq, rm, rhalf, lane);
+                else if (warp == 0) run_segment_rp<0, KT, STAGES, DU, UNIT>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
+                else if (warp == 1) run_segment_rp<1, KT, STAGES, DU, UNIT>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
+                else if (warp == 2) run_segment_rp<2, KT, STAGES, DU, UNIT>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
+                else if (warp == 3) run_segment_rp<3, KT, STAGES, DU, UNIT>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
+                else if (warp == 4) run_segment_rp<4, KT, STAGES, DU, UNIT>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
+                else if (warp == 5) run_segment_rp<5, KT, STAGES, DU, UNIT>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
+                else if (warp == 6) run_segment_rp<6, KT, STAGES, DU, UNIT>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
+                else run_segment_rp<7, KT, STAGES, DU, UNIT>(acc_dg, racc, sm, it, nst, g, kq, rm, rhalf, lane);
                 if (!single) {
                     flush(sg, diag, per > 0);
 #pragma unroll
@@ -871,7 +874,7 @@ __global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restri
                                                           int D, double* __restrict__ G, double* __restrict__ r,
                                                           double* __restrict__ scal,
                                                           const double* __restrict__ prep_partial, int prep_blocks,
-                                                          double n_obs) {
+                                                          double n_obs, double gscale) {
     __shared__ double red[32];
     int ti, tj;
     tile_from_index(blockIdx.x, ti, tj);
@@ -885,7 +888,7 @@ __global__ void __launch_bounds__(256) gram_reduce_kernel(const double* __restri
         if (gi < D && gj < D && gi >= gj) {
             double v = 0.0;
             for (int sl = s0; sl < s1; ++sl) v += P[(int64_t)sl * tsz + e];
-            const double nv = G[(int64_t)gj * D + gi] + v;
+            const double nv = G[(int64_t)gj * D + gi] + v * gscale;  // gscale = 1/σ² when the kernel ran unscaled, else 1
             G[(int64_t)gj * D + gi] = nv;
             if (gi != gj) G[(int64_t)gi * D + gj] = nv;
         }
@@ -1016,6 +1019,7 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
         const int64_t NP = (n_stages + PS - 1) / PS;
         const int64_t flush_cost = NP > 1 ? gk::W_OFF / 2 : 0;  // ~half a stage per tile switch
         const bool hybrid = KT == 32 && ctx->gram_cs && !row_native;
+        const bool unit = hybrid && sigma2 == nullptr && ctx->gram_unit;  // Σy = σ² I
         const int diag_weight = ctx->diag_weight > 0 ? ctx->diag_weight : (hybrid ? 38 : 40);
         if (ctx->sched_key[0] != nt || ctx->sched_key[1] != PS || ctx->sched_key[2] != G ||
             ctx->sched_key[3] != diag_weight * 1000 + flush_cost) {
@@ -1072,8 +1076,12 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
                                                          args, sizeof(SM), sm));
         } else if (hybrid) {
             using SM = gk::Smem<32, 3>;
-            // diagonal-tile code: partially unrolled when a large share of the SMs runs diagonal tiles (see consume_stage_rp)
-            void* kern = nt <= 4 ? (void*)gram_tma_kernel<32, 3, false, true, 4> : (void*)gram_tma_kernel<32, 3, false, true, 8>;
+            // diagonal-tile code: partially unrolled when a large share of the SMs runs diagonal tiles (see consume_stage_rp);
+            // homoscedastic noise: no per-observation scaling in the kernel at all, 1/σ² is applied by the reduction
+            void* kern = unit ? (nt <= 4 ? (void*)gram_tma_kernel<32, 3, false, true, 4, true>
+                                         : (void*)gram_tma_kernel<32, 3, false, true, 8, true>)
+                              : (nt <= 4 ? (void*)gram_tma_kernel<32, 3, false, true, 4, false>
+                                         : (void*)gram_tma_kernel<32, 3, false, true, 8, false>);
             BLR_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SM)));
             BLR_CUDA_OK(ctx, cudaLaunchCooperativeKernel(kern, dim3(G), dim3(gk::THREADS), args, sizeof(SM), sm));
         } else if (KT == 32) {
@@ -1100,7 +1108,7 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
         // the slot sum of one tile is spread over several CTAs (few tiles at small D, many slots per tile)
         const int ysplit = std::max(1, std::min(16, (2 * G) / T));
         gram_reduce_kernel<<<dim3(T, ysplit), 256, 0, sm>>>(gp.P, gp.Pr, TS, tile_slot_begin, 0, D, st->G(), st->r(), st->scal(),
-                                              prep_partial, prep_blocks, (double)N);
+                                              prep_partial, prep_blocks, (double)N, unit ? 1.0 / sigma2_scalar : 1.0);
         BLR_CHECK_LAUNCH(ctx, "gram_reduce_kernel");
     } else {
         const int TS = gg::TS;
@@ -1119,7 +1127,7 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
         BLR_CHECK_LAUNCH(ctx, "gram_generic_kernel");
         BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], sm));
         gram_reduce_kernel<<<ntiles, 256, 0, sm>>>(P, Pr, TS, nullptr, nsplit, D, st->G(), st->r(), st->scal(),
-                                                   prep_partial, prep_blocks, (double)N);
+                                                   prep_partial, prep_blocks, (double)N, 1.0);
         BLR_CHECK_LAUNCH(ctx, "gram_reduce_kernel");
     }
     BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], sm));

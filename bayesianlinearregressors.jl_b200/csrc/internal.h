@@ -68,6 +68,7 @@ struct blr_ctx {
     int64_t gram_period_obs = 0;  // observations per L2 period of the Gram kernel (0 = single period; BLR_GRAM_PERIOD_OBS)
     int gram_stages = 0;   // ring depth override for gram_kt == 16 (BLR_GRAM_STAGES = 6)
     int var_cfg = 1;       // marginals fast path: 1 = <4 x 64 rows, 64 points> (default), 0 = <8 x 64 rows, 32 points> (BLR_VAR_CFG=0)
+    int gram_unit = 1;     // homoscedastic noise: run the Gram kernel unscaled and apply 1/σ² in the reduction (BLR_GRAM_UNIT=0: off)
     int gram_cs = 1;       // Gram consumer tiling: 1 = hybrid (column strips, 1 x 8 warps, on off-diagonal tiles), 0 = 2 x 4 (BLR_GRAM_CS)
     int gram_kt = 32;      // observations per pipeline stage of the Gram kernel: 16 or 32 (BLR_GRAM_KT)
     int diag_weight = 0;   // cost of a diagonal-tile stage relative to W_OFF = 64; 0 = auto: 38 for the hybrid tiling, 40 for

@@ -194,7 +194,7 @@ def run_ours(args):
     ctx.sync()
 
     f = blr.BayesianLinearRegressor(np.zeros(D), blr.Diagonal(np.ones(D)))
-    fx = f(blr.ColVecs(X), σ2)
+    fx = f(blr.ColVecs(X), 0.37 if args.scalar_noise else σ2)
     fx.ctx = ctx
 
     def barrier():
@@ -257,7 +257,8 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": f"diagonal-noise BLR posterior+logpdf, N={N}, D={D}, fp64, ColVecs, N-sharded over {world} GPU(s)",
-                       "n_obs": N, "dim": D, "prior": "mw=0, Λw=I", "noise": "heteroscedastic diagonal exp(N(0,1))",
+                       "n_obs": N, "dim": D, "prior": "mw=0, Λw=I",
+                       "noise": "homoscedastic 0.37 I (secondary measurement)" if args.scalar_noise else "heteroscedastic diagonal exp(N(0,1))",
                        "l2": "inputs (%.1f GiB per GPU) far larger than L2; no flush needed" % (n_loc * D * 8 / 2**30),
                        "parallelism": f"obs-sharded x{world}, one NCCL allreduce of D^2+D+3 doubles"},
             "gpu_launches": launches,
@@ -367,6 +368,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-calibrate", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scalar-noise", action="store_true", help="secondary measurement: Σy = σ² I instead of the headline's heteroscedastic noise")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

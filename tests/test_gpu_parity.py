@@ -53,6 +53,8 @@ STAT_CASES = [
     (64, 16, True, False, "col"),
     (64, 1000, False, False, "col"),
     (128, 4096, True, True, "col"),
+    (192, 1003, False, True, "col"),     # scalar noise: unscaled Gram kernel (1/σ² applied by the reduction), partial last stage
+    (1024, 2049, True, True, "col"),
     (130, 515, False, False, "col"),     # D tail inside a 128 tile, N tail inside a stage
     (256, 20000, False, False, "col"),
     (320, 7777, True, False, "col"),

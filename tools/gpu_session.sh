@@ -170,6 +170,15 @@ print('variant $v mix TF', round(v.value, 3), 'pure DMMA TF', round(p.value, 3),
             | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['achieved'])"
         done
       done 2>&1 | tee "$OUT/shape_sweep.log";;
+    unit_ab)
+      timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_reference_suite.py -m gpu -q --timeout 600 2>&1 | tail -3
+      for u in 1 0; do
+        for cfg in "--n-obs 1048576 --dim 256" "--n-obs 2097152 --dim 1024"; do
+          echo "BLR_GRAM_UNIT=$u scalar-noise cfg=$cfg"
+          BLR_GRAM_UNIT=$u timeout 600 python bench.py $cfg --steps 5 --warmup 3 --no-cpu --no-e2e --no-calibrate --scalar-noise 2>> "$OUT/unit.err" \
+            | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['achieved'])"
+        done
+      done 2>&1 | tee "$OUT/unit_ab.log";;
     small_d)
       timeout 600 python tools/bench_small_d.py > "$OUT/small_d.jsonl" 2> "$OUT/small_d.err"; echo "small_d exit $?"; cat "$OUT/small_d.jsonl"; tail -3 "$OUT/small_d.err";;
     rff_multi)
