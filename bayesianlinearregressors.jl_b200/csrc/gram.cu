@@ -291,12 +291,13 @@ __device__ __forceinline__ void run_segment_cs(double (&acc)[16][2][2], double& 
 // sub-partition one heavy and one light (or idle) warp run the heavy warp's DMMA stream at 1 per 21-32 cycles instead of 16
 // -- a diagonal tile then costs as much as a full one.  Only the two A fragments are scaled by s_k (2 DMUL per 17 DMMA).
 // acc[c] (c <= R0) is sub-tile (R0, c); acc[R0 + 1 + c] (c <= R1) is sub-tile (R1, c).
-template <int W, int KT, int DU, bool UNIT>
-__device__ __forceinline__ void consume_stage_rp(double (&acc)[17][2], const gk::Stage<KT, false>& S, int g, int kq) {
+template <int W, int KT, int DU, bool UNIT, bool ROW>
+__device__ __forceinline__ void consume_stage_rp(double (&acc)[17][2], const gk::Stage<KT, ROW>& S, int g, int kq) {
     using namespace gk;
     constexpr int R0 = W, R1 = 15 - W;          // block rows of this warp (R0 < R1)
     constexpr int N0 = R0 + 1, N1 = R1 + 1;     // live sub-tiles in each (columns 0 .. R)
-    const double* Ap = S.a + g;
+    constexpr int SK = Stage<KT, ROW>::SK, SM = Stage<KT, ROW>::SM;  // element (k, m) of the panel at k * SK + m * SM
+    const double* Ap = S.a + g * SM;
     // DU = k4 steps per loop trip.  Eight warps run eight different instruction streams here; fully unrolled (DU = 8:
     // 56 KB for the eight variants) they miss the instruction cache once most SMs of the chip run diagonal tiles at the
     // same time (D <= 512: 37 % of the stall samples were `no_instructions`, a diagonal tile cost as much as a full one),
@@ -305,11 +306,11 @@ __device__ __forceinline__ void consume_stage_rp(double (&acc)[17][2], const gk:
     for (int kk = 0; kk < KT / 4; ++kk) {
         const int kl = kk * 4 + kq;
         const double sk = S.s[kl];
-        const double a0 = UNIT ? Ap[kl * LDT + R0 * 8] : Ap[kl * LDT + R0 * 8] * sk;
-        const double a1 = UNIT ? Ap[kl * LDT + R1 * 8] : Ap[kl * LDT + R1 * 8] * sk;
+        const double a0 = UNIT ? Ap[kl * SK + R0 * 8 * SM] : Ap[kl * SK + R0 * 8 * SM] * sk;
+        const double a1 = UNIT ? Ap[kl * SK + R1 * 8 * SM] : Ap[kl * SK + R1 * 8 * SM] * sk;
         double b[N1];
 #pragma unroll
-        for (int c = 0; c < N1; ++c) b[c] = Ap[kl * LDT + c * 8];
+        for (int c = 0; c < N1; ++c) b[c] = Ap[kl * SK + c * 8 * SM];
 #pragma unroll
         for (int c = 0; c < N1; ++c) {
             if (c < N0) dmma884(acc[c], a0, b[c]);
@@ -318,20 +319,20 @@ __device__ __forceinline__ void consume_stage_rp(double (&acc)[17][2], const gk:
     }
 }
 
-template <int W, int KT, int STAGES, int DU, bool UNIT>
-__device__ __forceinline__ void run_segment_rp(double (&acc)[17][2], double& racc, gk::Smem<KT, STAGES, false>& sm, int& it,
+template <int W, int KT, int STAGES, int DU, bool UNIT, bool ROW = false>
+__device__ __forceinline__ void run_segment_rp(double (&acc)[17][2], double& racc, gk::Smem<KT, STAGES, ROW>& sm, int& it,
                                                int nst, int g, int kq, int rm, int rhalf, int lane) {
     using namespace gk;
     for (int i = 0; i < nst; ++i, ++it) {
         const int stg = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(smem_u32(&sm.full[stg]), ph);
-        const Stage<KT, false>& S = sm.st[stg];
-        consume_stage_rp<W, KT, DU, UNIT>(acc, S, g, kq);
+        const Stage<KT, ROW>& S = sm.st[stg];
+        consume_stage_rp<W, KT, DU, UNIT, ROW>(acc, S, g, kq);
 #pragma unroll
         for (int k = 0; k < KT / 2; ++k) {  // r block of this row panel: r[m] += Σ_k X[m,k] t_k
             const int kl = rhalf * (KT / 2) + k;
-            racc = fma(S.a[kl * LDT + rm], S.t[kl], racc);
+            racc = fma(S.a[kl * Stage<KT, ROW>::SK + rm * Stage<KT, ROW>::SM], S.t[kl], racc);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&sm.empty[stg]));
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(ROW ? gk::THREADS_ROW : gk::THREADS, 1) gram_t
     __syncthreads();
 
     if (warp >= CONSUMER_WARPS) {
-        if constexpr (CS) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");  // hand registers to the consumer warpgroups
+        if constexpr (CS || ROW) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");  // hand registers to the consumer warpgroups
         // ------------------------------------------------------------ producer warps (TMA): 0 -> panel I + s, 1 -> panel J + t
         // (feature-major: warps 0, 1 -> halves of panel I, warps 2, 3 -> halves of panel J)
         const int pwr = warp - CONSUMER_WARPS;
@@ -577,6 +578,10 @@ __global__ void __launch_bounds__(ROW ? gk::THREADS_ROW : gk::THREADS, 1) gram_t
     }
     // off-diagonal tiles: warp -> (wm, wn) row-major.  Diagonal tiles: remapped so that the surviving sub-tile counts
     // {26, 10, 0, 0, 32, 32, 26, 10} pair up evenly over the four SM sub-partitions (warp % 4): 32, 32, 36, 36.
+    // The feature-major instantiation (ROW) takes the producers' registers and runs diagonal tiles as row pairs
+    // (consume_stage_rp) like the hybrid kernel; its off-diagonal tiles stay 2 x 4.
+    constexpr bool RPD = ROW;
+    if constexpr (RPD) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int wm_off = warp >> 2, wn_off = warp & 3;
     const int dmap = (0x7132'6054 >> (4 * warp)) & 0xf;  // warp 0..7 -> (1,0) (1,1) (0,0) (1,2) (0,2) (0,3) (0,1) (1,3)
     const int wm_dg = dmap >> 2, wn_dg = dmap & 3;
@@ -585,6 +590,7 @@ __global__ void __launch_bounds__(ROW ? gk::THREADS_ROW : gk::THREADS, 1) gram_t
     // switches tiles parks the partial tile in its workspace slot at every switch (first period: store, later: add).
     const bool single = (seg_end - seg_begin) == 1;
     double acc[8][4][2];
+    auto& acc_rp = reinterpret_cast<double (&)[17][2]>(acc);  // RPD: diagonal tiles use the first 34 of the 64 accumulators
 #pragma unroll
     for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
@@ -593,6 +599,16 @@ __global__ void __launch_bounds__(ROW ? gk::THREADS_ROW : gk::THREADS, 1) gram_t
 
     auto flush = [&](int sg, bool diag, int wm, int wn, int thr, bool add) {
         double* Pt = p.P + (int64_t)sg * (TM * TM);
+        if (RPD && diag) {
+            if (warp == 0) flush_rp<0>(acc_rp, Pt, g, kq, add);
+            else if (warp == 1) flush_rp<1>(acc_rp, Pt, g, kq, add);
+            else if (warp == 2) flush_rp<2>(acc_rp, Pt, g, kq, add);
+            else if (warp == 3) flush_rp<3>(acc_rp, Pt, g, kq, add);
+            else if (warp == 4) flush_rp<4>(acc_rp, Pt, g, kq, add);
+            else if (warp == 5) flush_rp<5>(acc_rp, Pt, g, kq, add);
+            else if (warp == 6) flush_rp<6>(acc_rp, Pt, g, kq, add);
+            else flush_rp<7>(acc_rp, Pt, g, kq, add);
+        } else
 #pragma unroll
         for (int mi = 0; mi < 8; ++mi) {
             const int row = wm * 64 + mi * 8 + g;
@@ -634,7 +650,16 @@ __global__ void __launch_bounds__(ROW ? gk::THREADS_ROW : gk::THREADS, 1) gram_t
 
             // warp-uniform dispatch to a fully unrolled, unpredicated instruction stream
             if (!diag) run_segment<0, KT, STAGES, ROW>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
-            else if (thr <= -3) run_segment<1, KT, STAGES, ROW>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
+            else if (RPD) {
+                if (warp == 0) run_segment_rp<0, KT, STAGES, 4, false, ROW>(acc_rp, racc, sm, it, nst, g, kq, rm, rhalf, lane);
+                else if (warp == 1) run_segment_rp<1, KT, STAGES, 4, false, ROW>(acc_rp, racc, sm, it, nst, g, kq, rm, rhalf, lane);
+                else if (warp == 2) run_segment_rp<2, KT, STAGES, 4, false, ROW>(acc_rp, racc, sm, it, nst, g, kq, rm, rhalf, lane);
+                else if (warp == 3) run_segment_rp<3, KT, STAGES, 4, false, ROW>(acc_rp, racc, sm, it, nst, g, kq, rm, rhalf, lane);
+                else if (warp == 4) run_segment_rp<4, KT, STAGES, 4, false, ROW>(acc_rp, racc, sm, it, nst, g, kq, rm, rhalf, lane);
+                else if (warp == 5) run_segment_rp<5, KT, STAGES, 4, false, ROW>(acc_rp, racc, sm, it, nst, g, kq, rm, rhalf, lane);
+                else if (warp == 6) run_segment_rp<6, KT, STAGES, 4, false, ROW>(acc_rp, racc, sm, it, nst, g, kq, rm, rhalf, lane);
+                else run_segment_rp<7, KT, STAGES, 4, false, ROW>(acc_rp, racc, sm, it, nst, g, kq, rm, rhalf, lane);
+            } else if (thr <= -3) run_segment<1, KT, STAGES, ROW>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
             else if (thr == 0) run_segment<2, KT, STAGES, ROW>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
             else if (thr == 4) run_segment<3, KT, STAGES, ROW>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
             else run_segment<4, KT, STAGES, ROW>(acc, racc, sm, it, nst, wm, wn, g, kq, rm, rhalf, lane);
@@ -1020,7 +1045,7 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
         const int64_t flush_cost = NP > 1 ? gk::W_OFF / 2 : 0;  // ~half a stage per tile switch
         const bool hybrid = KT == 32 && ctx->gram_cs && !row_native;
         const bool unit = hybrid && sigma2 == nullptr && ctx->gram_unit;  // Σy = σ² I
-        const int diag_weight = ctx->diag_weight > 0 ? ctx->diag_weight : (hybrid ? 38 : 40);
+        const int diag_weight = ctx->diag_weight > 0 ? ctx->diag_weight : ((hybrid || row_native) ? 38 : 40);
         if (ctx->sched_key[0] != nt || ctx->sched_key[1] != PS || ctx->sched_key[2] != G ||
             ctx->sched_key[3] != diag_weight * 1000 + flush_cost) {
             Schedule sc;
