@@ -18,9 +18,12 @@ def exe(tmp_path_factory):
 
 
 @pytest.mark.parametrize("nt,n_stages,G,wd", [
-    (8, 1 << 20, 148, 40),   # cfg3: D=1024, N=2^24
-    (2, 65536, 148, 40),     # cfg2: D=256, N=2^20
-    (32, 262144, 148, 36),   # cfg5: D=4096, N=2^22
+    (8, 1 << 19, 148, 38),   # cfg3: D=1024, N=2^24 in 32-observation stages, hybrid tiling's diagonal weight
+    (8, 1 << 20, 148, 40),   # same in 16-observation stages with the 2x4 tiling's weight
+    (2, 32768, 148, 38),     # cfg2: D=256, N=2^20
+    (2, 65536, 148, 40),
+    (32, 131072, 148, 38),   # cfg5: D=4096, N=2^22
+    (32, 262144, 148, 36),
     (1, 1, 148, 40), (1, 7, 148, 40), (3, 5, 148, 64), (2, 1000, 1, 40), (5, 999, 7, 50), (8, 131072, 132, 44),
 ])
 def test_schedule_properties(exe, nt, n_stages, G, wd):
