@@ -61,6 +61,23 @@ def test_no_cpu_fallback_without_gpu():
         blr.logpdf(f(blr.ColVecs(np.ones((2, 3))), 0.1), np.zeros(3))
 
 
+def test_plain_c_client_compiles_links_and_fails_loudly(lib, tmp_path):
+    """include/blr_cuda.h is a C header (not just C++): examples/minimal_client.c builds as C99 against the library.
+    Without a GPU it must stop at blr_ctx_create with the no-fallback message (exit code 2)."""
+    import torch
+
+    exe = tmp_path / "minimal_client"
+    libdir = os.path.dirname(L.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "minimal_client.c"), "-L", libdir, "-lblr_cuda", f"-Wl,-rpath,{libdir}",
+                    "-o", str(exe)], check=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert res.returncode == 0, res.stderr
+    else:
+        assert res.returncode == 2 and "no CPU fallback" in res.stderr
+
+
 def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "bayesianlinearregressors.jl_b200")
     for dirpath, _, files in os.walk(pkg):
