@@ -27,7 +27,7 @@ c_void_pp = C.POINTER(C.c_void_p)
 
 
 class Prior(C.Structure):
-    _fields_ = [("mw", c_double_p), ("lambda_kind", C.c_int), ("lambda_", c_double_p), ("ld", C.c_int64)]
+    _fields_ = [("mw", c_double_p), ("lambda_kind", C.c_int), ("lambda_", c_double_p), ("ld", C.c_int64), ("D", C.c_int64)]
 
 
 class Noise(C.Structure):
@@ -42,6 +42,8 @@ SIGNATURES = {
     "blr_last_error": (C.c_char_p, [C.c_void_p]),
     "blr_ctx_sync": (C.c_int, [C.c_void_p]),
     "blr_ctx_stream": (C.c_int, [C.c_void_p, c_void_pp]),
+    "blr_ctx_wait_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "blr_stream_wait_ctx": (C.c_int, [C.c_void_p, C.c_void_p]),
     "blr_launch_count": (C.c_int64, [C.c_void_p]),
     "blr_last_timings": (C.c_int, [C.c_void_p, c_double_p]),
     "blr_host_alloc": (C.c_int, [C.c_void_p, C.c_int64, c_void_pp]),

@@ -54,6 +54,7 @@ struct NcclApi {
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t*) = nullptr;  // optional
     std::string why;
 };
 static NcclApi* nccl_api() {
@@ -77,6 +78,7 @@ static NcclApi* nccl_api() {
     api.GroupEnd = (decltype(api.GroupEnd))dlsym(api.handle, "ncclGroupEnd");
     api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
     api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+    api.CommGetAsyncError = (decltype(api.CommGetAsyncError))dlsym(api.handle, "ncclCommGetAsyncError");
     if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.GetErrorString) {
         api.why = "libnccl is missing required symbols";
         api.handle = nullptr;
@@ -88,12 +90,30 @@ static int nccl_fail(blr_ctx* ctx, ncclResult_t r, const char* what) {
     return set_err(ctx, BLR_E_NCCL, std::string(what) + ": " + (a->GetErrorString ? a->GetErrorString(r) : "?"));
 }
 
-static int noise_args(blr_ctx* ctx, const blr_noise* noise, int64_t N, const double** vec, double* scalar) {
+// require_pd: the caller factorises Σy (`_cholesky(fx.Σy)`, src/bayesian_linear_regression.jl:52,:79), so a non-positive
+// variance is a PosDefException.  Scalar noise is checked here (info = 1: Diagonal(Fill(σ², N)) fails at its first entry);
+// a vector is checked on the device (Σ log σ² is not finite / check_noise_vector).  mean / var / cov only add diag(Σy) (:37,:42).
+// a communicator that hit an asynchronous error (peer died, NVLink fault) reports it here, not through the enqueue call
+int nccl_async_check(blr_ctx* ctx) {
+    NcclApi* a = nccl_api();
+    if (!ctx->nccl_comm || !a->CommGetAsyncError) return 0;
+    ncclResult_t st = ncclSuccess;
+    const ncclResult_t r = a->CommGetAsyncError((ncclComm_t)ctx->nccl_comm, &st);
+    if (r != ncclSuccess) return nccl_fail(ctx, r, "ncclCommGetAsyncError");
+    if (st != ncclSuccess && st != ncclInProgress) return nccl_fail(ctx, st, "NCCL asynchronous error");
+    return 0;
+}
+
+static int noise_args(blr_ctx* ctx, const blr_noise* noise, int64_t N, const double** vec, double* scalar, bool require_pd = false) {
     if (!noise) return set_err(ctx, BLR_E_INVALID, "noise is NULL");
     *vec = nullptr;
     *scalar = 0.0;
     if (noise->kind == BLR_NOISE_SCALAR) {
         *scalar = noise->scalar;
+        if (require_pd && N > 0 && !(noise->scalar > 0.0)) {
+            set_err(ctx, 1, "observation noise variance is not positive");
+            return 1;
+        }
         return 0;
     }
     if (noise->kind == BLR_NOISE_VECTOR) {
@@ -103,6 +123,29 @@ static int noise_args(blr_ctx* ctx, const blr_noise* noise, int64_t N, const dou
         return 0;
     }
     return set_err(ctx, BLR_E_INVALID, "unknown noise kind");
+}
+
+// first index (1-based) with a non-positive (or NaN) variance, or INT_MAX-ish if none: *info = min(*info, n + 1)
+__global__ void check_noise_kernel(const double* __restrict__ v, int64_t N, int* __restrict__ info) {
+    int bad = 0x7fffffff;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x)
+        if (!(v[n] > 0.0)) bad = min(bad, (int)(n + 1 < 0x7ffffffe ? n + 1 : 0x7ffffffe));
+    if (bad != 0x7fffffff) atomicMin(info, bad);
+}
+// Synchronising check (error paths and rand): returns 0 or the PosDefException info of Diagonal(v).
+int check_noise_vector(blr_ctx* ctx, const double* v, int64_t N) {
+    if (!v || N == 0) return 0;
+    int* slot = ctx->d_info + 1;
+    const int big = 0x7fffffff;
+    BLR_CUDA_OK(ctx, cudaMemcpyAsync(slot, &big, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    check_noise_kernel<<<(int)std::min<int64_t>((N + 255) / 256, ctx->sm_count * 8), 256, 0, ctx->stream>>>(v, N, slot);
+    ctx->launches++;
+    int info = 0;
+    BLR_CUDA_OK(ctx, cudaMemcpyAsync(&info, slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    BLR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (info == big) return 0;
+    set_err(ctx, info, "observation noise variance is not positive");
+    return info;
 }
 
 // ---------------------------------------------------------------------------------------------- dense Σy side path
@@ -154,11 +197,7 @@ static int dense_noise_prepare(blr_ctx* ctx, const blr_noise* noise, int64_t N, 
     int rc = potrf_lower(ctx, dn->L, N, ctx->d_info);
     if (rc == 0) rc = logdet_from_chol(ctx, dn->L, N, dn->scal);
     int info = 0;
-    if (rc == 0) {
-        e = cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, sm);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(sm);
-        if (e != cudaSuccess) rc = cuda_fail(ctx, e, "read info");
-    }
+    if (rc == 0) rc = read_info(ctx, &info);
     if (rc == 0 && info != 0) rc = info;
     if (rc != 0) dense_noise_release(ctx, dn);
     return rc;
@@ -205,14 +244,15 @@ int blr_ctx_create(blr_ctx** out, int device) {
     }
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->small, (size_t)SMALL_TOTAL * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_info, sizeof(int));
-    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_res, (size_t)(SMALL_VEC + 2) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_info, 8 * sizeof(int));  // [0] Cholesky info, [1] noise flag, [3] watchdog; [4..7] same for the prior's factor
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_res, (size_t)(SMALL_VEC + 8) * sizeof(double));
     // copy stream + hand-over events: host-streaming accumulation and the overlapped precision download
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming);
     }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_xstream, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_flags, 512 * sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(ctx->d_flags, 0, 512 * sizeof(int));
     if (e != cudaSuccess || ctx->sm_count * 16 > SMALL_SC) {
@@ -229,6 +269,7 @@ int blr_ctx_create(blr_ctx** out, int device) {
         if (atoi(k) == 16) ctx->gram_kt = 16;
         if (atoi(k) == 32) ctx->gram_kt = 32;
     }
+    if (const char* v = getenv("BLR_DXD")) ctx->dxd_legacy = (strcmp(v, "legacy") == 0) ? 1 : 0;
     if (const char* v = getenv("BLR_GRAM_UNIT")) ctx->gram_unit = atoi(v) != 0 ? 1 : 0;
     if (const char* v = getenv("BLR_GRAM_CS")) ctx->gram_cs = atoi(v) != 0 ? 1 : 0;
     if (const char* v = getenv("BLR_VAR_CFG")) ctx->var_cfg = atoi(v) == 0 ? 0 : 1;
@@ -252,6 +293,7 @@ int blr_ctx_destroy(blr_ctx* ctx) {
     cudaFree(ctx->d_info);
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
     cudaFree(ctx->d_flags);
+    cudaFree(ctx->tflags);
     cudaFree(ctx->sched);
     cudaFree(ctx->stage[0]);
     cudaFree(ctx->stage[1]);
@@ -259,6 +301,7 @@ int blr_ctx_destroy(blr_ctx* ctx) {
         if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
         if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]);
     }
+    if (ctx->ev_xstream) cudaEventDestroy(ctx->ev_xstream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < 8; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -277,6 +320,22 @@ int blr_ctx_sync(blr_ctx* ctx) {
 int blr_ctx_stream(blr_ctx* ctx, void** stream_out) {
     if (!ctx || !stream_out) return BLR_E_INVALID;
     *stream_out = (void*)ctx->stream;
+    return 0;
+}
+// Order this context's stream after everything already enqueued on `producer` (a cudaStream_t of the same device; NULL = the
+// legacy default stream): borrowed device buffers (blr_x_wrap_device / blr_vec_wrap_device) written by another stream.
+int blr_ctx_wait_stream(blr_ctx* ctx, void* producer) {
+    CTX_ENTER(ctx);
+    BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev_xstream, (cudaStream_t)producer));
+    BLR_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_xstream, 0));
+    return 0;
+}
+// The other direction: make `consumer` wait for everything enqueued on this context's stream (results written into borrowed
+// device buffers by the *_dev entry points).
+int blr_stream_wait_ctx(blr_ctx* ctx, void* consumer) {
+    CTX_ENTER(ctx);
+    BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev_xstream, ctx->stream));
+    BLR_CUDA_OK(ctx, cudaStreamWaitEvent((cudaStream_t)consumer, ctx->ev_xstream, 0));
     return 0;
 }
 int64_t blr_launch_count(const blr_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -389,6 +448,7 @@ int blr_stats_allreduce_all(blr_ctx** ctxs, blr_stats** stats, int n) {
     const ncclResult_t re = a->GroupEnd();
     if (r == ncclSuccess) r = re;
     if (r != ncclSuccess) return nccl_fail(ctxs[0], r, "ncclAllReduce (group)");
+    for (int i = 0; i < n; ++i) BLR_TRY(nccl_async_check(ctxs[i]));
     return 0;
 }
 int blr_comm_destroy(blr_ctx* ctx) {
@@ -677,7 +737,7 @@ int blr_stats_accumulate(blr_ctx* ctx, blr_stats* s, const double* mw_host, cons
     }
     const double* sig = nullptr;
     double sig_scalar = 0.0;
-    BLR_TRY(noise_args(ctx, noise, x->N, &sig, &sig_scalar));
+    BLR_TRY(noise_args(ctx, noise, x->N, &sig, &sig_scalar, true));
     bool zero = true;
     for (int64_t i = 0; i < s->D; ++i)
         if (mw_host[i] != 0.0) {
@@ -700,6 +760,10 @@ int blr_stats_accumulate_host(blr_ctx* ctx, blr_stats* s, const double* mw_host,
     if (noise_kind != BLR_NOISE_SCALAR && noise_kind != BLR_NOISE_VECTOR) return set_err(ctx, BLR_E_INVALID, "unknown noise kind");
     if (noise_kind == BLR_NOISE_VECTOR && N > 0 && !sigma2_host) return set_err(ctx, BLR_E_INVALID, "sigma2_host is NULL");
     if (N == 0) return 0;
+    if (noise_kind == BLR_NOISE_SCALAR && !(noise_scalar > 0.0)) {  // cholesky(Diagonal(Fill(σ², N))) fails at entry 1
+        set_err(ctx, 1, "observation noise variance is not positive");
+        return 1;
+    }
     if (chunk <= 0) chunk = 1 << 16;
     chunk = std::min<int64_t>((chunk + 15) / 16 * 16, (N + 15) / 16 * 16);
     // staging slot: X chunk (D x chunk, ld = D rounded to even; or chunk x D) | y chunk | σ² chunk
@@ -716,6 +780,7 @@ int blr_stats_accumulate_host(blr_ctx* ctx, blr_stats* s, const double* mw_host,
         ctx->stage_bytes = 0;
         for (int i = 0; i < 2; ++i) BLR_CUDA_OK(ctx, cudaMalloc(&ctx->stage[i], slot_bytes));
         ctx->stage_bytes = slot_bytes;
+        ctx->stage_used[0] = ctx->stage_used[1] = false;
     }
     bool zero = true;
     for (int64_t i = 0; i < D; ++i)
@@ -733,7 +798,9 @@ int blr_stats_accumulate_host(blr_ctx* ctx, blr_stats* s, const double* mw_host,
         double* xs = ctx->stage[b];
         double* ys = xs + x_elems;
         double* ss = ys + chunk;
-        if (it >= 2) BLR_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[b], 0));
+        // the slot may still be read by a Gram kernel of THIS call (it >= 2) or of a previous call on this context (the
+        // function returns without synchronising): always order the copy after the slot's last consumer
+        if (ctx->stage_used[b]) BLR_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[b], 0));
         if (layout == BLR_COLVECS && ld == D && ldx == D)  // contiguous block of columns: one linear copy
             BLR_CUDA_OK(ctx, cudaMemcpyAsync(xs, X + a * ld, (size_t)D * nb * sizeof(double), cudaMemcpyHostToDevice,
                                              ctx->copy_stream));
@@ -759,6 +826,7 @@ int blr_stats_accumulate_host(blr_ctx* ctx, blr_stats* s, const double* mw_host,
         xv.layout = layout;
         BLR_TRY(gram_accumulate(ctx, s, mwd, zero, &xv, ys, noise_kind == BLR_NOISE_VECTOR ? ss : nullptr, noise_scalar));
         BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev_consumed[b], ctx->stream));
+        ctx->stage_used[b] = true;
     }
     return 0;
 }
@@ -771,7 +839,7 @@ int blr_stats_allreduce(blr_ctx* ctx, blr_stats* s) {
     ncclResult_t r =
         a->AllReduce(s->p, s->p, (size_t)s->len(), ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream);
     if (r != ncclSuccess) return nccl_fail(ctx, r, "ncclAllReduce");
-    return 0;
+    return nccl_async_check(ctx);
 }
 int blr_stats_device_ptr(blr_ctx* ctx, const blr_stats* s, double** dev_out, int64_t* len_out) {
     if (!ctx || !s) return BLR_E_INVALID;
@@ -798,19 +866,38 @@ int blr_infer_from_stats(blr_ctx* ctx, const blr_prior* prior, const blr_stats* 
                          double* T_post, double* L_post, blr_post** post_out) {
     CTX_ENTER(ctx);
     if (!prior || !s || !prior->mw || !prior->lambda) return set_err(ctx, BLR_E_INVALID, "null argument");
-    return infer_solve(ctx, prior, s, logpdf_out, m_post, T_post, L_post, post_out);
+    if (prior->D > 0 && prior->D != s->D) return set_err(ctx, BLR_E_DIM, "length(mw) != dimension of the statistics");
+    const int rc = infer_solve(ctx, prior, s, logpdf_out, m_post, T_post, L_post, post_out);
+    if (rc == BLR_INFO_NOISE) {  // which entry is not known from the statistics alone: report the first
+        set_err(ctx, 1, "observation noise variance is not positive");
+        return 1;
+    }
+    return rc;
 }
 
 int blr_infer(blr_ctx* ctx, const blr_prior* prior, const blr_x* x, const blr_vec* y, const blr_noise* noise,
               double* logpdf_out, double* m_post, double* T_post, double* L_post, blr_post** post_out) {
     CTX_ENTER(ctx);
     if (!prior || !x) return set_err(ctx, BLR_E_INVALID, "null argument");
+    if (prior->D > 0 && prior->D != x->D) return set_err(ctx, BLR_E_DIM, "size(X, 1) != length(mw)");
     blr_stats* s = nullptr;
     BLR_TRY(blr_stats_create(ctx, x->D, &s));
     int rc = blr_stats_accumulate(ctx, s, prior->mw, x, y, noise);
     if (rc == 0) rc = blr_stats_allreduce(ctx, s);
-    if (rc == 0) rc = blr_infer_from_stats(ctx, prior, s, logpdf_out, m_post, T_post, L_post, post_out);
+    if (rc == 0 && (!prior->mw || !prior->lambda)) rc = set_err(ctx, BLR_E_INVALID, "null argument");
+    if (rc == 0) rc = infer_solve(ctx, prior, s, logpdf_out, m_post, T_post, L_post, post_out);
     blr_stats_free(ctx, s);
+    if (rc == BLR_INFO_NOISE) {
+        // Σ log σ² was not finite: some variance is <= 0 (or NaN).  Report Diagonal(σ²)'s PosDefException index when this
+        // rank holds the offending entry (another rank's shard may hold it: then the index is not known here).
+        int info = 1;
+        if (noise && noise->kind == BLR_NOISE_VECTOR && noise->vec) {
+            const int loc = check_noise_vector(ctx, noise->vec->p, noise->vec->n);
+            if (loc != 0) info = loc;
+        }
+        set_err(ctx, info, "observation noise variance is not positive");
+        return info;
+    }
     return rc;
 }
 
@@ -819,6 +906,7 @@ int blr_post_create(blr_ctx* ctx, const blr_prior* prior, int64_t D, blr_post** 
     CTX_ENTER(ctx);
     if (!prior || !out || !prior->mw || !prior->lambda || D < 1 || D > SMALL_VEC)
         return set_err(ctx, BLR_E_INVALID, "bad prior");
+    if (prior->D > 0 && prior->D != D) return set_err(ctx, BLR_E_DIM, "length(mw) != D");
     return post_from_prior(ctx, prior, D, out);
 }
 int blr_post_free(blr_ctx* ctx, blr_post* p) {
@@ -944,10 +1032,12 @@ int blr_rand_finite_dev(blr_ctx* ctx, blr_post* p, const blr_x* x, const blr_noi
     double sig_scalar = 0.0;
     DenseNoise dn;
     const bool dense = noise && noise->kind == BLR_NOISE_DENSE;
-    if (dense)
+    if (dense) {
         BLR_TRY(dense_noise_prepare(ctx, noise, x->N, &dn));
-    else
-        BLR_TRY(noise_args(ctx, noise, x->N, &sig, &sig_scalar));
+    } else {
+        BLR_TRY(noise_args(ctx, noise, x->N, &sig, &sig_scalar, true));
+        BLR_TRY(check_noise_vector(ctx, sig, x->N));  // `_cholesky(fx.Σy)` (:52): PosDefException for a non-positive variance
+    }
     double* buf = nullptr;
     BLR_CUDA_OK(ctx, dev_alloc(ctx, &buf, (size_t)2 * (D + 1) * S * sizeof(double)));
     double *Zd = buf, *Wd = buf + (D + 1) * S;

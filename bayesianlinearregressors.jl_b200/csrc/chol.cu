@@ -13,98 +13,11 @@
 #include <vector>
 
 #include "blockgemm.cuh"
+#include "cholblock.cuh"
 #include "common.cuh"
 #include "internal.h"
 
 namespace blr {
-
-constexpr int NB = 64;  // block size of the D x D phase
-
-// ---------------------------------------------------------------------------------------------
-// Factor a 64 x 64 diagonal block held in shared memory, in place: Ls[c * LDL + r] = element (r, c) for r >= c (the
-// strict upper part is never read or written).  The sequential pivot chain is what bounds this phase (D dependent
-// column steps for the whole matrix), so it is kept in registers: the block is processed as four 16-column strips;
-//   1. warp 0 factors the strip's 16 x 16 diagonal sub-block with lane r holding row r (16 registers); pivots and
-//      scaled columns travel by warp shuffle, 1/sqrt comes from rsqrt + one Newton step for the diagonal itself --
-//      one column step is a shuffle, an rsqrt and a multiply deep, no barrier, no shared-memory round trip;
-//   2. one thread per row below solves its 16 entries of the strip against that sub-block (registers);
-//   3. all 256 threads apply the rank-16 update to the rest of the block.
-// On return L[r][c] = Ls[c * LDL + r] for r >= c and rdiag[k] = 1 / L[k][k].  Blocks smaller than 64 are padded
-// with the identity by the caller.  Returns (to all threads) the 1-based index of the first non-positive pivot, or 0.
-constexpr int PANEL_THREADS = 256;
-constexpr int LDL = NB + 2;  // even stride: 16-byte aligned column starts, conflict-free for consecutive rows
-constexpr int SB = 16;       // strip width
-__device__ int factor_block_smem(double* Ls, double* rdiag) {
-    __shared__ int fail;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) fail = 0;
-    __syncthreads();
-#pragma unroll 1
-    for (int k0 = 0; k0 < NB; k0 += SB) {
-        if (warp == 0) {
-            const int r = lane & (SB - 1);  // lanes 16..31 mirror lanes 0..15 so that every shuffle is full-warp
-            double a[SB];
-#pragma unroll
-            for (int c = 0; c < SB; ++c) a[c] = (c <= r) ? Ls[(k0 + c) * LDL + k0 + r] : 0.0;
-            int bad = 0;
-#pragma unroll
-            for (int k = 0; k < SB; ++k) {
-                const double akk = __shfl_sync(0xffffffffu, a[k], k);
-                const double rd = rsqrt(akk);
-                double d = akk * rd;
-                d = fma(fma(-d, d, akk), 0.5 * rd, d);  // sqrt(akk) to the last bit or two
-                if (!(akk > 0.0) && bad == 0) bad = k0 + k + 1;
-                a[k] = (r == k) ? d : a[k] * rd;        // rows r > k: L[r][k]; rows r < k hold zeros
-                if (lane == k) rdiag[k0 + k] = rd;
-#pragma unroll
-                for (int c = k + 1; c < SB; ++c) {
-                    const double lck = __shfl_sync(0xffffffffu, a[k], c);  // L[c][k]
-                    a[c] = fma(-a[k], lck, a[c]);
-                }
-            }
-            if (lane < SB) {
-#pragma unroll
-                for (int c = 0; c < SB; ++c)
-                    if (c <= r) Ls[(k0 + c) * LDL + k0 + r] = a[c];
-            }
-            if (lane == 0 && bad != 0 && fail == 0) fail = bad;
-        }
-        __syncthreads();
-        const int below = NB - k0 - SB;  // rows of the block under this strip's diagonal sub-block
-        if (below > 0) {
-            if (tid < below) {
-                const int row = k0 + SB + tid;
-                double a[SB];
-#pragma unroll
-                for (int c = 0; c < SB; ++c) a[c] = Ls[(k0 + c) * LDL + row];
-#pragma unroll
-                for (int k = 0; k < SB; ++k) {
-                    const double xk = a[k] * rdiag[k0 + k];
-                    a[k] = xk;
-#pragma unroll
-                    for (int c = k + 1; c < SB; ++c) a[c] = fma(-xk, Ls[(k0 + k) * LDL + k0 + c], a[c]);
-                }
-#pragma unroll
-                for (int c = 0; c < SB; ++c) Ls[(k0 + c) * LDL + row] = a[c];
-            }
-            __syncthreads();
-            const int i = tid & (NB - 1), ty = tid >> 6;
-            if (i >= k0 + SB) {
-                double li[SB];
-#pragma unroll
-                for (int k = 0; k < SB; ++k) li[k] = Ls[(k0 + k) * LDL + i];
-                for (int j = k0 + SB + ty; j <= i; j += PANEL_THREADS / NB) {
-                    double dot = 0.0;
-#pragma unroll
-                    for (int k = 0; k < SB; ++k) dot = fma(li[k], Ls[(k0 + k) * LDL + j], dot);
-                    Ls[j * LDL + i] -= dot;
-                }
-            }
-            __syncthreads();
-        }
-    }
-    return fail;
-}
 
 // Panel step j of the right-looking Cholesky: every CTA factors the diagonal block A[j0:j0+64, j0:j0+64]
 // redundantly in shared memory (saves a launch + a dependency), CTA 0 writes it back, and each CTA solves
@@ -176,10 +89,12 @@ __global__ void zero_strict_upper_kernel(double* __restrict__ A, int64_t ld, int
     }
 }
 
+// info_dev: 4 device ints ([0] = LAPACK-style info; [3] = watchdog flag of the fused kernel).
 int potrf_lower(blr_ctx* ctx, double* A, int64_t D64, int* info_dev) {
+    if (!ctx->dxd_legacy) return dxd_fused(ctx, A, D64, info_dev, nullptr, nullptr, nullptr);  // one cooperative launch
     const int D = (int)D64;
     cudaStream_t sm = ctx->stream;
-    BLR_CUDA_OK(ctx, cudaMemsetAsync(info_dev, 0, sizeof(int), sm));
+    BLR_CUDA_OK(ctx, cudaMemsetAsync(info_dev, 0, 4 * sizeof(int), sm));
     for (int j0 = 0; j0 < D; j0 += NB) {
         const int below = D - j0 - NB;
         const int pgrid = below > 0 ? (below + PANEL_THREADS - 1) / PANEL_THREADS : 1;
@@ -452,13 +367,14 @@ __global__ void __launch_bounds__(256) dot_self_kernel(const double* __restrict_
 }
 __global__ void finalize_kernel(const double* __restrict__ scal /* q, ℓ, n */, const double* __restrict__ sc,
                                 const double* __restrict__ mw, const double* __restrict__ u, int D,
-                                double* __restrict__ m_post, double* __restrict__ logpdf) {
+                                double* __restrict__ m_post, double* __restrict__ logpdf, int* __restrict__ noise_info) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D; i += gridDim.x * blockDim.x) m_post[i] = mw[i] + u[i];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const double LOG2PI = 1.8378770664093454835606594728112;
         const double q = scal[0], l = scal[1], n = scal[2];
         // sc[0] = logdet Λw, sc[1] = logdet Λ', sc[2] = z'z
         logpdf[0] = -0.5 * (n * LOG2PI + l + q + (sc[1] - sc[0]) - sc[2]);
+        if (!isfinite(l)) *noise_info = 1;  // Σ log σ²: some variance is <= 0 or not finite
     }
 }
 
@@ -518,9 +434,12 @@ static int upload_prior_precision(blr_ctx* ctx, const blr_prior* prior, int64_t 
     return set_err(ctx, BLR_E_INVALID, "unknown lambda_kind");
 }
 
-static int read_info(blr_ctx* ctx, int* info_host) {
-    BLR_CUDA_OK(ctx, cudaMemcpyAsync(info_host, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+int read_info(blr_ctx* ctx, int* info_host) {
+    int h[4] = {0, 0, 0, 0};
+    BLR_CUDA_OK(ctx, cudaMemcpyAsync(h, ctx->d_info, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     BLR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h[3] != 0) return set_err(ctx, BLR_E_CUDA, "D x D phase: dependency wait timed out (internal error)");
+    *info_host = h[0];
     return 0;
 }
 
@@ -570,9 +489,12 @@ int infer_solve(blr_ctx* ctx, const blr_prior* prior, const blr_stats* st, doubl
     BLR_TRY(alloc_post(ctx, D, &p));
     // scratch scalars live behind the prep partials in ctx->small
     double* sc = ctx->small + SMALL_SC;    // [0] logdet Λw  [1] logdet Λ'  [2] z'z  [3] logpdf
-    double* rhs = ctx->small + SMALL_RHS;  // D doubles
+    double* rhs = ctx->small + SMALL_RHS;  // D doubles: r in, z = L^-1 r out
+    double* usol = ctx->small + SMALL_U;   // D doubles: u = L^-T z
     double* mwd = ctx->small + SMALL_MW;
-    int rc = 0, info = 0;
+    int* info_post = ctx->d_info;          // [0] info of chol(Λ'), [1] noise flag, [3] watchdog
+    int* info_prior = ctx->d_info + 4;     // same for chol(Λw) of a dense prior
+    int rc = 0;
     double ldh = 0.0;
     bool have = false;
     bool lam_on_copy_stream = false;  // the precision download is in flight on the copy stream
@@ -583,16 +505,16 @@ int infer_solve(blr_ctx* ctx, const blr_prior* prior, const blr_stats* st, doubl
     };
     if (D > SMALL_VEC) return fail(set_err(ctx, BLR_E_INVALID, "D > 16384 not supported"));
 
-    // logdet Λw (and PosDef check of the prior): Diagonal on host, dense via a device Cholesky of a copy in p->L.
+    // logdet Λw (and PosDef check of the prior): Diagonal on host, dense via a device Cholesky of a copy in p->L.  No host
+    // synchronisation here: a failed prior factorisation is reported with the results (one sync per inference).
     rc = upload_prior_precision(ctx, prior, D, p->Lam, &ldh, &have);
     if (rc != 0) return fail(rc);
+    BLR_CUDA_OK(ctx, cudaMemsetAsync(info_prior, 0, 4 * sizeof(int), sm));
     if (!have) {
         BLR_CUDA_OK(ctx, cudaMemcpyAsync(p->L, p->Lam, (size_t)D * D * sizeof(double), cudaMemcpyDeviceToDevice, sm));
-        rc = potrf_lower(ctx, p->L, D, ctx->d_info);
+        rc = potrf_lower(ctx, p->L, D, info_prior);
         if (rc == 0) rc = logdet_from_chol(ctx, p->L, D, sc + 0);
-        if (rc == 0) rc = read_info(ctx, &info);
         if (rc != 0) return fail(rc);
-        if (info != 0) return fail(info);
     } else {
         BLR_CUDA_OK(ctx, cudaMemcpyAsync(sc + 0, &ldh, sizeof(double), cudaMemcpyHostToDevice, sm));
     }
@@ -613,36 +535,46 @@ int infer_solve(blr_ctx* ctx, const blr_prior* prior, const blr_stats* st, doubl
         BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[7], ctx->copy_stream));
         lam_on_copy_stream = true;
     }
-    rc = potrf_lower(ctx, p->L, D, ctx->d_info);
-    if (rc != 0) return fail(rc);
-    // z = L'^-1 r ; z'z ; u = L'^-T z ; m' = mw + u
     BLR_CUDA_OK(ctx, cudaMemcpyAsync(rhs, st->r(), (size_t)D * sizeof(double), cudaMemcpyDeviceToDevice, sm));
-    // inverse diagonal blocks for the wavefront solves
-    const int64_t nblk = (D + NB - 1) / NB;
-    rc = ensure_dinv(ctx, (size_t)nblk * NB * NB * sizeof(double));
-    if (rc != 0) return fail(rc);
-    double* Dinv = ctx->dinv;
-    rc = trtri_diag_packed(ctx, p->L, D, Dinv);
-    if (rc == 0) rc = trsv_lower_forward(ctx, p->L, D, Dinv, rhs);
-    if (rc != 0) return fail(rc);
-    dot_self_kernel<<<1, 256, 0, sm>>>(rhs, (int)D, sc + 2);
-    BLR_CHECK_LAUNCH(ctx, "dot_self_kernel");
-    rc = trsv_lower_backward(ctx, p->L, D, Dinv, rhs);
-    if (rc == 0) rc = logdet_from_chol(ctx, p->L, D, sc + 1);
-    if (rc != 0) return fail(rc);
-    finalize_kernel<<<(int)std::min<int64_t>((D + 255) / 256, 64), 256, 0, sm>>>(st->scal(), sc, mwd, rhs, (int)D, p->mw,
-                                                                              sc + 3);
-    BLR_CHECK_LAUNCH(ctx, "finalize_kernel");
+    if (!ctx->dxd_legacy) {
+        // L = chol(Λ'), z = L^-1 r, u = L^-T z, logdet, z'z, m' = mw + u, logpdf: one cooperative launch (chol_tiled.cu)
+        DxdFinalize fin;
+        fin.stat_scal = st->scal();
+        fin.mw = mwd;
+        fin.m_post = p->mw;
+        fin.sc = sc;
+        rc = dxd_fused(ctx, p->L, D, info_post, rhs, usol, &fin);
+        if (rc != 0) return fail(rc);
+    } else {
+        rc = potrf_lower(ctx, p->L, D, info_post);
+        if (rc != 0) return fail(rc);
+        // z = L'^-1 r ; z'z ; u = L'^-T z ; m' = mw + u  (inverse diagonal blocks for the wavefront solves)
+        const int64_t nblk = (D + NB - 1) / NB;
+        rc = ensure_dinv(ctx, (size_t)nblk * NB * NB * sizeof(double));
+        if (rc != 0) return fail(rc);
+        double* Dinv = ctx->dinv;
+        rc = trtri_diag_packed(ctx, p->L, D, Dinv);
+        if (rc == 0) rc = trsv_lower_forward(ctx, p->L, D, Dinv, rhs);
+        if (rc != 0) return fail(rc);
+        dot_self_kernel<<<1, 256, 0, sm>>>(rhs, (int)D, sc + 2);
+        BLR_CHECK_LAUNCH(ctx, "dot_self_kernel");
+        rc = trsv_lower_backward(ctx, p->L, D, Dinv, rhs);
+        if (rc == 0) rc = logdet_from_chol(ctx, p->L, D, sc + 1);
+        if (rc != 0) return fail(rc);
+        finalize_kernel<<<(int)std::min<int64_t>((D + 255) / 256, 64), 256, 0, sm>>>(st->scal(), sc, mwd, rhs, (int)D, p->mw,
+                                                                                  sc + 3, info_post + 1);
+        BLR_CHECK_LAUNCH(ctx, "finalize_kernel");
+    }
     BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[5], sm));
     ctx->ev_valid[3] = true;
 
     // Results: the small ones (pivot status, logpdf, m') go through page-locked staging so that every copy is truly
     // asynchronous and the whole inference costs ONE host synchronisation (a cudaMemcpyAsync into pageable memory
     // blocks the host, i.e. one GPU-idle round trip per output).
-    double* hr = ctx->h_res;
-    BLR_CUDA_OK(ctx, cudaMemcpyAsync(hr, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, sm));
-    if (logpdf_out) BLR_CUDA_OK(ctx, cudaMemcpyAsync(hr + 1, sc + 3, sizeof(double), cudaMemcpyDeviceToHost, sm));
-    if (m_post) BLR_CUDA_OK(ctx, cudaMemcpyAsync(hr + 2, p->mw, (size_t)D * sizeof(double), cudaMemcpyDeviceToHost, sm));
+    double* hr = ctx->h_res;  // [8 ints | logpdf | m']
+    BLR_CUDA_OK(ctx, cudaMemcpyAsync(hr, ctx->d_info, 8 * sizeof(int), cudaMemcpyDeviceToHost, sm));
+    if (logpdf_out) BLR_CUDA_OK(ctx, cudaMemcpyAsync(hr + 4, sc + 3, sizeof(double), cudaMemcpyDeviceToHost, sm));
+    if (m_post) BLR_CUDA_OK(ctx, cudaMemcpyAsync(hr + 5, p->mw, (size_t)D * sizeof(double), cudaMemcpyDeviceToHost, sm));
     if (L_post && !lam_on_copy_stream)
         BLR_CUDA_OK(ctx, cudaMemcpyAsync(L_post, p->Lam, (size_t)n2 * sizeof(double), cudaMemcpyDeviceToHost, sm));
     if (T_post) {
@@ -655,10 +587,14 @@ int infer_solve(blr_ctx* ctx, const blr_prior* prior, const blr_stats* st, doubl
     }
     BLR_CUDA_OK(ctx, cudaStreamSynchronize(sm));
     if (lam_on_copy_stream) BLR_CUDA_OK(ctx, cudaEventSynchronize(ctx->ev[7]));
-    memcpy(&info, hr, sizeof(int));
-    if (info != 0) return fail(info);  // non-positive pivot: the outputs above are not meaningful
-    if (logpdf_out) *logpdf_out = hr[1];
-    if (m_post) memcpy(m_post, hr + 2, (size_t)D * sizeof(double));
+    int hi[8];
+    memcpy(hi, hr, sizeof(hi));
+    if (hi[3] != 0 || hi[7] != 0) return fail(set_err(ctx, BLR_E_CUDA, "D x D phase: dependency wait timed out (internal error)"));
+    if (hi[4] != 0) return fail(hi[4]);          // the prior precision is not positive definite (:78)
+    if (hi[1] != 0) return fail(BLR_INFO_NOISE);  // a non-positive observation-noise variance (:79)
+    if (hi[0] != 0) return fail(hi[0]);          // non-positive pivot: the outputs above are not meaningful
+    if (logpdf_out) *logpdf_out = hr[4];
+    if (m_post) memcpy(m_post, hr + 5, (size_t)D * sizeof(double));
     if (post_out)
         *post_out = p;
     else

@@ -58,6 +58,10 @@ struct blr_ctx {
     double* h_res = nullptr;  // page-locked result staging: [info | logpdf | m_post (SMALL_VEC)] -> one sync per inference
     int* d_flags = nullptr;  // wavefront-solve ready flags (one per 64-row block), compared against flag_epoch
     int flag_epoch = 0;
+    int* tflags = nullptr;   // ready flags of the fused tiled D x D kernel (one per tile + 2 per block row + abort)
+    size_t tflags_n = 0;
+    int dxd_occ = 0;         // resident CTAs per SM of dxd_fused_kernel (occupancy query, cached)
+    int dxd_legacy = 0;      // BLR_DXD=legacy: round-1 multi-launch D x D phase (A/B and fallback for debugging)
     cudaEvent_t ev[8] = {};
     bool ev_valid[4] = {};
     // stream-K schedule of the Gram fast path (cached by shape)
@@ -78,12 +82,17 @@ struct blr_ctx {
     double* stage[2] = {nullptr, nullptr};
     size_t stage_bytes = 0;
     cudaEvent_t ev_copied[2] = {}, ev_consumed[2] = {};
+    bool stage_used[2] = {false, false};  // ev_consumed[b] has been recorded since the slot was (re)allocated
+    cudaEvent_t ev_xstream = nullptr;     // blr_ctx_wait_stream / blr_stream_wait_ctx
     // NCCL (dlopen'ed)
     void* nccl_comm = nullptr;
     int nranks = 1, rank = 0;
 };
 
 namespace blr {
+
+// internal status of infer_solve: Σ log σ² is not finite, i.e. some observation-noise variance is <= 0 (or NaN)
+constexpr int BLR_INFO_NOISE = 0x7ffffff0;
 
 // layout of blr_ctx::small (doubles)
 constexpr int PERIOD_COUNTER_SLOT = 448;  // index into blr_ctx::d_flags (wavefront flags use < 256)
@@ -93,7 +102,8 @@ constexpr int SMALL_VEC = 16384;     // capacity of each D-vector slot (max supp
 constexpr int SMALL_RHS = 8192;
 constexpr int SMALL_MW = SMALL_RHS + SMALL_VEC;
 constexpr int SMALL_DTMP = SMALL_MW + SMALL_VEC;
-constexpr int SMALL_TOTAL = SMALL_DTMP + SMALL_VEC;
+constexpr int SMALL_U = SMALL_DTMP + SMALL_VEC;  // backward-solve output of the fused D x D kernel
+constexpr int SMALL_TOTAL = SMALL_U + SMALL_VEC;
 
 int set_err(blr_ctx* ctx, int code, const std::string& msg);
 int cuda_fail(blr_ctx* ctx, cudaError_t e, const char* what);
@@ -103,6 +113,8 @@ void dev_free(cudaStream_t stream, void* p);
 int ensure_ws(blr_ctx* ctx, size_t bytes);
 int ensure_nbuf(blr_ctx* ctx, size_t bytes);
 int ensure_dinv(blr_ctx* ctx, size_t bytes);
+// 0, or the 1-based index of the first non-positive variance (PosDefException info of Diagonal(v)); synchronises
+int check_noise_vector(blr_ctx* ctx, const double* v, int64_t N);
 
 #define BLR_CUDA_OK(ctx, call)                                           \
     do {                                                                 \
@@ -132,10 +144,25 @@ bool gram_small_fused(int64_t D);
 int gram_small(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double* y, const double* sigma2, double sigma2_scalar,
                const double* mw_dev, bool mw_is_zero, const double* s, const double* t, double* partial, int partial_blocks);
 
+// ---- chol_tiled.cu
+// inputs / outputs of the finalize step of the fused D x D kernel (all device pointers)
+struct DxdFinalize {
+    const double* stat_scal;  // q, ℓ, n of the reduced statistics
+    const double* mw;         // prior mean
+    double* m_post;           // out: mw + u
+    double* sc;               // [0] logdet Λw (in); [1] logdet Λ', [2] z'z, [3] logpdf (out)
+};
+// One cooperative launch: A (lower triangle in) -> Cholesky factor (lower, strict upper zeroed); optionally z = L^-1 z in
+// place, u = L^-T z, and the finalize step.  info_dev: 4 device ints, [0] = LAPACK-style info, [1] = noise flag, [3] = abort.
+int dxd_fused(blr_ctx* ctx, double* A, int64_t D, int* info_dev, double* z, double* u, const DxdFinalize* fin);
+
 // ---- chol.cu
 // In-place lower Cholesky of the column-major D x D matrix A (only the lower triangle is read);
 // strictly-upper part is zeroed.  *info_dev (device int) receives 0 or the 1-based failing order.
 int potrf_lower(blr_ctx* ctx, double* A, int64_t D, int* info_dev);
+// synchronising read of ctx->d_info after potrf_lower(..., ctx->d_info): *info_host = LAPACK-style info; error if the
+// fused kernel's watchdog fired
+int read_info(blr_ctx* ctx, int* info_host);
 // W = inv(L) (lower triangular, column-major), strictly-upper part zeroed.
 int trtri_lower(blr_ctx* ctx, const double* L, double* W, int64_t D);
 // Solve L z = b (forward) then optionally L' u = z (backward); b overwritten.  zz_out (device) = z'z.

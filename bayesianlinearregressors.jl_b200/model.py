@@ -154,7 +154,7 @@ class BayesianLinearRegressor:
             if lam.shape != (D, D):
                 raise L.BLRError(L.E_INVALID, "size(Λw) does not match length(mw)")
             kind, ld = L.LAMBDA_DENSE, D
-        p = L.Prior(mw.ctypes.data_as(L.c_double_p), kind, lam.ctypes.data_as(L.c_double_p), ld)
+        p = L.Prior(mw.ctypes.data_as(L.c_double_p), kind, lam.ctypes.data_as(L.c_double_p), ld, D)
         return p, [mw, lam]
 
     def _device(self, ctx: Context) -> DevicePosterior:
@@ -248,6 +248,8 @@ def _infer(fx: FiniteGP, y, want_logpdf: bool, want_post: bool):
         if hn is not None:  # host data + diagonal noise: stream it (no staging copy of X on the device)
             return _infer_host(ctx, blr, fx.x.X, layout, y, hn, 1 << 16, want_logpdf, want_post)
     X = x_as_colvecs(ctx, fx.x)
+    if X.D != D:  # `X' * mw` (:33) throws DimensionMismatch in the reference; the C ABI checks prior.D as well
+        raise L.DimensionMismatch(L.E_DIM, "size(X, 1) != length(mw)")
     yv = _as_device_vector(ctx, y)
     if yv.n != X.N:  # src/bayesian_linear_regression.jl:74
         raise L.DimensionMismatch(L.E_DIM, "length(y) != size(fx.x.X, 2)")
@@ -335,8 +337,13 @@ def _infer_host(ctx: Context, f: BayesianLinearRegressor, X, layout: int, y, noi
     Λ_post = ctx.empty_pinned((D, D)) if want_post else None
     T_post = ctx.empty_pinned((D, D)) if (want_post and isinstance(f.Λw, PDMat)) else None
     h = C.c_void_p()
-    ctx.check(ctx.lib.blr_infer_from_stats(ctx.handle, C.byref(prior), st.handle, C.byref(lp) if want_logpdf else None,
-                                           _ptr(m_post), _ptr(T_post), _ptr(Λ_post), C.byref(h) if want_post else None))
+    try:
+        ctx.check(ctx.lib.blr_infer_from_stats(ctx.handle, C.byref(prior), st.handle, C.byref(lp) if want_logpdf else None,
+                                               _ptr(m_post), _ptr(T_post), _ptr(Λ_post), C.byref(h) if want_post else None))
+    except L.PosDefException:
+        if s2 is not None and not np.all(s2 > 0):  # cholesky(Diagonal(σ²)) fails at the first non-positive entry (:79)
+            raise L.PosDefException(int(np.argmax(~(s2 > 0))) + 1) from None
+        raise
     post = None
     if want_post:
         post = BayesianLinearRegressor(m_post, _build_Λ(f.Λw, Λ_post, T_post), _post=DevicePosterior(ctx, h, D))

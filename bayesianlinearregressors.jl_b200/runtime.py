@@ -81,6 +81,22 @@ class Context:
         self.check(self.lib.blr_ctx_stream(self.handle, C.byref(s)))
         return int(s.value or 0)
 
+    def wait_torch_stream(self, t=None):
+        """Order this context's (private, non-blocking) stream after the work already enqueued on torch's current stream
+        of this device: borrowed CUDA tensors may still be being written by the caller's kernels."""
+        import torch
+
+        s = torch.cuda.current_stream(t.device if t is not None else self.device)
+        self.check(self.lib.blr_ctx_wait_stream(self.handle, C.c_void_p(s.cuda_stream)))
+
+    def release_to_torch_stream(self, device=None):
+        """The other direction: torch's current stream waits for everything this context has enqueued (results written
+        into borrowed tensors by the *_dev entry points)."""
+        import torch
+
+        s = torch.cuda.current_stream(self.device if device is None else device)
+        self.check(self.lib.blr_stream_wait_ctx(self.handle, C.c_void_p(s.cuda_stream)))
+
     def launch_count(self) -> int:
         return int(self.lib.blr_launch_count(self.handle))
 
@@ -181,6 +197,7 @@ class DeviceMatrix:
             raise L.BLRError(L.E_INVALID, "expected a 2-D float64 CUDA tensor with unit inner stride")
         cols, rows = t.shape
         D, N = (rows, cols) if layout == L.COLVECS else (cols, rows)
+        ctx.wait_torch_stream(t)  # the tensor's producer may still be running on torch's stream
         h = C.c_void_p()
         ctx.check(ctx.lib.blr_x_wrap_device(ctx.handle, C.c_void_p(t.data_ptr()), D, N, max(t.stride(0), 1), layout, C.byref(h)))
         return DeviceMatrix(ctx, h, D, N, layout, keepalive=t)
@@ -223,6 +240,7 @@ class DeviceVector:
     def wrap_torch(ctx: Context, t) -> "DeviceVector":
         if not (t.is_cuda and t.dim() == 1 and t.element_size() == 8 and t.is_contiguous()):
             raise L.BLRError(L.E_INVALID, "expected a contiguous 1-D float64 CUDA tensor")
+        ctx.wait_torch_stream(t)
         h = C.c_void_p()
         ctx.check(ctx.lib.blr_vec_wrap_device(ctx.handle, C.c_void_p(t.data_ptr()), t.shape[0], C.byref(h)))
         return DeviceVector(ctx, h, t.shape[0], keepalive=t)

@@ -41,6 +41,7 @@ int main(void) {
     prior.lambda_kind = BLR_LAMBDA_DIAGONAL;
     prior.lambda = lam_diag;
     prior.ld = D;
+    prior.D = D;
     blr_noise noise;
     noise.kind = BLR_NOISE_SCALAR;
     noise.scalar = 0.1;
@@ -55,12 +56,12 @@ int main(void) {
     CHECK(blr_vec_upload(ctx, y, N, &yv));
     double logpdf, m_post[D], Lambda_post[D * D];
     CHECK(blr_infer(ctx, &prior, x, yv, &noise, &logpdf, m_post, NULL, Lambda_post, &post));
-    printf("logpdf = %.12g\nposterior mean = [%.12g, %.12g]\n", logpdf, m_post[0], m_post[1]);
+    printf("logpdf = %.17g\nposterior mean = [%.17g, %.17g]\n", logpdf, m_post[0], m_post[1]);
 
     double mean[NT], var[NT];
     CHECK(blr_x_upload(ctx, Xt, D, NT, D, BLR_COLVECS, &xt));
     CHECK(blr_mean_var(ctx, post, xt, &noise, mean, var));
-    for (int i = 0; i < NT; ++i) printf("x* = %+.1f: mean %.6f, var %.6f\n", Xt[D * i], mean[i], var[i]);
+    for (int i = 0; i < NT; ++i) printf("x* = %+.1f: mean %.17g, var %.17g\n", Xt[D * i], mean[i], var[i]);
 
     blr_post_free(ctx, post);
     blr_x_free(ctx, xt);

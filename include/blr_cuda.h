@@ -47,6 +47,9 @@ extern "C" {
 /* observation-noise kinds of FiniteGP.Σy */
 #define BLR_NOISE_SCALAR 0 /* Diagonal(Fill(σ², N)) : f(X, 0.1) */
 #define BLR_NOISE_VECTOR 1 /* Diagonal(v)           : f(X, Diagonal(v)) */
+/* Observation-noise variances must be positive wherever the reference factorises Σy (posterior / logpdf :79, rand :52):
+ * a non-positive entry returns info > 0 (-> PosDefException(info), info = its 1-based index when known to this rank,
+ * else 1).  mean / var / cov only add diag(Σy) (:37,:42) and accept anything, as the reference does. */
 #define BLR_NOISE_DENSE 2  /* dense N x N Σy (the reference's test fixtures, test/test_utils.jl:7-8): small-N side path --
                               Σy is factorised on the device and X, y are whitened before the same Gram kernel runs */
 
@@ -61,6 +64,9 @@ typedef struct blr_prior {
     int lambda_kind;      /* BLR_LAMBDA_* */
     const double* lambda; /* host */
     int64_t ld;           /* leading dimension for DENSE (>= D); ignored for DIAGONAL */
+    int64_t D;            /* length(mw) = size(Λw, 1).  Checked against size(X, 1) / the statistics' dimension by every
+                             entry point that takes a prior (BLR_E_DIM on mismatch -- the reference throws
+                             DimensionMismatch from `X' * mw`, src/bayesian_linear_regression.jl:33); 0 = unchecked */
 } blr_prior;
 
 typedef struct blr_noise {
@@ -79,6 +85,13 @@ const char* blr_last_error(const blr_ctx* ctx);
 int blr_ctx_sync(blr_ctx* ctx);
 /* cudaStream_t all kernels of this context are launched on (for CUDA-event timing by the host). */
 int blr_ctx_stream(blr_ctx* ctx, void** stream_out);
+/* Stream ordering for BORROWED device buffers (blr_x_wrap_device / blr_vec_wrap_device, the *_dev outputs): the context
+ * launches on its own non-blocking stream, which does not synchronise with the caller's streams implicitly.
+ *   blr_ctx_wait_stream: everything already enqueued on `producer` (cudaStream_t, NULL = legacy default stream) happens
+ *                        before any later work of this context  (inputs produced by the caller's kernels);
+ *   blr_stream_wait_ctx: everything this context has enqueued happens before later work on `consumer`  (outputs). */
+int blr_ctx_wait_stream(blr_ctx* ctx, void* producer);
+int blr_stream_wait_ctx(blr_ctx* ctx, void* consumer);
 /* number of libblr_cuda kernels launched by this context so far. */
 int64_t blr_launch_count(const blr_ctx* ctx);
 /* Device-event timings (ms) of the last blr_stats_accumulate / blr_infer* call:

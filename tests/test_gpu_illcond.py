@@ -1,0 +1,140 @@
+"""GPU parity under stress (VERDICT r01 "weak" #2, "missing" #2): ill-conditioned prior precisions, low observation noise,
+N < D, and sequential conditioning, at D in {64, 256, 1024} so that every kernel family runs (small-D streaming kernels, the
+TMA Gram / marginals / rand kernels, the tiled D x D phase).
+
+What is asserted.  Once cond * eps approaches 1e-9, two backward-stable Float64 algorithms differ from each other by more
+than 1e-9 and neither is wrong: the reference's own literal op sequence (oracle/blr_oracle.py: whitening by Uw, Cholesky of
+Bt'Bt + I, src/bayesian_linear_regression.jl:72-89) is then itself further than 1e-9 from the mathematical answer.  So every
+quantity is measured against an independent extended-precision evaluation (tests/highprec.py, numpy longdouble, eps 1e-19;
+itself pinned against 50-digit mpmath in tests/test_highprec_pins.py) and the requirement is
+
+        err(GPU, truth)  <=  max(1e-9, SLACK * err(reference op sequence, truth)),      SLACK = 4
+
+i.e. the 1e-9 bar wherever the reference itself meets it, and never (materially) further from the truth than the reference
+where it does not.  The posterior precision (a sum, no cancellation) must meet 1e-12 everywhere.  Observed: the device's
+direct form chol(Λw + G) is at least as accurate as the reference's whitened form in every regime below -- the numbers are
+printed and the study behind the choice is tools/illcond_study.py (output committed under profiles/r02/).
+"""
+import math
+
+import numpy as np
+import pytest
+
+import blr_b200 as blr
+from oracle import blr_oracle as ref
+from tests import highprec as hp
+
+pytestmark = pytest.mark.gpu
+RTOL, SLACK = 1e-9, 4.0
+EPS = np.finfo(np.float64).eps
+
+_CACHE = {}
+
+
+def data(D, N, noise, seed):
+    key = (D, N, noise if np.isscalar(noise) else "het", seed)
+    if key not in _CACHE:
+        rng = np.random.default_rng(seed)
+        X = rng.standard_normal((D, N))
+        σ2 = np.full(N, noise) if np.isscalar(noise) else np.exp(rng.standard_normal(N))
+        y = X.T @ rng.standard_normal(D) + np.sqrt(σ2) * rng.standard_normal(N)
+        mw = rng.standard_normal(D)
+        Q, _ = np.linalg.qr(rng.standard_normal((D, D)))
+        Nt = 96
+        ntr = min(Nt // 2, N)
+        Xt = np.concatenate([X[:, :ntr], rng.standard_normal((D, Nt - ntr))], axis=1)  # training points + fresh points
+        Zw, Zy = rng.standard_normal((D, 3)), rng.standard_normal((Nt, 3))
+        _CACHE[key] = dict(X=X, σ2=σ2, y=y, mw=mw, Q=Q, Xt=Xt, Zw=Zw, Zy=Zy, st=hp.ld_stats(X, y, σ2, mw))
+    return _CACHE[key]
+
+
+def spectrum_prior(Q, lo, hi):
+    lam = np.geomspace(lo, hi, Q.shape[0])
+    Λ = (Q * lam) @ Q.T
+    return (Λ + Λ.T) / 2
+
+
+CASES = [
+    # tag, D, N, (λmin, λmax) of Λw, noise (None = heteroscedastic exp(N(0,1))), noise at the test points
+    ("cond1e6", 64, 500, (1.0, 1e6), None, 0.1),
+    ("cond1e10", 64, 500, (1.0, 1e10), None, 0.1),
+    ("cond1e13", 64, 500, (1.0, 1e13), None, 0.1),
+    ("weak-ill-prior N<D", 64, 40, (1e-8, 1.0), 0.5, 0.5),
+    ("noise1e-8 N<D", 64, 40, (1.0, 10.0), 1e-8, 1e-8),
+    ("low-noise eps()", 64, 100, (1.0, 10.0), EPS, EPS),
+    ("cond1e6", 256, 1500, (1.0, 1e6), None, 0.1),
+    ("cond1e10", 256, 1500, (1.0, 1e10), None, 0.1),
+    ("cond1e13", 256, 1500, (1.0, 1e13), None, 0.1),
+    ("weak-ill-prior N<D", 256, 100, (1e-10, 1.0), 0.5, 0.5),
+    ("low-noise eps()", 256, 300, (1.0, 10.0), EPS, EPS),
+    ("noise1e-6 N<D", 256, 100, (1.0, 10.0), 1e-6, 1e-6),
+    ("cond1e10", 1024, 1100, (1.0, 1e10), None, 0.1),
+    ("low-noise eps()", 1024, 1100, (1.0, 10.0), EPS, EPS),
+]
+
+
+@pytest.mark.parametrize("tag,D,N,lam,noise,noise_t", CASES, ids=[f"{c[0]}-D{c[1]}" for c in CASES])
+def test_ill_conditioned_against_extended_precision(tag, D, N, lam, noise, noise_t):
+    d = data(D, N, noise if noise is not None else np.zeros(1), seed=7 * D + N)
+    X, σ2, y, mw, Xt, Zw, Zy = d["X"], d["σ2"], d["y"], d["mw"], d["Xt"], d["Zw"], d["Zy"]
+    Λ = spectrum_prior(d["Q"], *lam)
+    tr = hp.ld_truth(d["st"], mw, Λ, Xt, noise_t, Zw, Zy)
+
+    # the reference's literal op sequence (oracle) and its distance from the truth
+    fo = ref.BayesianLinearRegressor(mw, Λ)
+    fxo = fo(ref.ColVecs(X), σ2)
+    lp_o, po = ref.logpdf(fxo, y), ref.posterior(fxo, y)
+    mo, vo = ref.mean_and_var(po(ref.ColVecs(Xt), noise_t))
+    Yo = ref.rand(po(ref.ColVecs(Xt), noise_t), Zw, Zy)
+    e_ref = {"logpdf": hp.rel(lp_o, tr["logpdf"]), "m_post": hp.rel(po.mw, tr["m_post"]), "mean_t": hp.rel(mo, tr["mean_t"]),
+             "var_t": hp.rel(vo, tr["var_t"]), "rand_t": hp.rel(Yo, tr["rand_t"])}
+
+    # the device
+    f = blr.BayesianLinearRegressor(mw, Λ)
+    post, lp = blr.posterior_and_logpdf(f(blr.ColVecs(X), σ2), y)
+    m, v = blr.mean_and_var(post(blr.ColVecs(Xt), noise_t))
+    Y = blr.rand_with_draws(post(blr.ColVecs(Xt), noise_t), Zw, Zy)
+    e_gpu = {"logpdf": hp.rel(lp, tr["logpdf"]), "m_post": hp.rel(post.mw, tr["m_post"]), "mean_t": hp.rel(m, tr["mean_t"]),
+             "var_t": hp.rel(v, tr["var_t"]), "rand_t": hp.rel(Y, tr["rand_t"])}
+    e_prec = hp.rel(post.Λw.dense(), tr["Lambda_post"])
+    print(f"[illcond] D={D} N={N} {tag}: precision {e_prec:.1e} | " +
+          " | ".join(f"{k} gpu {e_gpu[k]:.1e} ref {e_ref[k]:.1e}" for k in e_gpu))
+    assert e_prec < 1e-12
+    if "low-noise" in tag:
+        # σ² = eps(): log p is a difference of terms ~1e16 larger than itself; neither implementation has digits there
+        # (the reference only tests interpolation and vanishing covariance at this noise level, test/...:40-48)
+        e_gpu.pop("logpdf")
+    bad = {k: (e_gpu[k], e_ref[k]) for k in e_gpu if not e_gpu[k] <= max(RTOL, SLACK * e_ref[k])}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("D,N", [(64, 600), (256, 2000), (1024, 3000)])
+def test_sequential_conditioning_posterior_as_prior(D, N):
+    """test/bayesian_linear_regression.jl:49-70 at kernel-exercising sizes with an ill-conditioned start: the posterior of
+    batch 1 is the (dense, badly scaled) prior of batch 2; the two-step result must agree with one-shot conditioning and
+    with the extended-precision truth."""
+    rng = np.random.default_rng(D)
+    X = rng.standard_normal((D, N)) * np.geomspace(1e-3, 1e3, D)[:, None]      # badly scaled features
+    σ2 = np.exp(rng.standard_normal(N))
+    y = X.T @ (rng.standard_normal(D) / np.geomspace(1e-3, 1e3, D)) + np.sqrt(σ2) * rng.standard_normal(N)
+    mw = rng.standard_normal(D) / np.geomspace(1e-3, 1e3, D)
+    lam = np.geomspace(1e-6, 1e6, D)
+    f = blr.BayesianLinearRegressor(mw, blr.Diagonal(lam))
+    N1 = N // 3 + 5
+    f1 = blr.posterior(f(blr.ColVecs(X[:, :N1]), σ2[:N1]), y[:N1])
+    f2, lp2 = blr.posterior_and_logpdf(f1(blr.ColVecs(X[:, N1:]), σ2[N1:]), y[N1:])
+    fp = blr.posterior(f(blr.ColVecs(X), σ2), y)
+    tr = hp.ld_truth(hp.ld_stats(X, y, σ2, mw), mw, lam)
+    fo = ref.BayesianLinearRegressor(mw, ref.Diagonal(lam))
+    po1 = ref.posterior(fo(ref.ColVecs(X[:, :N1]), σ2[:N1]), y[:N1])
+    po2 = ref.posterior(po1(ref.ColVecs(X[:, N1:]), σ2[N1:]), y[N1:])
+    e_ref = hp.rel(po2.mw, tr["m_post"])
+    e_two, e_one = hp.rel(f2.mw, tr["m_post"]), hp.rel(fp.mw, tr["m_post"])
+    e_prec = hp.rel(f2.Λw.dense(), tr["Lambda_post"])
+    print(f"[illcond] sequential D={D}: m' two-step {e_two:.1e} one-shot {e_one:.1e} reference two-step {e_ref:.1e}; precision {e_prec:.1e}")
+    assert e_prec < 1e-12
+    assert e_one <= max(RTOL, SLACK * e_ref) and e_two <= max(RTOL, SLACK * e_ref)
+    # chain rule of the evidence: log p(y) = log p(y1) + log p(y2 | y1)
+    lp1 = blr.logpdf(f(blr.ColVecs(X[:, :N1]), σ2[:N1]), y[:N1])
+    lp = blr.logpdf(f(blr.ColVecs(X), σ2), y)
+    assert abs((lp1 + lp2) - lp) <= 1e-9 * abs(lp)

@@ -203,6 +203,29 @@ for w in (1,2,3,4,8,12,16):
             | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['achieved'])"
         done
       done 2>&1 | tee "$OUT/sweep_diag.log";;
+    tests_new)
+      timeout 2400 python -m pytest tests/test_gpu_contracts.py tests/test_gpu_shapes.py tests/test_gpu_illcond.py tests/test_highprec_pins.py -m gpu -q -s --timeout 900 > "$OUT/tests_new.log" 2>&1; echo "tests_new exit $?"; grep -E "^\[|passed|failed|Error|error" "$OUT/tests_new.log" | tail -80;;
+    tests_contracts)
+      timeout 1200 python -m pytest tests/test_gpu_contracts.py -m gpu -q -s -x --timeout 600 > "$OUT/tests_contracts.log" 2>&1; echo "tests_contracts exit $?"; tail -30 "$OUT/tests_contracts.log";;
+    sanitize)
+      for tool in ${SAN_TOOLS:-memcheck racecheck synccheck}; do
+        BLR_SANITIZE_SET=${SAN_SET:-all} timeout 1500 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_small.py > "$OUT/sanitize_$tool.log" 2>&1
+        echo "sanitize $tool exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|max rel err|Error|hazard" "$OUT/sanitize_$tool.log" | tail -20
+      done;;
+    traffic)
+      timeout 1500 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:gram_tma --csv \
+        --log-file "$OUT/traffic.csv" python tools/gram_traffic.py > "$OUT/traffic.log" 2>&1; echo "traffic exit $?"; tail -8 "$OUT/traffic.log"; grep -c gram_tma "$OUT/traffic.csv";;
+    dxd_ab)
+      for mode in fused legacy; do
+        for cfg in "--n-obs 1048576 --dim 256" "--n-obs 1048576 --dim 1024" "--n-obs 262144 --dim 2048" "--n-obs 262144 --dim 4096"; do
+          echo "BLR_DXD=$mode cfg=$cfg"
+          BLR_DXD=$mode timeout 600 python bench.py $cfg --steps 10 --warmup 3 --no-cpu --no-e2e --no-calibrate 2>> "$OUT/dxd.err" \
+            | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('ms_per_step', d['ms_per_step'], 'gram', d['roofline']['kernel_ms'], 'solve', d['roofline']['solve_ms'], 'TF', d['roofline']['achieved'], 'logpdf', d['logpdf'])"
+        done
+      done 2>&1 | tee "$OUT/dxd_ab.log";;
+    ncu_dxd)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:dxd_fused -s 2 -c 1 -o "$OUT/prof_dxd" -f \
+        python bench.py --n-obs 262144 --dim 1024 --steps 1 --warmup 2 --no-cpu --no-calibrate --no-e2e > "$OUT/ncu_dxd.log" 2>&1; echo "ncu_dxd exit $?";;
     *) echo "unknown stage $stage";;
   esac
 done
