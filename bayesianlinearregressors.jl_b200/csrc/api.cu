@@ -245,6 +245,7 @@ int blr_ctx_create(blr_ctx** out, int device) {
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->small, (size_t)SMALL_TOTAL * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_info, 8 * sizeof(int));  // [0] Cholesky info, [1] noise flag, [3] watchdog; [4..7] same for the prior's factor
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_in, (size_t)(2 * SMALL_VEC + 8) * sizeof(double));
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_res, (size_t)(SMALL_VEC + 8) * sizeof(double));
     // copy stream + hand-over events: host-streaming accumulation and the overlapped precision download
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
@@ -292,6 +293,7 @@ int blr_ctx_destroy(blr_ctx* ctx) {
     cudaFree(ctx->small);
     cudaFree(ctx->d_info);
     if (ctx->h_res) cudaFreeHost(ctx->h_res);
+    if (ctx->h_in) cudaFreeHost(ctx->h_in);
     cudaFree(ctx->d_flags);
     cudaFree(ctx->tflags);
     cudaFree(ctx->sched);

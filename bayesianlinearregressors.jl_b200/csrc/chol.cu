@@ -366,14 +366,14 @@ __global__ void __launch_bounds__(256) dot_self_kernel(const double* __restrict_
     if (threadIdx.x == 0) out[0] = acc;
 }
 __global__ void finalize_kernel(const double* __restrict__ scal /* q, ℓ, n */, const double* __restrict__ sc,
-                                const double* __restrict__ mw, const double* __restrict__ u, int D,
+                                const double* __restrict__ logdet_w, const double* __restrict__ mw, const double* __restrict__ u, int D,
                                 double* __restrict__ m_post, double* __restrict__ logpdf, int* __restrict__ noise_info) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D; i += gridDim.x * blockDim.x) m_post[i] = mw[i] + u[i];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const double LOG2PI = 1.8378770664093454835606594728112;
         const double q = scal[0], l = scal[1], n = scal[2];
-        // sc[0] = logdet Λw, sc[1] = logdet Λ', sc[2] = z'z
-        logpdf[0] = -0.5 * (n * LOG2PI + l + q + (sc[1] - sc[0]) - sc[2]);
+        // sc[1] = logdet Λ', sc[2] = z'z
+        logpdf[0] = -0.5 * (n * LOG2PI + l + q + (sc[1] - logdet_w[0]) - sc[2]);
         if (!isfinite(l)) *noise_info = 1;  // Σ log σ²: some variance is <= 0 or not finite
     }
 }
@@ -480,6 +480,27 @@ int post_ensure_W(blr_ctx* ctx, blr_post* p) {
     return 0;
 }
 
+// Λ' = Λw + G into both Lam (kept: the posterior precision) and L (factored in place), rhs = r -- one pass instead of
+// memset + set_diag + add + two device copies.  diag != nullptr: Diagonal prior (Lam holds nothing yet);
+// else Lam already holds the dense prior precision.
+__global__ void __launch_bounds__(256) assemble_posterior_kernel(double* __restrict__ Lam, double* __restrict__ L,
+                                                                 const double* __restrict__ G, const double* __restrict__ diag,
+                                                                 int D, const double* __restrict__ r, double* __restrict__ rhs) {
+    const int64_t n2 = (int64_t)D * D;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += (int64_t)gridDim.x * blockDim.x) {
+        double v = G[e];
+        if (diag) {
+            const int row = (int)(e % D), col = (int)(e / D);
+            if (row == col) v += diag[row];
+        } else {
+            v += Lam[e];
+        }
+        Lam[e] = v;
+        L[e] = v;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D; i += gridDim.x * blockDim.x) rhs[i] = r[i];
+}
+
 int infer_solve(blr_ctx* ctx, const blr_prior* prior, const blr_stats* st, double* logpdf_out, double* m_post,
                 double* T_post, double* L_post, blr_post** post_out) {
     const int64_t D = st->D;
@@ -488,15 +509,16 @@ int infer_solve(blr_ctx* ctx, const blr_prior* prior, const blr_stats* st, doubl
     blr_post* p = nullptr;
     BLR_TRY(alloc_post(ctx, D, &p));
     // scratch scalars live behind the prep partials in ctx->small
-    double* sc = ctx->small + SMALL_SC;    // [0] logdet Λw  [1] logdet Λ'  [2] z'z  [3] logpdf
+    double* sc = ctx->small + SMALL_SC;    // [0] logdet Λw (dense prior)  [1] logdet Λ'  [2] z'z  [3] logpdf
     double* rhs = ctx->small + SMALL_RHS;  // D doubles: r in, z = L^-1 r out
     double* usol = ctx->small + SMALL_U;   // D doubles: u = L^-T z
-    double* mwd = ctx->small + SMALL_MW;
+    double* in = ctx->small + SMALL_MW;    // host inputs, ONE page-locked H2D copy: [mw (D) | diag Λw (D) | logdet Λw]
+    double* mwd = in;
+    double* diagd = in + D;
+    const double* logdet_w = in + 2 * D;
     int* info_post = ctx->d_info;          // [0] info of chol(Λ'), [1] noise flag, [3] watchdog
     int* info_prior = ctx->d_info + 4;     // same for chol(Λw) of a dense prior
     int rc = 0;
-    double ldh = 0.0;
-    bool have = false;
     bool lam_on_copy_stream = false;  // the precision download is in flight on the copy stream
     auto fail = [&](int code) {
         if (lam_on_copy_stream) cudaEventSynchronize(ctx->ev[7]);  // it reads p->Lam and writes the caller's buffer
@@ -504,27 +526,43 @@ int infer_solve(blr_ctx* ctx, const blr_prior* prior, const blr_stats* st, doubl
         return code;
     };
     if (D > SMALL_VEC) return fail(set_err(ctx, BLR_E_INVALID, "D > 16384 not supported"));
+    const bool diagonal = prior->lambda_kind == BLR_LAMBDA_DIAGONAL;
+    if (!diagonal && prior->lambda_kind != BLR_LAMBDA_DENSE) return fail(set_err(ctx, BLR_E_INVALID, "unknown lambda_kind"));
 
-    // logdet Λw (and PosDef check of the prior): Diagonal on host, dense via a device Cholesky of a copy in p->L.  No host
-    // synchronisation here: a failed prior factorisation is reported with the results (one sync per inference).
-    rc = upload_prior_precision(ctx, prior, D, p->Lam, &ldh, &have);
-    if (rc != 0) return fail(rc);
+    // ---- host inputs.  Diagonal prior: positivity and logdet on the host (D numbers).  The previous inference on this
+    // context ended with a stream synchronisation, so the staging buffer is free.
+    double* hin = ctx->h_in;
+    memcpy(hin, prior->mw, (size_t)D * sizeof(double));
+    double ldh = 0.0;
+    if (diagonal) {
+        for (int64_t i = 0; i < D; ++i) {
+            if (!(prior->lambda[i] > 0.0)) return fail((int)(i + 1));
+            ldh += log(prior->lambda[i]);
+        }
+        memcpy(hin + D, prior->lambda, (size_t)D * sizeof(double));
+    }
+    hin[2 * D] = ldh;
+    BLR_CUDA_OK(ctx, cudaMemcpyAsync(in, hin, (size_t)(2 * D + 1) * sizeof(double), cudaMemcpyHostToDevice, sm));
     BLR_CUDA_OK(ctx, cudaMemsetAsync(info_prior, 0, 4 * sizeof(int), sm));
-    if (!have) {
+    if (!diagonal) {
+        // dense prior: logdet Λw (and its PosDef check) from a device Cholesky of a copy in p->L.  No host synchronisation
+        // here: a failed prior factorisation is reported with the results (one sync per inference).
+        const int64_t ld = prior->ld > 0 ? prior->ld : D;
+        if (ld < D) return fail(set_err(ctx, BLR_E_INVALID, "prior.ld < D"));
+        BLR_CUDA_OK(ctx, cudaMemcpy2DAsync(p->Lam, (size_t)D * sizeof(double), prior->lambda, (size_t)ld * sizeof(double),
+                                           (size_t)D * sizeof(double), (size_t)D, cudaMemcpyHostToDevice, sm));
         BLR_CUDA_OK(ctx, cudaMemcpyAsync(p->L, p->Lam, (size_t)D * D * sizeof(double), cudaMemcpyDeviceToDevice, sm));
         rc = potrf_lower(ctx, p->L, D, info_prior);
         if (rc == 0) rc = logdet_from_chol(ctx, p->L, D, sc + 0);
         if (rc != 0) return fail(rc);
-    } else {
-        BLR_CUDA_OK(ctx, cudaMemcpyAsync(sc + 0, &ldh, sizeof(double), cudaMemcpyHostToDevice, sm));
+        logdet_w = sc + 0;
     }
-    BLR_CUDA_OK(ctx, cudaMemcpyAsync(mwd, prior->mw, (size_t)D * sizeof(double), cudaMemcpyHostToDevice, sm));
 
-    // Λ' = Λw + G  (kept in p->Lam), factor a copy
+    // ---- Λ' = Λw + G  (kept in p->Lam), a copy to factor in p->L, rhs = r
     const int64_t n2 = D * D;
-    add_inplace_kernel<<<(int)std::min<int64_t>((n2 + 255) / 256, ctx->sm_count * 8), 256, 0, sm>>>(p->Lam, st->G(), n2);
-    BLR_CHECK_LAUNCH(ctx, "add_inplace_kernel");
-    BLR_CUDA_OK(ctx, cudaMemcpyAsync(p->L, p->Lam, (size_t)n2 * sizeof(double), cudaMemcpyDeviceToDevice, sm));
+    assemble_posterior_kernel<<<(int)std::min<int64_t>((n2 + 255) / 256, ctx->sm_count * 8), 256, 0, sm>>>(
+        p->Lam, p->L, st->G(), diagonal ? diagd : nullptr, (int)D, st->r(), rhs);
+    BLR_CHECK_LAUNCH(ctx, "assemble_posterior_kernel");
     // The posterior precision is final here: its download (8 MiB at D = 1024, 128 MiB at D = 4096) runs on the copy stream
     // underneath the factorisation and the solves instead of after them (small matrices keep the plain in-order copy:
     // measured, the extra stream hand-over costs more than a sub-100 us copy saves).
@@ -535,13 +573,13 @@ int infer_solve(blr_ctx* ctx, const blr_prior* prior, const blr_stats* st, doubl
         BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[7], ctx->copy_stream));
         lam_on_copy_stream = true;
     }
-    BLR_CUDA_OK(ctx, cudaMemcpyAsync(rhs, st->r(), (size_t)D * sizeof(double), cudaMemcpyDeviceToDevice, sm));
     if (!ctx->dxd_legacy) {
         // L = chol(Λ'), z = L^-1 r, u = L^-T z, logdet, z'z, m' = mw + u, logpdf: one cooperative launch (chol_tiled.cu)
         DxdFinalize fin;
         fin.stat_scal = st->scal();
         fin.mw = mwd;
         fin.m_post = p->mw;
+        fin.logdet_w = logdet_w;
         fin.sc = sc;
         rc = dxd_fused(ctx, p->L, D, info_post, rhs, usol, &fin);
         if (rc != 0) return fail(rc);
@@ -561,8 +599,8 @@ int infer_solve(blr_ctx* ctx, const blr_prior* prior, const blr_stats* st, doubl
         rc = trsv_lower_backward(ctx, p->L, D, Dinv, rhs);
         if (rc == 0) rc = logdet_from_chol(ctx, p->L, D, sc + 1);
         if (rc != 0) return fail(rc);
-        finalize_kernel<<<(int)std::min<int64_t>((D + 255) / 256, 64), 256, 0, sm>>>(st->scal(), sc, mwd, rhs, (int)D, p->mw,
-                                                                                  sc + 3, info_post + 1);
+        finalize_kernel<<<(int)std::min<int64_t>((D + 255) / 256, 64), 256, 0, sm>>>(st->scal(), sc, logdet_w, mwd, rhs, (int)D,
+                                                                                  p->mw, sc + 3, info_post + 1);
         BLR_CHECK_LAUNCH(ctx, "finalize_kernel");
     }
     BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[5], sm));

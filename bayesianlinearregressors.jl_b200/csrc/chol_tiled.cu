@@ -26,7 +26,11 @@
 // (~1 s of SM clocks) turns any violated assumption into an error code instead of a hung device.
 #include <math.h>
 
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <algorithm>
+#include <vector>
 
 #include "cholblock.cuh"
 #include "common.cuh"
@@ -52,6 +56,7 @@ struct Smem {
     double xs[NB];
     double part[4][NB];
     double red[32];
+    unsigned long long t_ready;  // trace: when the last wait of the current task returned
     int ready;
     int ok;
 };
@@ -70,9 +75,17 @@ struct TiledParams {
     const double* stat_scal;  // q, ℓ, n
     const double* mw;         // prior mean
     double* m_post;           // mw + u
-    double* sc;               // [0] logdet Λw (in)  [1] logdet Λ'  [2] z'z  [3] logpdf (out)
+    const double* logdet_w;   // logdet Λw (device scalar)
+    double* sc;               // out: [1] logdet Λ'  [2] z'z  [3] logpdf
     int* noise_info;          // set to 1 when ℓ is not finite (a non-positive noise variance)
+    unsigned long long* trace;  // debugging (BLR_DXD_TRACE): per task [kind/i/j, t_start, t_inputs_ready, t_end] in ns (globaltimer)
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     int v;
@@ -107,6 +120,7 @@ __device__ bool wait_flags(const TiledParams& p, tc::Smem& sm, int f0, int f1) {
             st_release_gpu(p.flags + abort_slot, p.epoch);
             atomicExch(p.info + 3, 1);
         }
+        if (p.trace) sm.t_ready = globaltimer_ns();
         sm.ok = ok;
     }
     __syncthreads();
@@ -344,20 +358,26 @@ __device__ bool border_task(const TiledParams& p, tc::Smem& sm, int j) {
     return true;
 }
 
-// Backward-solve task j:  u_j = L_jj^-T (z_j - Σ_{i>j} L_ij' u_i)
+// Backward-solve task j:  u_j = L_jj^-T (z_j - Σ_{i>j} L_ij' u_i).  Everything that does not depend on the u's is staged
+// before waiting for them (L_jj and its reciprocal diagonal in T; each tile L_ij before its u_i), so that the chain
+// u_{nb-1} -> ... -> u_0 pays per block one 64-vector load, 16 FMAs per thread and one 64 x 64 substitution.
 __device__ bool bsolve_task(const TiledParams& p, tc::Smem& sm, int j) {
     using namespace tc;
     const int tid = threadIdx.x, c = tid & (NB - 1), rq = tid >> 6;
     const int j0 = j * NB, rows_j = min(NB, p.D - j0);
     const int ntile = p.nb * (p.nb + 1) / 2;
+    if (!wait_flags(p, sm, tile_flag(j, j), ntile + j)) return false;  // L_jj and z_j (both final long before u_{j+1})
+    load_diag_block(p, j0, rows_j, sm.T, sm.rdiag);
+    const double zj = (tid < rows_j) ? __ldcg(p.z + j0 + tid) : 0.0;
     double acc = 0.0;
     for (int i = p.nb - 1; i > j; --i) {
         const int i0 = i * NB, rows_i = min(NB, p.D - i0);
-        if (!wait_flags(p, sm, tile_flag(i, j), ntile + p.nb + i)) return false;
+        if (!wait_flags(p, sm, tile_flag(i, j), -1)) return false;
         for (int e = tid; e < NB * NB; e += THREADS) {  // stage L_ij [cc][rr], coalesced over rr
             const int rr = e & (NB - 1), cc = e >> 6;
             sm.u.Ls[cc * LDL + rr] = (rr < rows_i) ? __ldcg(p.A + (int64_t)(j0 + cc) * p.ld + i0 + rr) : 0.0;
         }
+        if (!wait_flags(p, sm, ntile + p.nb + i, -1)) return false;
         if (tid < NB) sm.xs[tid] = (tid < rows_i) ? __ldcg(p.u + i0 + tid) : 0.0;
         __syncthreads();
 #pragma unroll
@@ -365,14 +385,10 @@ __device__ bool bsolve_task(const TiledParams& p, tc::Smem& sm, int j) {
         __syncthreads();
     }
     sm.part[rq][c] = acc;
-    if (!wait_flags(p, sm, tile_flag(j, j), ntile + j)) return false;
-    load_diag_block(p, j0, rows_j, sm.u.Ls, sm.rdiag);
-    if (tid < NB) {
-        const double zj = (tid < rows_j) ? __ldcg(p.z + j0 + tid) : 0.0;
-        sm.xs[tid] = zj - (sm.part[0][tid] + sm.part[1][tid] + sm.part[2][tid] + sm.part[3][tid]);
-    }
     __syncthreads();
-    tri_solve64_warp0<true>(sm.u.Ls, sm.rdiag, sm.xs);
+    if (tid < NB) sm.xs[tid] = zj - (sm.part[0][tid] + sm.part[1][tid] + sm.part[2][tid] + sm.part[3][tid]);
+    __syncthreads();
+    tri_solve64_warp0<true>(sm.T, sm.rdiag, sm.xs);
     __syncthreads();
     if (tid < rows_j) p.u[j0 + tid] = sm.xs[tid];
     publish(p, ntile + p.nb + j);
@@ -402,7 +418,7 @@ __device__ void finalize_task(const TiledParams& p, tc::Smem& sm) {
         const double q = p.stat_scal[0], l = p.stat_scal[1], n = p.stat_scal[2];
         p.sc[1] = 2.0 * ld;
         p.sc[2] = zz;
-        p.sc[3] = -0.5 * (n * LOG2PI + l + q + (2.0 * ld - p.sc[0]) - zz);
+        p.sc[3] = -0.5 * (n * LOG2PI + l + q + (2.0 * ld - p.logdet_w[0]) - zz);
         if (!isfinite(l)) *p.noise_info = 1;  // Σ log σ²: some variance is <= 0 (-inf / NaN) or not finite
     }
 }
@@ -416,19 +432,43 @@ __global__ void __launch_bounds__(tc::THREADS, 2) dxd_fused_kernel(const TiledPa
     const int ntasks = ncol_tasks + (p.u ? nb : 0);
     for (int t = blockIdx.x; t < ntasks; t += gridDim.x) {
         bool ok;
+        unsigned long long t_start = 0;
+        int kind, ti, tj;
+        if (p.trace && threadIdx.x == 0) {
+            t_start = globaltimer_ns();
+            sm.t_ready = t_start;
+        }
         if (t < ncol_tasks) {
             // column j holds (nb - j) tile tasks followed by its border task; off(j) = j nb - j (j - 1) / 2 + e j
             int j = 0;
             while (j + 1 < nb && (j + 1) * nb - (j + 1) * j / 2 + per_col_extra * (j + 1) <= t) ++j;
             const int within = t - (j * nb - j * (j - 1) / 2 + per_col_extra * j);
-            ok = (within < nb - j) ? tile_task(p, sm, j + within, j) : border_task(p, sm, j);
+            tj = j;
+            if (within < nb - j) {
+                ti = j + within;
+                kind = (ti == j) ? 0 : 1;
+                ok = tile_task(p, sm, ti, j);
+            } else {
+                ti = nb;
+                kind = 2;
+                ok = border_task(p, sm, j);
+            }
         } else {
             const int j = nb - 1 - (t - ncol_tasks);
+            ti = tj = j;
+            kind = 3;
             ok = bsolve_task(p, sm, j);
             if (ok && j == 0 && p.m_post) finalize_task(p, sm);
         }
         if (!ok) return;
         __syncthreads();
+        if (p.trace && threadIdx.x == 0) {
+            unsigned long long* tr = p.trace + 4 * (size_t)t;
+            tr[0] = ((unsigned long long)kind << 32) | ((unsigned long long)ti << 16) | (unsigned long long)tj;
+            tr[1] = t_start;
+            tr[2] = sm.t_ready;
+            tr[3] = globaltimer_ns();
+        }
     }
 }
 
@@ -471,13 +511,36 @@ int dxd_fused(blr_ctx* ctx, double* A, int64_t D64, int* info_dev, double* z, do
     p.mw = fin ? fin->mw : nullptr;
     p.m_post = (fin && p.u) ? fin->m_post : nullptr;
     p.sc = fin ? fin->sc : nullptr;
+    p.logdet_w = fin ? fin->logdet_w : nullptr;
     p.noise_info = info_dev + 1;
-    BLR_CUDA_OK(ctx, cudaMemsetAsync(info_dev, 0, 4 * sizeof(int), sm));
+    p.trace = nullptr;
     const int ntasks = ntile + (p.z ? nb : 0) + (p.u ? nb : 0);
+    const char* trace_path = getenv("BLR_DXD_TRACE");
+    if (trace_path) {
+        BLR_CUDA_OK(ctx, cudaMalloc(&p.trace, (size_t)ntasks * 4 * sizeof(unsigned long long)));
+        BLR_CUDA_OK(ctx, cudaMemsetAsync(p.trace, 0, (size_t)ntasks * 4 * sizeof(unsigned long long), sm));
+    }
+    BLR_CUDA_OK(ctx, cudaMemsetAsync(info_dev, 0, 4 * sizeof(int), sm));
     const int grid = std::min(ntasks, ctx->dxd_occ * ctx->sm_count);
     void* args[] = {(void*)&p};
     BLR_CUDA_OK(ctx, cudaLaunchCooperativeKernel((void*)dxd_fused_kernel, dim3(grid), dim3(tc::THREADS), args, smem, sm));
     BLR_CHECK_LAUNCH(ctx, "dxd_fused_kernel");
+    if (trace_path) {  // debugging aid: dump the task timeline (kind: 0 potrf, 1 trsm, 2 border, 3 bsolve)
+        std::vector<unsigned long long> h((size_t)ntasks * 4);
+        BLR_CUDA_OK(ctx, cudaStreamSynchronize(sm));
+        BLR_CUDA_OK(ctx, cudaMemcpy(h.data(), p.trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        cudaFree(p.trace);
+        if (FILE* fp = fopen(trace_path, "a")) {
+            unsigned long long t0 = ~0ull;
+            for (int t = 0; t < ntasks; ++t)
+                if (h[4 * t + 1] && h[4 * t + 1] < t0) t0 = h[4 * t + 1];
+            fprintf(fp, "# D=%d nb=%d grid=%d ntasks=%d: task kind i j start_us ready_us end_us\n", D, nb, grid, ntasks);
+            for (int t = 0; t < ntasks; ++t)
+                fprintf(fp, "%d %d %d %d %.2f %.2f %.2f\n", t, (int)(h[4 * t] >> 32), (int)((h[4 * t] >> 16) & 0xffff),
+                        (int)(h[4 * t] & 0xffff), (h[4 * t + 1] - t0) * 1e-3, (h[4 * t + 2] - t0) * 1e-3, (h[4 * t + 3] - t0) * 1e-3);
+            fclose(fp);
+        }
+    }
     return 0;
 }
 

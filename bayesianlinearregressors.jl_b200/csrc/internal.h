@@ -55,6 +55,7 @@ struct blr_ctx {
     double* small = nullptr;  // small device scratch (scalars, block partial sums)
     size_t small_bytes = 0;
     int* d_info = nullptr;
+    double* h_in = nullptr;   // page-locked input staging of infer_solve: [mw | diag(Λw) | logdet Λw] in ONE H2D copy
     double* h_res = nullptr;  // page-locked result staging: [info | logpdf | m_post (SMALL_VEC)] -> one sync per inference
     int* d_flags = nullptr;  // wavefront-solve ready flags (one per 64-row block), compared against flag_epoch
     int flag_epoch = 0;
@@ -102,7 +103,8 @@ constexpr int SMALL_VEC = 16384;     // capacity of each D-vector slot (max supp
 constexpr int SMALL_RHS = 8192;
 constexpr int SMALL_MW = SMALL_RHS + SMALL_VEC;
 constexpr int SMALL_DTMP = SMALL_MW + SMALL_VEC;
-constexpr int SMALL_U = SMALL_DTMP + SMALL_VEC;  // backward-solve output of the fused D x D kernel
+constexpr int SMALL_U = SMALL_DTMP + SMALL_VEC + 8;  // backward-solve output of the fused D x D kernel (8 spare doubles: the
+                                                     // staged host inputs [mw | diag Λw | logdet Λw] span SMALL_MW .. +2D+1)
 constexpr int SMALL_TOTAL = SMALL_U + SMALL_VEC;
 
 int set_err(blr_ctx* ctx, int code, const std::string& msg);
@@ -150,7 +152,8 @@ struct DxdFinalize {
     const double* stat_scal;  // q, ℓ, n of the reduced statistics
     const double* mw;         // prior mean
     double* m_post;           // out: mw + u
-    double* sc;               // [0] logdet Λw (in); [1] logdet Λ', [2] z'z, [3] logpdf (out)
+    const double* logdet_w;   // logdet Λw
+    double* sc;               // out: [1] logdet Λ', [2] z'z, [3] logpdf
 };
 // One cooperative launch: A (lower triangle in) -> Cholesky factor (lower, strict upper zeroed); optionally z = L^-1 z in
 // place, u = L^-T z, and the finalize step.  info_dev: 4 device ints, [0] = LAPACK-style info, [1] = noise flag, [3] = abort.

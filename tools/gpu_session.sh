@@ -226,6 +226,21 @@ for w in (1,2,3,4,8,12,16):
     ncu_dxd)
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:dxd_fused -s 2 -c 1 -o "$OUT/prof_dxd" -f \
         python bench.py --n-obs 262144 --dim 1024 --steps 1 --warmup 2 --no-cpu --no-calibrate --no-e2e > "$OUT/ncu_dxd.log" 2>&1; echo "ncu_dxd exit $?";;
+    dxd_trace)
+      for cfg in "--n-obs 65536 --dim 256" "--n-obs 65536 --dim 1024" "--n-obs 32768 --dim 4096"; do
+        d=$(echo $cfg | awk '{print $4}')
+        BLR_DXD_TRACE="$OUT/dxd_trace_D$d.txt" timeout 300 python bench.py $cfg --steps 2 --warmup 1 --no-cpu --no-e2e --no-calibrate > /dev/null 2>> "$OUT/trace.err"
+        echo "trace D=$d lines $(wc -l < $OUT/dxd_trace_D$d.txt)"
+      done;;
+    bench_cfgs)
+      for cfgname in ${CFGS:-cfg2 cfg4 cfg5}; do
+        timeout 1500 python bench.py --config $cfgname --steps ${STEPS:-5} --warmup 3 > "$OUT/bench_$cfgname.json" 2> "$OUT/bench_$cfgname.err"; echo "bench $cfgname exit $?"
+        tail -c 2500 "$OUT/bench_$cfgname.json"; tail -3 "$OUT/bench_$cfgname.err"
+      done;;
+    bench_pm)
+      timeout 1500 python bench.py --prior-mean random --steps 5 --warmup 3 --no-cpu --no-e2e > "$OUT/bench_cfg3_pm.json" 2> "$OUT/bench_cfg3_pm.err"; echo "bench_pm exit $?"; tail -c 1500 "$OUT/bench_cfg3_pm.json";;
+    bench20)
+      timeout 1500 python bench.py --gpus 1 --steps 20 --warmup 5 > "$OUT/bench20.json" 2> "$OUT/bench20.err"; echo "bench20 exit $?"; tail -c 3500 "$OUT/bench20.json"; tail -5 "$OUT/bench20.err";;
     *) echo "unknown stage $stage";;
   esac
 done
