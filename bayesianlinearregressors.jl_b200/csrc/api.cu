@@ -1,6 +1,7 @@
 // C ABI of libblr_cuda (declared in include/blr_cuda.h): contexts, handles, and the entry points the Julia
 // glue / Python host mirror bind.  No torch types, no exceptions across the boundary, no CPU fallback.
 #include <dlfcn.h>
+#include <math.h>
 #include <nccl.h>
 #include <stdlib.h>
 #include <string.h>
@@ -633,9 +634,10 @@ int blr_vec_synth_targets(blr_ctx* ctx, const blr_x* x, const blr_vec* sigma2, u
     return synth_targets(ctx, x, sigma2->p, seed, n_offset, y->p);
 }
 
-int blr_x_rff(blr_ctx* ctx, const blr_x* xin, const double* W, const double* b, int64_t D, blr_x** out) {
+int blr_x_features(blr_ctx* ctx, const blr_x* xin, const double* W, const double* b, int64_t D, int act, double scale,
+                   blr_x** out) {
     CTX_ENTER(ctx);
-    if (!xin || !W || !b || !out || D < 1) return set_err(ctx, BLR_E_INVALID, "bad rff arguments");
+    if (!xin || !W || !b || !out || D < 1) return set_err(ctx, BLR_E_INVALID, "bad feature-map arguments");
     const int64_t din = xin->D;
     double *Wd = nullptr, *bd = nullptr;
     blr_x* phi = nullptr;
@@ -644,7 +646,7 @@ int blr_x_rff(blr_ctx* ctx, const blr_x* xin, const double* W, const double* b, 
     if (e == cudaSuccess) e = dev_alloc(ctx, &bd, (size_t)D * sizeof(double));
     if (e == cudaSuccess) e = cudaMemcpyAsync(Wd, W, (size_t)D * din * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(bd, b, (size_t)D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
-    int rc = (e == cudaSuccess) ? rff_features(ctx, xin, Wd, bd, D, phi->p, phi->ld) : cuda_fail(ctx, e, "rff upload");
+    int rc = (e == cudaSuccess) ? affine_features(ctx, xin, Wd, bd, D, act, scale, phi->p, phi->ld) : cuda_fail(ctx, e, "feature-map upload");
     dev_free(ctx->stream, Wd);
     dev_free(ctx->stream, bd);
     if (rc != 0) {
@@ -653,6 +655,9 @@ int blr_x_rff(blr_ctx* ctx, const blr_x* xin, const double* W, const double* b, 
     }
     *out = phi;
     return 0;
+}
+int blr_x_rff(blr_ctx* ctx, const blr_x* xin, const double* W, const double* b, int64_t D, blr_x** out) {
+    return blr_x_features(ctx, xin, W, b, D, BLR_ACT_COS, sqrt(2.0 / (double)(D > 0 ? D : 1)), out);
 }
 
 // ---------------------------------------------------------------------------------------------- inference

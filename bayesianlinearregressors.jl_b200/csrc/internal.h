@@ -205,6 +205,8 @@ int synth_normal(blr_ctx* ctx, double* out, int64_t rows, int64_t cols, int64_t 
                  int64_t col_offset);
 int synth_noise(blr_ctx* ctx, double* sigma2, int64_t n, uint64_t seed, int64_t n_offset);
 int synth_targets(blr_ctx* ctx, const blr_x* x, const double* sigma2, uint64_t seed, int64_t n_offset, double* y);
+int affine_features(blr_ctx* ctx, const blr_x* xin, const double* W_dev, const double* b_dev, int64_t D, int act, double scale,
+                    double* out, int64_t ldo);
 int rff_features(blr_ctx* ctx, const blr_x* xin, const double* W_dev, const double* b_dev, int64_t D, double* out,
                  int64_t ldo);
 int transpose_to_colvecs(blr_ctx* ctx, const blr_x* x, double* out, int64_t ldo);

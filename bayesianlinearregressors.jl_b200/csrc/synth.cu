@@ -113,11 +113,21 @@ int synth_targets(blr_ctx* ctx, const blr_x* x, const double* sigma2, uint64_t s
     return 0;
 }
 
-// out[d + n * ldo] = sqrt(2 / D) cos(Σ_i W[d, i] x[i, n] + b[d]);  one CTA = 8 observations x all D features.
+// out[d + n * ldo] = scale * act(Σ_i W[d, i] x[i, n] + b[d]);  one CTA = 8 observations x all D features.
+// ACT: 0 cos (random Fourier features with scale = sqrt(2 / D)), 1 tanh, 2 relu, 3 identity, 4 sin.
 constexpr int RFF_OBS = 8;
-__global__ void __launch_bounds__(256) rff_kernel(const double* __restrict__ Xin, int64_t ldx, int din, int64_t N,
-                                                  const double* __restrict__ W, const double* __restrict__ b, int D,
-                                                  double* __restrict__ out, int64_t ldo) {
+template <int ACT>
+__device__ __forceinline__ double feature_act(double z) {
+    if (ACT == 0) return cos(z);
+    if (ACT == 1) return tanh(z);
+    if (ACT == 2) return z > 0.0 ? z : 0.0;
+    if (ACT == 4) return sin(z);
+    return z;
+}
+template <int ACT>
+__global__ void __launch_bounds__(256) features_kernel(const double* __restrict__ Xin, int64_t ldx, int din, int64_t N,
+                                                       const double* __restrict__ W, const double* __restrict__ b, int D,
+                                                       double scale, double* __restrict__ out, int64_t ldo) {
     extern __shared__ double xs[];  // [RFF_OBS][din]
     const int64_t n0 = (int64_t)blockIdx.x * RFF_OBS;
     for (int e = threadIdx.x; e < RFF_OBS * din; e += 256) {
@@ -125,7 +135,6 @@ __global__ void __launch_bounds__(256) rff_kernel(const double* __restrict__ Xin
         xs[e] = (n0 + o < N) ? Xin[(n0 + o) * ldx + i] : 0.0;
     }
     __syncthreads();
-    const double scale = sqrt(2.0 / (double)D);
     for (int d = threadIdx.x; d < D; d += 256) {
         double acc[RFF_OBS];
         const double bd = b[d];
@@ -138,20 +147,34 @@ __global__ void __launch_bounds__(256) rff_kernel(const double* __restrict__ Xin
         }
 #pragma unroll
         for (int o = 0; o < RFF_OBS; ++o)
-            if (n0 + o < N) out[(n0 + o) * ldo + d] = scale * cos(acc[o]);
+            if (n0 + o < N) out[(n0 + o) * ldo + d] = scale * feature_act<ACT>(acc[o]);
     }
+}
+int affine_features(blr_ctx* ctx, const blr_x* xin, const double* W_dev, const double* b_dev, int64_t D, int act, double scale,
+                    double* out, int64_t ldo) {
+    if (xin->N == 0) return 0;
+    if (xin->layout != BLR_COLVECS) return set_err(ctx, BLR_E_INVALID, "device feature maps expect ColVecs inputs");
+    const size_t smem = (size_t)RFF_OBS * xin->D * sizeof(double);
+    if (smem > 48 * 1024) return set_err(ctx, BLR_E_INVALID, "device feature map: d_in too large");
+    const int64_t grid = (xin->N + RFF_OBS - 1) / RFF_OBS;
+#define BLR_FEATURES_LAUNCH(A)                                                                                              \
+    features_kernel<A><<<(unsigned)grid, 256, smem, ctx->stream>>>(xin->p, xin->ld, (int)xin->D, xin->N, W_dev, b_dev, (int)D, \
+                                                                  scale, out, ldo)
+    switch (act) {
+        case 0: BLR_FEATURES_LAUNCH(0); break;
+        case 1: BLR_FEATURES_LAUNCH(1); break;
+        case 2: BLR_FEATURES_LAUNCH(2); break;
+        case 3: BLR_FEATURES_LAUNCH(3); break;
+        case 4: BLR_FEATURES_LAUNCH(4); break;
+        default: return set_err(ctx, BLR_E_INVALID, "unknown activation");
+    }
+#undef BLR_FEATURES_LAUNCH
+    BLR_CHECK_LAUNCH(ctx, "features_kernel");
+    return 0;
 }
 int rff_features(blr_ctx* ctx, const blr_x* xin, const double* W_dev, const double* b_dev, int64_t D, double* out,
                  int64_t ldo) {
-    if (xin->N == 0) return 0;
-    if (xin->layout != BLR_COLVECS) return set_err(ctx, BLR_E_INVALID, "blr_x_rff expects ColVecs inputs");
-    const size_t smem = (size_t)RFF_OBS * xin->D * sizeof(double);
-    if (smem > 48 * 1024) return set_err(ctx, BLR_E_INVALID, "blr_x_rff: d_in too large");
-    const int64_t grid = (xin->N + RFF_OBS - 1) / RFF_OBS;
-    rff_kernel<<<(unsigned)grid, 256, smem, ctx->stream>>>(xin->p, xin->ld, (int)xin->D, xin->N, W_dev, b_dev, (int)D, out,
-                                                         ldo);
-    BLR_CHECK_LAUNCH(ctx, "rff_kernel");
-    return 0;
+    return affine_features(ctx, xin, W_dev, b_dev, D, 0, sqrt(2.0 / (double)D), out, ldo);
 }
 
 // RowVecs (N x D column-major, element (n, d) at d * ld + n)  ->  ColVecs (D x N, element (d, n) at n * ldo + d)

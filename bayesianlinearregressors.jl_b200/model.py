@@ -218,6 +218,64 @@ class RandomFourierFeatures:
         return ColVecs(DeviceMatrix(ctx, h, self.W.shape[0], xin.N, L.COLVECS))
 
 
+class AffineFeatures:
+    """Device-native one-layer feature map ϕ(x) = scale * act(W x + b) (blr_x_features): random Fourier features are
+    act = "cos", scale = sqrt(2/D); "tanh" / "relu" give the last-layer features of examples/nn-blr.jl style models;
+    "identity" a linear projection.  Output resident on the device like RandomFourierFeatures."""
+
+    ACTS = {"cos": 0, "tanh": 1, "relu": 2, "identity": 3, "sin": 4}
+
+    def __init__(self, W, b, act: str = "tanh", scale: float = 1.0, ctx: Optional[Context] = None):
+        if act not in self.ACTS:
+            raise L.BLRError(L.E_INVALID, f"unknown activation {act!r}")
+        self.W = _f64(np.asarray(W, dtype=np.float64), "F")
+        self.b = _f64(np.asarray(b, dtype=np.float64).reshape(-1))
+        self.act, self.scale, self.ctx = act, float(scale), ctx
+
+    def __call__(self, x):
+        ctx = self.ctx if self.ctx is not None else default_context()
+        x = _wrap_inputs(x)
+        if isinstance(x, RowVecs):
+            x = ColVecs(np.ascontiguousarray(np.asarray(x.X).T)) if isinstance(x.X, np.ndarray) else x
+        xin = x_as_colvecs(ctx, x)
+        if xin.D != self.W.shape[1]:
+            raise L.DimensionMismatch(L.E_DIM, "size(W, 2) != size(x, 1)")
+        h = C.c_void_p()
+        ctx.check(ctx.lib.blr_x_features(ctx.handle, xin.handle, _ptr(self.W), _ptr(self.b), self.W.shape[0], self.ACTS[self.act],
+                                         self.scale, C.byref(h)))
+        return ColVecs(DeviceMatrix(ctx, h, self.W.shape[0], xin.N, L.COLVECS))
+
+
+class TorchFeatureMap:
+    """Generic device-resident feature-map protocol (src/basis_function_regression.jl:34-37: ϕ is any callable): `fn` is
+    user code in torch that maps the (N, d_in) CUDA tensor of inputs to an (N, D) CUDA tensor of features.  Inputs arrive as
+    a zero-copy view of the library's device matrix (or are uploaded once if they live on the host), the result is borrowed
+    back as a ColVecs design matrix -- ϕ(x) never visits the host, whatever ϕ is.  Stream ordering between torch's stream and
+    the library's is handled on both sides (blr_stream_wait_ctx / blr_ctx_wait_stream).  The Julia counterpart wraps CUDA.jl
+    arrays with blr_x_wrap_device (INTEGRATION.md)."""
+
+    def __init__(self, fn: Callable, ctx: Optional[Context] = None):
+        self.fn, self.ctx = fn, ctx
+
+    def __call__(self, x):
+        import torch
+
+        ctx = self.ctx if self.ctx is not None else default_context()
+        x = _wrap_inputs(x)
+        if isinstance(x, RowVecs) and not isinstance(x.X, DeviceMatrix) and not _is_torch_cuda(x.X):
+            x = ColVecs(np.ascontiguousarray(np.asarray(x.X).T))
+        if _is_torch_cuda(x.X):
+            xin = x.X if isinstance(x, ColVecs) else x.X.T
+        else:
+            xd = x_as_colvecs(ctx, x)
+            xin = xd.as_torch() if xd.layout == L.COLVECS else xd.as_torch().T
+        out = self.fn(xin)
+        if not (isinstance(out, torch.Tensor) and out.is_cuda and out.dim() == 2 and out.shape[0] == xin.shape[0]):
+            raise L.BLRError(L.E_INVALID, "a TorchFeatureMap must return an (N, D) CUDA tensor")
+        out = out.to(torch.float64).contiguous()
+        return ColVecs(out)  # borrowed by x_as_colvecs -> DeviceMatrix.wrap_torch (orders the library after torch's stream)
+
+
 # ------------------------------------------------------------------------------------------------
 # Inference: logpdf / posterior  (src/bayesian_linear_regression.jl:55-93)
 # ------------------------------------------------------------------------------------------------

@@ -202,6 +202,29 @@ class DeviceMatrix:
         ctx.check(ctx.lib.blr_x_wrap_device(ctx.handle, C.c_void_p(t.data_ptr()), D, N, max(t.stride(0), 1), layout, C.byref(h)))
         return DeviceMatrix(ctx, h, D, N, layout, keepalive=t)
 
+    def as_torch(self):
+        """Zero-copy torch view of the device matrix (the inverse of wrap_torch): ColVecs -> tensor of shape (N, D), RowVecs ->
+        (D, N), row stride = the leading dimension.  torch's current stream is ordered after this context's pending work;
+        the view keeps the handle alive."""
+        import torch
+
+        self.ctx.release_to_torch_stream()
+        ptr, ld = self.device_ptr()
+        rows, cols = (self.N, self.D) if self.layout == L.COLVECS else (self.D, self.N)
+        if rows == 0 or cols == 0:
+            return torch.empty((rows, cols), dtype=torch.float64, device=f"cuda:{self.ctx.device}")
+
+        class _View:
+            pass
+
+        v = _View()
+        v.__cuda_array_interface__ = {"shape": (rows, cols), "typestr": "<f8", "data": (ptr, False), "version": 2,
+                                      "strides": (ld * 8, 8)}
+        v.owner = self
+        t = torch.as_tensor(v, device=f"cuda:{self.ctx.device}")
+        t._blr_owner = self  # the tensor must not outlive the library-owned memory
+        return t
+
     def device_ptr(self) -> Tuple[int, int]:
         p, ld = C.c_void_p(), C.c_int64()
         self.ctx.check(self.ctx.lib.blr_x_device_ptr(self.ctx.handle, self.handle, C.byref(p), C.byref(ld)))

@@ -136,6 +136,16 @@ int blr_vec_synth_targets(blr_ctx* ctx, const blr_x* x, const blr_vec* sigma2, u
  * (replaces ϕ(x) of src/basis_function_regression.jl:41 for ϕ(x) = sqrt(2/D) cos(W x + b)):
  * xin: d_in x N ColVecs; W host D x d_in column-major; b host D; out: new D x N ColVecs handle. */
 int blr_x_rff(blr_ctx* ctx, const blr_x* xin, const double* W, const double* b, int64_t D, blr_x** out);
+/* the general one-layer device feature map  out = scale * act(W x + b)  (blr_x_rff is act = COS, scale = sqrt(2/D)); any
+ * other ϕ (src/basis_function_regression.jl:34-37: an arbitrary callable) stays on the device by producing its output in
+ * device memory and handing it over with blr_x_wrap_device + blr_ctx_wait_stream ("device feature maps"). */
+#define BLR_ACT_COS 0
+#define BLR_ACT_TANH 1
+#define BLR_ACT_RELU 2
+#define BLR_ACT_IDENTITY 3
+#define BLR_ACT_SIN 4
+int blr_x_features(blr_ctx* ctx, const blr_x* xin, const double* W, const double* b, int64_t D, int act, double scale,
+                   blr_x** out);
 
 /* ------------------------------------------------------------------ inference
  * replaces __compute_inference_quantities / logpdf / posterior,

@@ -11,10 +11,29 @@ _device_x(ctx, x::AbstractVector) = x_as_colvecs(x)                           # 
 # Λw kinds (:11-14): Diagonal is sent as its diagonal, everything else as the dense symmetric matrix.
 _prior(f::BayesianLinearRegressor{<:Any,<:Diagonal}) =
     (mw = collect(Float64, f.mw); λ = collect(Float64, f.Λw.diag);
-     (LibBLR.Prior(pointer(mw), LibBLR.LAMBDA_DIAGONAL, pointer(λ), length(mw)), (mw, λ)))
+     (LibBLR.Prior(pointer(mw), LibBLR.LAMBDA_DIAGONAL, pointer(λ), length(mw), length(mw)), (mw, λ)))
 _prior(f::BayesianLinearRegressor) =
     (mw = collect(Float64, f.mw); Λ = Matrix{Float64}(f.Λw);
-     (LibBLR.Prior(pointer(mw), LibBLR.LAMBDA_DENSE, pointer(Λ), size(Λ, 1)), (mw, Λ)))
+     (LibBLR.Prior(pointer(mw), LibBLR.LAMBDA_DENSE, pointer(Λ), size(Λ, 1), length(mw)), (mw, Λ)))
+
+# Device-resident factorisation cached per regressor (the reference re-runs `_cholesky(Λw)` on every predict call, :36,:41,:51;
+# model.py keeps the handle in the Python object).  The Julia struct is immutable and unchanged, so the handle lives in a
+# weak-keyed side table: key = the (mutable) array behind Λw, value = (copy of mw, DevicePost).  `posterior` registers the
+# handle blr_infer returned, so mean / var / cov / rand on a posterior never factorise again.
+const _POST_CACHE = WeakKeyDict{Any,Tuple{Vector{Float64},LibBLR.DevicePost}}()
+_cache_key(Λ::Diagonal) = Λ.diag
+_cache_key(Λ::Symmetric) = parent(Λ)
+_cache_key(Λ::AbstractPDMat) = Λ.mat
+_cache_key(Λ::AbstractMatrix) = Λ
+function _device_post(ctx, f::BayesianLinearRegressor)
+    key = _cache_key(f.Λw)
+    hit = get(_POST_CACHE, key, nothing)
+    hit !== nothing && hit[2].ctx === ctx && hit[1] == f.mw && return hit[2]
+    prior, keep = _prior(f)
+    p = GC.@preserve keep LibBLR.post_create(ctx, prior, length(f.mw))
+    ismutable(key) && (_POST_CACHE[key] = (collect(Float64, f.mw), p))
+    return p
+end
 
 # Σy kinds of FiniteGP: Diagonal(Fill) -> scalar, Diagonal(v) -> device vector, dense -> small-N whitening side path.
 function _noise(ctx, Σy::AbstractMatrix)
@@ -45,7 +64,8 @@ end
 AbstractGPs.logpdf(fx::FiniteBLR, y::AbstractVector{<:Real}) = _infer(fx, y; want_T=false)[1]     # :55-58
 
 function AbstractGPs.posterior(fx::FiniteBLR, y::AbstractVector{<:Real})                           # :60-69
-    _, m′, Λ′, T, _ = _infer(fx, y; want_T=fx.f.Λw isa AbstractPDMat)
+    _, m′, Λ′, T, p = _infer(fx, y; want_T=fx.f.Λw isa AbstractPDMat)
+    _POST_CACHE[Λ′] = (copy(m′), p)          # the returned regressor carries its device factor (keyed by its Λ′ array)
     return BayesianLinearRegressor(m′, __build_Λ(typeof(fx.f.Λw), Λ′, T))
 end
 __build_Λ(_, Λ′, _) = Symmetric(Λ′)                                                                # :92
@@ -54,12 +74,9 @@ __build_Λ(::Type{<:AbstractPDMat}, Λ′, T) = PDMat(Λ′, Cholesky(UpperTrian
 function _predict(fx::FiniteBLR; mean::Bool, var::Bool)
     ctx = LibBLR.default_context()
     x = _device_x(ctx, fx.x)
-    prior, keep1 = _prior(fx.f)
+    size(fx.x isa RowVecs ? fx.x.X' : fx.x.X, 1) == length(fx.f.mw) || throw(DimensionMismatch("size(X, 1) != length(mw)"))
     noise, keep2 = _noise(ctx, fx.Σy)
-    GC.@preserve keep1 keep2 begin
-        p = LibBLR.post_create(ctx, prior, length(fx.f.mw))
-        LibBLR.mean_var(ctx, p, x, noise; mean=mean, var=var)
-    end
+    GC.@preserve keep2 LibBLR.mean_var(ctx, _device_post(ctx, fx.f), x, noise; mean=mean, var=var)
 end
 AbstractGPs.mean(fx::FiniteBLR) = _predict(fx; mean=true, var=false)[1]                            # :33
 AbstractGPs.var(fx::FiniteBLR) = _predict(fx; mean=false, var=true)[2]                             # :40-43
@@ -68,9 +85,8 @@ AbstractGPs.mean_and_var(fx::FiniteBLR) = _predict(fx; mean=true, var=true)     
 function AbstractGPs.cov(fx::FiniteBLR)                                                            # :35-38
     ctx = LibBLR.default_context()
     x = _device_x(ctx, fx.x)
-    prior, keep1 = _prior(fx.f)
     noise, keep2 = _noise(ctx, fx.Σy)
-    GC.@preserve keep1 keep2 Symmetric(LibBLR.cov(ctx, LibBLR.post_create(ctx, prior, length(fx.f.mw)), x, noise))
+    GC.@preserve keep2 Symmetric(LibBLR.cov(ctx, _device_post(ctx, fx.f), x, noise))
 end
 AbstractGPs.mean_and_cov(fx::FiniteBLR) = (mean(fx), cov(fx))                                      # :45
 
@@ -79,7 +95,6 @@ function AbstractGPs.rand(rng::AbstractRNG, fx::FiniteBLR, samples::Int)        
     x = _device_x(ctx, fx.x)
     Zw = randn(rng, length(fx.f.mw), samples)          # drawn FIRST (:51)
     Zy = randn(rng, length(fx.x), samples)             # drawn SECOND (:52)
-    prior, keep1 = _prior(fx.f)
     noise, keep2 = _noise(ctx, fx.Σy)
-    GC.@preserve keep1 keep2 LibBLR.rand_finite(ctx, LibBLR.post_create(ctx, prior, length(fx.f.mw)), x, noise, Zw, Zy)
+    GC.@preserve keep2 LibBLR.rand_finite(ctx, _device_post(ctx, fx.f), x, noise, Zw, Zy)
 end

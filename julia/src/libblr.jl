@@ -6,6 +6,7 @@
 module LibBLR
 
 using LinearAlgebra: PosDefException
+using FillArrays: FillArrays
 
 const libblr = get(ENV, "LIBBLR_CUDA", "libblr_cuda")
 
@@ -19,6 +20,7 @@ struct Prior
     lambda_kind::Cint
     lambda::Ptr{Float64}
     ld::Int64
+    D::Int64                # length(mw) = size(Λw, 1): validated by the library against size(X, 1) (BLR_E_DIM)
 end
 
 struct Noise
@@ -50,7 +52,9 @@ function check(ctx::Context, rc::Cint)
     rc == 0 && return nothing
     rc > 0 && throw(PosDefException(Int(rc)))                    # LAPACK-style info from the device Cholesky
     msg = unsafe_string(ccall((:blr_last_error, libblr), Cstring, (Ptr{Cvoid},), ctx.ptr))
-    error(rc == E_DIM ? "length(y) != size(fx.x.X, 2)" : "libblr_cuda error $rc: $msg")   # ErrorException
+    rc == E_DIM && occursin("length(y)", msg) && error("length(y) != size(fx.x.X, 2)")      # ErrorException (:74)
+    rc == E_DIM && throw(DimensionMismatch(msg))                                             # X' * mw (:33)
+    error("libblr_cuda error $rc: $msg")
 end
 
 # ---- device handles with finalizers ---------------------------------------------------------------
@@ -184,10 +188,11 @@ function apply_weights(ctx::Context, x::DeviceX, w::Vector{Float64})
     return out
 end
 
-end # module
+
 
 
 # ------------------------------------------------------------------------------------------------ several GPUs, one process
+# (inside the module: uses Context, check, libblr, Prior, COLVECS, NOISE_VECTOR unqualified)
 # One Context per device; observations are sharded over them (contiguous column blocks), each device accumulates the
 # statistics of its shard, ONE grouped all-reduce sums them, every device then holds the same posterior
 # (SURVEY.md section 8e).  UNEXECUTED -- see INTEGRATION.md.
@@ -210,7 +215,7 @@ function shard_bounds(N::Integer, P::Integer, r::Integer)
     return lo + 1, lo + q + (r < rem ? 1 : 0)
 end
 
-"posterior + logpdf of ColVecs data X (D x N) sharded over the devices of `mc`; returns (logpdf, m′, Λ′) from device 1"
+"posterior + logpdf of ColVecs data X (D x N) sharded over the devices of `mc`; returns (logpdf, m′, Λ′) from device 1.\nblr_stats_accumulate_host only ENQUEUES (it returns without synchronising), so the devices' copies and kernels overlap."
 function infer_sharded(mc::MultiContext, prior::Prior, X::StridedMatrix{Float64}, y::Vector{Float64}, σ²::Vector{Float64},
                        mw::Vector{Float64})
     D, N = size(X)
@@ -239,3 +244,9 @@ function infer_sharded(mc::MultiContext, prior::Prior, X::StridedMatrix{Float64}
     end
     return lp[], m, Λ
 end
+
+# ---- stream ordering for borrowed device buffers (CUDA.jl arrays wrapped with blr_x_wrap_device)
+wait_stream(ctx::Context, stream::Ptr{Cvoid}) = check(ctx, ccall((:blr_ctx_wait_stream, libblr), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.ptr, stream))
+release_to_stream(ctx::Context, stream::Ptr{Cvoid}) = check(ctx, ccall((:blr_stream_wait_ctx, libblr), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.ptr, stream))
+
+end # module

@@ -4,8 +4,7 @@
 function _device_weights(rng::AbstractRNG, blr::BayesianLinearRegressor, S::Int)
     ctx = LibBLR.default_context()
     Z = randn(rng, length(blr.mw), S)
-    prior, keep = _prior(blr)
-    GC.@preserve keep LibBLR.rand_weights(ctx, LibBLR.post_create(ctx, prior, length(blr.mw)), Z)
+    return LibBLR.rand_weights(ctx, _device_post(ctx, blr), Z)   # cached device factor (bayesian_linear_regression.jl)
 end
 
 function Random.rand(rng::AbstractRNG, b::BLRorBasisFunction)                                      # :27-31

@@ -1,9 +1,9 @@
 #!/usr/bin/env python
-"""One small-shape pass over every kernel family of libblr_cuda, to be run under compute-sanitizer
+"""TEST INFRASTRUCTURE (lives under tests/ because it checks against the oracle).  One small-shape pass over every kernel family of libblr_cuda, to be run under compute-sanitizer
 (memcheck / racecheck / synccheck / initcheck): SURVEY.md section 5 asks for race / failure evidence for kernels that use
 mbarrier rings, setmaxnreg, cross-CTA spin flags and soft grid barriers.  No torch import (keeps the tool's overhead down).
 
-    compute-sanitizer --tool racecheck python tools/sanitize_small.py
+    compute-sanitizer --tool racecheck python tests/sanitize_small.py
 """
 import os
 import sys

@@ -209,7 +209,7 @@ for w in (1,2,3,4,8,12,16):
       timeout 1200 python -m pytest tests/test_gpu_contracts.py -m gpu -q -s -x --timeout 600 > "$OUT/tests_contracts.log" 2>&1; echo "tests_contracts exit $?"; tail -30 "$OUT/tests_contracts.log";;
     sanitize)
       for tool in ${SAN_TOOLS:-memcheck racecheck synccheck}; do
-        BLR_SANITIZE_SET=${SAN_SET:-all} timeout 1500 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_small.py > "$OUT/sanitize_$tool.log" 2>&1
+        BLR_SANITIZE_SET=${SAN_SET:-all} timeout 1500 compute-sanitizer --tool $tool --print-limit 20 python tests/sanitize_small.py > "$OUT/sanitize_$tool.log" 2>&1
         echo "sanitize $tool exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|max rel err|Error|hazard" "$OUT/sanitize_$tool.log" | tail -20
       done;;
     traffic)
