@@ -48,6 +48,7 @@ static __device__ int factor_block_smem(double* Ls, double* rdiag) {
                     a[c] = fma(-a[k], lck, a[c]);
                 }
             }
+            __syncwarp();  // the mirror lanes' loads above precede the stores below (explicit for racecheck; free here)
             if (lane < SB) {
 #pragma unroll
                 for (int c = 0; c < SB; ++c)

