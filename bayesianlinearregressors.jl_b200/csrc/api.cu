@@ -908,6 +908,88 @@ int blr_infer(blr_ctx* ctx, const blr_prior* prior, const blr_x* x, const blr_ve
     return rc;
 }
 
+int blr_logpdf_multi(blr_ctx* ctx, const blr_prior* prior, const blr_x* x, const double* Y_dev, int64_t ldy, int64_t k,
+                     const blr_noise* noise, double* logpdf_out) {
+    CTX_ENTER(ctx);
+    if (!prior || !x || !prior->mw || !prior->lambda || (k > 0 && (!Y_dev || !logpdf_out)) || k < 0)
+        return set_err(ctx, BLR_E_INVALID, "null argument");
+    if (prior->D > 0 && prior->D != x->D) return set_err(ctx, BLR_E_DIM, "size(X, 1) != length(mw)");
+    if (k == 0) return 0;
+    if (ldy < x->N) return set_err(ctx, BLR_E_DIM, "size(Y, 1) != size(fx.x.X, 2)");
+    if (noise && noise->kind == BLR_NOISE_DENSE)
+        return set_err(ctx, BLR_E_INVALID, "blr_logpdf_multi: dense Σy is not supported (loop blr_infer over the columns)");
+    const int64_t D = x->D, N = x->N, K = k - 1;
+    blr_vec y0;  // column 0 goes down the ordinary path: Gram statistics, factorisation, logpdf_0
+    y0.p = const_cast<double*>(Y_dev);
+    y0.n = N;
+    blr_stats* s = nullptr;
+    blr_post* post = nullptr;
+    double* extra = nullptr;  // [R (K x D) | q (K) | zz (K) | q_0 | z_0'z_0]
+    BLR_TRY(blr_stats_create(ctx, D, &s));
+    auto done = [&](int rc) {
+        dev_free(ctx->stream, extra);
+        blr_stats_free(ctx, s);
+        if (post) post_release(post);
+        return rc;
+    };
+    int rc = blr_stats_accumulate(ctx, s, prior->mw, x, &y0, noise);
+    if (rc != 0) return done(rc);
+    if (K > 0) {
+        cudaError_t e = dev_alloc(ctx, &extra, (size_t)(K * D + 2 * K + 2) * sizeof(double));
+        if (e != cudaSuccess) return done(cuda_fail(ctx, e, "cudaMallocAsync(logpdf_multi)"));
+        const double* sig = nullptr;
+        double sig_scalar = 0.0;
+        rc = noise_args(ctx, noise, N, &sig, &sig_scalar, true);
+        if (rc != 0) return done(rc);
+        bool zero = true;
+        for (int64_t i = 0; i < D; ++i)
+            if (prior->mw[i] != 0.0) zero = false;
+        double* pm = nullptr;  // X'mw, shared by every column
+        if (!zero && N > 0) {
+            e = dev_alloc(ctx, &pm, (size_t)N * sizeof(double));
+            if (e != cudaSuccess) return done(cuda_fail(ctx, e, "cudaMallocAsync(pm)"));
+            // blr_stats_accumulate left mw in ctx->small + SMALL_MW (stream-ordered)
+            rc = apply_weights(ctx, x, ctx->small + SMALL_MW, pm);
+        }
+        if (rc == 0) rc = rhs_multi(ctx, x, Y_dev + ldy, ldy, K, sig, sig_scalar, pm, extra, extra + K * D);
+        dev_free(ctx->stream, pm);
+        if (rc != 0) return done(rc);
+    }
+    rc = blr_stats_allreduce(ctx, s);
+    if (rc == 0 && K > 0 && ctx->nccl_comm && ctx->nranks > 1) {
+        NcclApi* a = nccl_api();
+        ncclResult_t r = a->AllReduce(extra, extra, (size_t)(K * D + K), ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+        rc = (r != ncclSuccess) ? nccl_fail(ctx, r, "ncclAllReduce") : nccl_async_check(ctx);
+    }
+    if (rc != 0) return done(rc);
+    rc = infer_solve(ctx, prior, s, logpdf_out, nullptr, nullptr, nullptr, &post);
+    if (rc == BLR_INFO_NOISE) {
+        int info = 1;
+        if (noise && noise->kind == BLR_NOISE_VECTOR && noise->vec) {
+            const int loc = check_noise_vector(ctx, noise->vec->p, noise->vec->n);
+            if (loc != 0) info = loc;
+        }
+        set_err(ctx, info, "observation noise variance is not positive");
+        return done(info);
+    }
+    if (rc != 0 || K == 0) return done(rc);
+    // logpdf_j - logpdf_0 = -1/2 [(q_j - q_0) - (z_j'z_j - z_0'z_0)]: every other term of (:57) is common to the columns
+    double* tail = extra + K * D;
+    rc = forward_solve_multi(ctx, post, extra, K, tail + K);
+    if (rc != 0) return done(rc);
+    std::vector<double> h((size_t)(2 * K + 2));
+    cudaError_t e = cudaMemcpyAsync(tail + 2 * K, s->scal(), sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(tail + 2 * K + 1, ctx->small + SMALL_SC + 2, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(h.data(), tail, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return done(cuda_fail(ctx, e, "download logpdf_multi"));
+    const double q0 = h[2 * K], zz0 = h[2 * K + 1];
+    for (int64_t j = 0; j < K; ++j) logpdf_out[j + 1] = logpdf_out[0] - 0.5 * ((h[j] - q0) - (h[K + j] - zz0));
+    return done(0);
+}
+
 // ---------------------------------------------------------------------------------------------- prediction
 int blr_post_create(blr_ctx* ctx, const blr_prior* prior, int64_t D, blr_post** out) {
     CTX_ENTER(ctx);

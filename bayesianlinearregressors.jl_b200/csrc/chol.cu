@@ -378,6 +378,20 @@ __global__ void finalize_kernel(const double* __restrict__ scal /* q, ℓ, n */,
     }
 }
 
+// Z_j = L^-1 R_j in place for the K columns of R (column j = D contiguous doubles), zz_dev[j] = Z_j'Z_j.  Substitution against
+// the factor itself (no inverse factor): the diagonal 64 x 64 blocks are inverted once, each column is one wavefront launch.
+int forward_solve_multi(blr_ctx* ctx, const blr_post* p, double* R, int64_t K, double* zz_dev) {
+    const int64_t D = p->D, nblk = (D + NB - 1) / NB;
+    BLR_TRY(ensure_dinv(ctx, (size_t)nblk * NB * NB * sizeof(double)));
+    BLR_TRY(trtri_diag_packed(ctx, p->L, D, ctx->dinv));
+    for (int64_t j = 0; j < K; ++j) {
+        BLR_TRY(trsv_lower_forward(ctx, p->L, D, ctx->dinv, R + j * D));
+        dot_self_kernel<<<1, 256, 0, ctx->stream>>>(R + j * D, (int)D, zz_dev + j);
+        BLR_CHECK_LAUNCH(ctx, "dot_self_kernel");
+    }
+    return 0;
+}
+
 void post_release(blr_post* p) {
     if (!p) return;
     dev_free(p->stream, p->mw);

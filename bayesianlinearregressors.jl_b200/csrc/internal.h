@@ -177,6 +177,8 @@ int logdet_from_chol(blr_ctx* ctx, const double* L, int64_t D, double* out_dev);
 int infer_solve(blr_ctx* ctx, const blr_prior* prior, const blr_stats* st, double* logpdf_out, double* m_post,
                 double* T_post, double* L_post, blr_post** post_out);
 int post_from_prior(blr_ctx* ctx, const blr_prior* prior, int64_t D, blr_post** out);
+// Z_j = L^-1 R_j in place (K columns of D contiguous doubles), zz_dev[j] = Z_j'Z_j
+int forward_solve_multi(blr_ctx* ctx, const blr_post* p, double* R, int64_t K, double* zz_dev);
 int post_ensure_W(blr_ctx* ctx, blr_post* p);
 void post_release(blr_post* p);
 
@@ -191,6 +193,10 @@ int apply_weights(blr_ctx* ctx, const blr_x* x, const double* w_dev, double* out
 // C[m, n] = beta * C + Σ_k A[m, k] B[k, n] with arbitrary element strides (small / odd shapes; plain DFMA)
 int gemm_generic(blr_ctx* ctx, int64_t M, int64_t Nn, int64_t K, const double* A, int64_t as_m, int64_t as_k,
                  const double* B, int64_t bs_k, int64_t bs_n, double* C, int64_t cs_m, int64_t cs_n, double beta);
+
+// ---- rhs_multi.cu: R_out[j] = X Σy⁻¹ (Y_j - pm) (K x D, column j contiguous), q_out[j] = (Y_j - pm)' Σy⁻¹ (Y_j - pm); pm = X'mw or nullptr
+int rhs_multi(blr_ctx* ctx, const blr_x* x, const double* Y, int64_t ldy, int64_t K, const double* sigma2,
+              double sigma2_scalar, const double* pm, double* R_out, double* q_out);
 
 // ---- predict_tma.cu
 bool predict_fast_eligible(const blr_post* p, const blr_x* x);

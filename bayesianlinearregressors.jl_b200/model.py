@@ -332,9 +332,43 @@ def _infer(fx: FiniteGP, y, want_logpdf: bool, want_post: bool):
 def logpdf(fx: FiniteGP, y):
     """src/bayesian_linear_regression.jl:55-58 / basis_function_regression.jl:60.  A matrix `Y` (N x k, one
     observation vector per column) returns the k log densities, as AbstractGPs' `logpdf(fx, Y::AbstractMatrix)`."""
-    if isinstance(y, np.ndarray) and y.ndim == 2:
-        return np.array([_infer(fx, np.ascontiguousarray(y[:, j]), True, False)[0] for j in range(y.shape[1])])
+    if (isinstance(y, np.ndarray) or _is_torch_cuda(y)) and y.ndim == 2:
+        return _logpdf_multi(fx, y)
     return _infer(fx, y, True, False)[0]
+
+
+def _logpdf_multi(fx: FiniteGP, Y) -> np.ndarray:
+    """logpdf(fx, Y::AbstractMatrix): one Gram pass, one factorisation, k right-hand sides (blr_logpdf_multi).  Y is a host
+    array or a CUDA tensor of shape (N, k).  Dense Σy (the small-N side path) loops over the columns."""
+    fx = _to_finite_blr(fx)
+    ctx = fx._context()
+    blr = fx.f
+    k = int(Y.shape[1])
+    if k == 0:
+        return np.empty(0)
+    if isinstance(fx.Σy, (Symmetric, PDMat)) or (isinstance(fx.Σy, np.ndarray) and fx.Σy.ndim == 2):
+        cols = Y.T.contiguous() if _is_torch_cuda(Y) else np.ascontiguousarray(np.asarray(Y, dtype=np.float64).T)
+        return np.array([_infer(fx, cols[j], True, False)[0] for j in range(k)])
+    X = x_as_colvecs(ctx, fx.x)
+    if X.D != blr.mw.shape[0]:
+        raise L.DimensionMismatch(L.E_DIM, "size(X, 1) != length(mw)")
+    if Y.shape[0] != X.N:  # src/bayesian_linear_regression.jl:74
+        raise L.DimensionMismatch(L.E_DIM, "length(y) != size(fx.x.X, 2)")
+    if _is_torch_cuda(Y):
+        import torch
+
+        Yt = Y.to(torch.float64).T.contiguous()  # (k, N) row-major == N x k column-major
+        ctx.wait_torch_stream()
+        y_ptr, keep = C.c_void_p(Yt.data_ptr()), Yt
+    else:
+        Yd = DeviceVector.upload(ctx, np.asarray(Y, dtype=np.float64).T.reshape(-1))  # column-major N x k, flattened
+        y_ptr, keep = C.c_void_p(Yd.device_ptr()), Yd
+    noise, keep_noise = make_noise(ctx, fx.Σy, X.N)
+    prior, keep_prior = blr._prior_struct()
+    out = np.empty(k)
+    ctx.check(ctx.lib.blr_logpdf_multi(ctx.handle, C.byref(prior), X.handle, y_ptr, max(X.N, 1), k, C.byref(noise), _ptr(out)))
+    del keep
+    return out
 
 
 def posterior(fx: FiniteGP, y):

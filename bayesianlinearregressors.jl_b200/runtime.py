@@ -268,6 +268,11 @@ class DeviceVector:
         ctx.check(ctx.lib.blr_vec_wrap_device(ctx.handle, C.c_void_p(t.data_ptr()), t.shape[0], C.byref(h)))
         return DeviceVector(ctx, h, t.shape[0], keepalive=t)
 
+    def device_ptr(self) -> int:
+        p = C.c_void_p()
+        self.ctx.check(self.ctx.lib.blr_vec_device_ptr(self.ctx.handle, self.handle, C.byref(p)))
+        return int(p.value or 0)
+
     def download(self) -> np.ndarray:
         out = np.empty(self.n, dtype=np.float64)
         self.ctx.check(self.ctx.lib.blr_vec_download(self.ctx.handle, self.handle, _ptr(out)))

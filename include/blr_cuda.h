@@ -182,6 +182,15 @@ int blr_infer_from_stats(blr_ctx* ctx, const blr_prior* prior, const blr_stats* 
 /* zero + accumulate + allreduce + infer_from_stats in one call. */
 int blr_infer(blr_ctx* ctx, const blr_prior* prior, const blr_x* x, const blr_vec* y, const blr_noise* noise,
               double* logpdf_out, double* m_post, double* T_post, double* L_post, blr_post** post_out);
+/* log marginal likelihood of k observation vectors under one regressor and one set of inputs -- AbstractGPs'
+ * `logpdf(fx, Y::AbstractMatrix)`, the form the reference's conformance test calls (test/bayesian_linear_regression.jl:7-9),
+ * which with the reference's `logpdf` (:55-58) re-runs __compute_inference_quantities (:72-89) once per column.  Only δy (:84)
+ * depends on y: here the Gram pass, the factorisation and the log-determinants run ONCE; every further column costs a share of
+ * one skinny pass R = X Σy⁻¹ (Y - X'mw) over X and one forward solve.
+ *   Y_dev : device, N x k column-major, leading dimension ldy >= N;   logpdf_out : host, k.
+ * Scalar / vector Σy only (dense Σy: BLR_E_INVALID -- loop blr_infer).  Statistics are all-reduced when a communicator is set. */
+int blr_logpdf_multi(blr_ctx* ctx, const blr_prior* prior, const blr_x* x, const double* Y_dev, int64_t ldy, int64_t k,
+                     const blr_noise* noise, double* logpdf_out);
 
 /* ------------------------------------------------------------------ prediction / sampling
  * replaces mean / var / mean_and_var / rand, src/bayesian_linear_regression.jl:33-53,

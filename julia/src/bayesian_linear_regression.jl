@@ -62,6 +62,18 @@ function _infer(fx::FiniteBLR, y::AbstractVector{<:Real}; want_T::Bool)
 end
 
 AbstractGPs.logpdf(fx::FiniteBLR, y::AbstractVector{<:Real}) = _infer(fx, y; want_T=false)[1]     # :55-58
+# AbstractGPs' generic `logpdf(fx, Y::AbstractMatrix)` maps the vector method over the columns, i.e. one full
+# __compute_inference_quantities (:72-89) per column; only δy (:84) depends on y, so the device runs the Gram pass and the
+# factorisation once for all columns (blr_logpdf_multi).  Dense Σy keeps the per-column loop (small-N side path).
+function AbstractGPs.logpdf(fx::FiniteBLR, Y::AbstractMatrix{<:Real})
+    size(Y, 1) == length(fx.x) || throw(error("length(y) != size(fx.x.X, 2)"))            # :74
+    fx.Σy isa Diagonal || return [AbstractGPs.logpdf(fx, collect(Float64, c)) for c in eachcol(Y)]
+    ctx = LibBLR.default_context()
+    x = _device_x(ctx, fx.x)
+    prior, keep1 = _prior(fx.f)
+    noise, keep2 = _noise(ctx, fx.Σy)
+    GC.@preserve keep1 keep2 x LibBLR.logpdf_multi(ctx, prior, x, Matrix{Float64}(Y), noise)
+end
 
 function AbstractGPs.posterior(fx::FiniteBLR, y::AbstractVector{<:Real})                           # :60-69
     _, m′, Λ′, T, p = _infer(fx, y; want_T=fx.f.Λw isa AbstractPDMat)

@@ -111,6 +111,19 @@ function infer(ctx::Context, prior::Prior, x::DeviceX, y::DeviceVec, noise::Nois
     return lp[], m, Λ, T, _post(ctx, h[])
 end
 
+# logpdf of the k columns of Y under one fx (AbstractGPs' logpdf(fx, Y::AbstractMatrix)): one Gram pass, one factorisation
+function logpdf_multi(ctx::Context, prior::Prior, x::DeviceX, Y::Matrix{Float64}, noise::Noise)
+    N, k = size(Y)
+    Yd = upload_vec(ctx, vec(Y))                       # column-major N x k, ld = N
+    p = Ref{Ptr{Float64}}(C_NULL)
+    check(ctx, ccall((:blr_vec_device_ptr, libblr), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Float64}}), ctx.ptr, Yd.ptr, p))
+    out = Vector{Float64}(undef, k)
+    GC.@preserve Yd check(ctx, ccall((:blr_logpdf_multi, libblr), Cint,
+        (Ptr{Cvoid}, Ref{Prior}, Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ref{Noise}, Ptr{Float64}),
+        ctx.ptr, prior, x.ptr, p[], max(N, 1), k, noise, out))
+    return out
+end
+
 # the same from host arrays: blr_stats_create -> blr_stats_accumulate_host -> blr_stats_allreduce -> blr_infer_from_stats
 function infer_host(ctx::Context, prior::Prior, X::StridedMatrix{Float64}, layout::Cint, y::Vector{Float64}, Σy;
                     want_T::Bool=false, chunk::Integer=1 << 16)
