@@ -43,12 +43,13 @@ class Context:
         self._fin = weakref.finalize(self, self.lib.blr_ctx_destroy, h)
 
     # ---- pinned result buffers ---------------------------------------------------------------------
-    def empty_pinned(self, shape, order="F") -> np.ndarray:
-        """np.empty in page-locked memory (large results download at PCIe speed).  Buffers are recycled through a
-        per-context free list once every numpy view of them is gone; small results stay pageable."""
+    def empty_pinned(self, shape, order="F", min_bytes: int = 1 << 15) -> np.ndarray:
+        """np.empty in page-locked memory (results download at PCIe speed and truly asynchronously: a D2H copy into pageable
+        memory is staged by the driver and blocks the host).  Buffers are recycled through a per-context free list once
+        every numpy view of them is gone; results below `min_bytes` stay pageable."""
         n = int(np.prod(shape))
         nbytes = n * 8
-        if nbytes < (1 << 20):
+        if nbytes < min_bytes:
             return np.empty(shape, dtype=np.float64, order=order)
         free = self._pinned_free.setdefault(nbytes, [])
         if free:

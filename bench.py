@@ -101,11 +101,31 @@ def config_dict(args, c, world):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock, power and throttle reasons of one GPU sampled DURING the timed region: NVML in-process every 5 ms (a timed
+    region can be as short as ~10 ms at cfg2 -- `nvidia-smi -lms` needs longer than that just to start), nvidia-smi as the
+    fallback when pynvml is unavailable."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, device: int):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nvml, self.samples, self._stop = [], None, None, [], threading.Event()
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[device]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else device
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self._sample_nvml()  # fail here, not in the thread, if a query is unsupported
+            self.samples.clear()
+            self.t = threading.Thread(target=self._pump_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:  # noqa: BLE001  (no pynvml / NVML error: fall back to the CLI)
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(device), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
@@ -115,11 +135,42 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+        pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.samples.append((sm, pw, int(get(self.h))))
+
+    def _pump_nvml(self):
+        while not self._stop.is_set():
+            try:
+                self._sample_nvml()
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.005)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self._stop.set()
+            self.t.join(timeout=2)
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            n = self.nvml
+            masks = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            seen = 0
+            for _, _, m in self.samples:
+                seen |= m
+            return {"sm_mhz": statistics.median(x[0] for x in self.samples), "sm_max_mhz": self.mx,
+                    "power_w_max": max(x[1] for x in self.samples), "samples": len(self.samples), "source": "nvml, 5 ms period",
+                    "reasons": sorted(k for k, v in masks.items() if seen & v)}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -128,7 +179,6 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             p = [x.strip() for x in r.split(",")]
             if len(p) < 7:
@@ -137,13 +187,13 @@ class ClockSampler:
                 sm.append(float(p[0])); mx.append(float(p[1])); pw.append(float(p[2]))
             except ValueError:
                 continue
-            for nm, val in zip(names, p[3:7]):
+            for nm, val in zip(self.NAMES, p[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "source": "nvidia-smi -lms 100", "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------ host placement

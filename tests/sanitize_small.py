@@ -52,6 +52,11 @@ def one(ctx, D, N, layout, dense, scalar_noise, Nt, S, tag):
     e += [rel(m, mo), rel(v, vo), rel(Y, ref.rand(po(ref.ColVecs(Xt), 0.2), Zw, Zy))]
     Yr = blr.rand(blr.DeviceRNG(3), fp, S)  # device Philox epilogue
     assert np.isfinite(Yr).all()
+    # one-pass multi-column logpdf (rhs_multi_kernel, both layouts; k = 3 is a partial column block)
+    Ym = np.stack([y, 2.0 * y + 1.0, -y], axis=1)
+    lps = blr.logpdf(fx, Ym)
+    fo = ref.BayesianLinearRegressor(mw, Λo)(ref.ColVecs(X), σ2)
+    e += [abs(lps[j] - ref.logpdf(fo, Ym[:, j])) / abs(lps[j]) for j in range(3)]
     print(f"{tag}: D={D} N={N} {layout} dense={dense} scalar={scalar_noise}  max rel err {max(e):.1e}", flush=True)
     assert max(e) < 1e-9, e
 
@@ -71,6 +76,10 @@ def main():
     ]
     if which == "quick":
         cases = cases[3:5]
+    if which.startswith("case:"):  # one case alone (to attribute a sanitizer report to a kernel configuration)
+        one(ctx, *cases[int(which[5:])])
+        print("sanitize_small: single case done", flush=True)
+        return
     for c in cases:
         one(ctx, *c)
     # periodic schedule (soft grid barrier) and the legacy D x D path (wavefront flags)

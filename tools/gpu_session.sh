@@ -209,8 +209,21 @@ for w in (1,2,3,4,8,12,16):
       timeout 1200 python -m pytest tests/test_gpu_contracts.py -m gpu -q -s -x --timeout 600 > "$OUT/tests_contracts.log" 2>&1; echo "tests_contracts exit $?"; tail -30 "$OUT/tests_contracts.log";;
     sanitize)
       for tool in ${SAN_TOOLS:-memcheck racecheck synccheck}; do
-        BLR_SANITIZE_SET=${SAN_SET:-all} timeout 1500 compute-sanitizer --tool $tool --print-limit 20 python tests/sanitize_small.py > "$OUT/sanitize_$tool.log" 2>&1
+        BLR_SANITIZE_SET=${SAN_SET:-all} timeout 1500 compute-sanitizer --tool $tool --print-limit ${PRINT_LIMIT:-20} python tests/sanitize_small.py > "$OUT/sanitize_$tool.log" 2>&1
         echo "sanitize $tool exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|max rel err|Error|hazard" "$OUT/sanitize_$tool.log" | tail -20
+      done;;
+    racecheck_cases)
+      # one racecheck run per TMA case with an unbounded report, reduced to the distinct (write site, read site) pairs
+      for c in ${RC_CASES:-3 4 5 6}; do
+        BLR_SANITIZE_SET=case:$c timeout 900 compute-sanitizer --tool racecheck --print-limit 100000 python tests/sanitize_small.py > "$OUT/racecheck_case$c.log" 2>&1
+        echo "racecheck case $c exit $?: $(grep -E 'RACECHECK SUMMARY|max rel err' "$OUT/racecheck_case$c.log" | tr '\n' ' ')"
+        grep -E "Race reported|and (Read|Write) access" "$OUT/racecheck_case$c.log" | sed -E 's/\+0x[0-9a-f]+//; s/\[[0-9]+ hazards\]//; s/^=+ +//' | sort | uniq -c | sort -rn > "$OUT/racecheck_case${c}_sites.txt"
+        head -12 "$OUT/racecheck_case${c}_sites.txt"
+        gzip -f "$OUT/racecheck_case$c.log"
+      done;;
+    breakdown)
+      for cfg in "256 1048576" "1024 1048576" "64 4194304"; do
+        timeout 300 python tools/step_breakdown.py $cfg 50 2>> "$OUT/breakdown.err" | tee -a "$OUT/breakdown.jsonl"
       done;;
     traffic)
       timeout 1500 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:gram_tma --csv \
