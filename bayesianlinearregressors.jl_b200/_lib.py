@@ -87,7 +87,7 @@ SIGNATURES = {
         [C.c_void_p, C.POINTER(Prior), C.c_void_p, c_double_p, C.c_void_p, C.c_void_p, C.c_void_p, c_void_pp],
     ),
     "blr_logpdf_multi": (C.c_int, [C.c_void_p, C.POINTER(Prior), C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(Noise),
-                                  c_double_p]),
+                                  C.c_void_p]),
     "blr_infer": (
         C.c_int,
         [C.c_void_p, C.POINTER(Prior), C.c_void_p, C.c_void_p, C.POINTER(Noise), c_double_p, C.c_void_p, C.c_void_p,

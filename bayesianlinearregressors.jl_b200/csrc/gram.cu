@@ -47,11 +47,37 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(const double* __rest
         // one warp per observation: the column is contiguous, lanes stride over features.
         const int lane = threadIdx.x & 31;
         const int64_t warps = (int64_t)gridDim.x * (PREP_THREADS / 32);
+        // 16-byte streaming loads with four independent accumulator chains when the columns are 16-byte aligned (D and ld even):
+        // this pass is pure HBM streaming (8 D bytes per observation) and runs serially in front of the Gram kernel
+        const bool vec2 = ((D | ld) & 1) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
+                          (reinterpret_cast<uintptr_t>(mw) & 15) == 0;
         for (int64_t n = (int64_t)blockIdx.x * (PREP_THREADS / 32) + (threadIdx.x >> 5); n < npad; n += warps) {
             if (n < N) {
                 const double* col = X + n * ld;
                 double dot = 0.0;
-                for (int d = lane; d < D; d += 32) dot = fma(col[d], __ldg(mw + d), dot);
+                if (vec2) {
+                    const double2* c2 = reinterpret_cast<const double2*>(col);
+                    const double2* m2 = reinterpret_cast<const double2*>(mw);
+                    const int D2 = D >> 1;
+                    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+                    int i = lane;
+                    for (; i + 32 < D2; i += 64) {
+                        const double2 xa = __ldcs(c2 + i), xb = __ldcs(c2 + i + 32);
+                        const double2 ma = __ldg(m2 + i), mb = __ldg(m2 + i + 32);
+                        d0 = fma(xa.x, ma.x, d0);
+                        d1 = fma(xa.y, ma.y, d1);
+                        d2 = fma(xb.x, mb.x, d2);
+                        d3 = fma(xb.y, mb.y, d3);
+                    }
+                    if (i < D2) {
+                        const double2 xa = __ldcs(c2 + i), ma = __ldg(m2 + i);
+                        d0 = fma(xa.x, ma.x, d0);
+                        d1 = fma(xa.y, ma.y, d1);
+                    }
+                    dot = (d0 + d1) + (d2 + d3);
+                } else {
+                    for (int d = lane; d < D; d += 32) dot = fma(col[d], __ldg(mw + d), dot);
+                }
                 dot = warp_sum(dot);
                 if (lane == 0) {
                     const double v = sigma2 ? sigma2[n] : sigma2_scalar;

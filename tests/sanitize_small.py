@@ -73,6 +73,9 @@ def main():
         (256, 1500, "col", False, True, 300, 70, "TMA Gram unit-noise, rand 2 sample blocks"),
         (192, 1024, "row", True, False, 128, 4, "feature-major ring"),
         (320, 900, "col", True, False, 200, 4, "3 tile rows, multi-segment CTAs, D x D fused nb=5"),
+        # every tile and every pipeline stage FULL (D % 128 == 0, N % 32 == 0, test points % 128 == 0, S == 64): no slot is ever
+        # read beyond what the current phase wrote -- the control for racecheck's reports on the ragged cases above
+        (256, 1536, "col", True, False, 384, 64, "aligned control: full tiles and stages only"),
     ]
     if which == "quick":
         cases = cases[3:5]

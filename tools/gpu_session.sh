@@ -214,7 +214,7 @@ for w in (1,2,3,4,8,12,16):
       done;;
     racecheck_cases)
       # one racecheck run per TMA case with an unbounded report, reduced to the distinct (write site, read site) pairs
-      for c in ${RC_CASES:-3 4 5 6}; do
+      for c in ${RC_CASES:-3 4 5 6 7}; do
         BLR_SANITIZE_SET=case:$c timeout 900 compute-sanitizer --tool racecheck --print-limit 100000 python tests/sanitize_small.py > "$OUT/racecheck_case$c.log" 2>&1
         echo "racecheck case $c exit $?: $(grep -E 'RACECHECK SUMMARY|max rel err' "$OUT/racecheck_case$c.log" | tr '\n' ' ')"
         grep -E "Race reported|and (Read|Write) access" "$OUT/racecheck_case$c.log" | sed -E 's/\+0x[0-9a-f]+//; s/\[[0-9]+ hazards\]//; s/^=+ +//' | sort | uniq -c | sort -rn > "$OUT/racecheck_case${c}_sites.txt"
