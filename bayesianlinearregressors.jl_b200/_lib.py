@@ -137,12 +137,15 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    # LIBBLR_CUDA=<path>: load another build of the SAME library (the strict-arrive sanitizer variant, `make strict`);
+    # the same variable names the library in the Julia glue (julia/src/libblr.jl)
+    path = os.environ.get("LIBBLR_CUDA") or LIB_PATH
+    if not os.path.exists(path):
         raise ImportError(
-            f"{LIB_PATH} is missing: the CUDA extension has not been built "
+            f"{path} is missing: the CUDA extension has not been built "
             "(run `python -c 'import __graft_entry__ as g; g.build()'`).  There is no CPU fallback."
         )
-    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res

@@ -116,8 +116,10 @@ int potrf_lower(blr_ctx* ctx, double* A, int64_t D64, int* info_dev) {
 //     x_j = inv(L_jj) (b_j - Σ_{k<j} L_jk x_k)            (forward;  backward is the transposed mirror image)
 // CTA j consumes x_k as soon as CTA k publishes it (flag = launch epoch, release/acquire through global memory),
 // so the D x D factor is streamed by D/64 SMs at once and the critical path is D/64 short steps instead of one
-// SM reading the whole matrix.  inv(L_jj) comes from trtri_diag_packed_kernel.  CTAs only wait on lower
-// blockIdx (dispatch order), so the grid cannot deadlock even if it were not fully resident.
+// SM reading the whole matrix.  inv(L_jj) comes from trtri_diag_packed_kernel.
+// Deadlock freedom rests on CO-RESIDENCY, not on dispatch order (which CUDA does not guarantee): a CTA spins on flags of other
+// CTAs, so every CTA of the grid must be resident at once.  The grid has D / 64 <= 256 CTAs (D <= 16384) of 256 threads and
+// <= 35 KB of shared memory, of which an SM holds at least two; the launcher checks nblk <= 2 x #SMs and refuses otherwise.
 constexpr int TRSV_THREADS = 256;
 
 __device__ __forceinline__ void wait_flag(const int* flag, int epoch) {
@@ -225,6 +227,7 @@ __global__ void __launch_bounds__(TRSV_THREADS) trsv_wavefront_kernel(const doub
 
 static int trsv_wavefront(blr_ctx* ctx, const double* L, int64_t D, const double* Dinv, double* b, bool trans) {
     const int nblk = (int)((D + NB - 1) / NB);
+    if (nblk > 2 * ctx->sm_count) return set_err(ctx, BLR_E_INVALID, "trsv wavefront: grid would not be co-resident");
     const int epoch = ++ctx->flag_epoch;
     if (trans)
         trsv_wavefront_kernel<true><<<nblk, TRSV_THREADS, 0, ctx->stream>>>(L, D, (int)D, Dinv, b, ctx->d_flags, epoch);

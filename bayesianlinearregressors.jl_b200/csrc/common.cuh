@@ -44,6 +44,33 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// Ring hand-over.  Production: ONE elected lane arrives for its warp after __syncwarp() -- the other lanes' shared-memory accesses
+// are ordered before that arrive by bar.warp.sync (PTX memory model: causality order is transitive), the idiom of every
+// warp-specialised TMA pipeline.  -DBLR_STRICT_ARRIVE builds the variant used to cross-check compute-sanitizer racecheck
+// reports (profiles/r02/sanitizer/): every lane arrives itself and the barrier counts are 32x larger, so no ordering relies on
+// composing bar.warp.sync with mbarrier.arrive.
+#ifdef BLR_STRICT_ARRIVE
+constexpr int RING_LANES = 32;
+#else
+constexpr int RING_LANES = 1;
+#endif
+// consumer warp: finished reading the slot
+__device__ __forceinline__ void ring_release(uint32_t bar, int lane) {
+#ifdef BLR_STRICT_ARRIVE
+    mbar_arrive(bar);
+#else
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+#endif
+}
+// producer warp: announce the bytes its copies will deliver (all lanes' earlier generic stores to the slot included)
+__device__ __forceinline__ void ring_expect(uint32_t bar, uint32_t bytes, int lane) {
+    if (lane == 0) mbar_arrive_expect_tx(bar, bytes);
+#ifdef BLR_STRICT_ARRIVE
+    else mbar_arrive(bar);
+#endif
+    __syncwarp();
+}
 // 1-D bulk async copy global -> shared, completion signalled on an mbarrier (TMA engine).
 // dst/src 16-byte aligned, bytes a multiple of 16.
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {

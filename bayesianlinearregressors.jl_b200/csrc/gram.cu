@@ -247,8 +247,7 @@ __device__ __forceinline__ void run_segment(double (&acc)[8][4][2], double& racc
                 racc = fma(S.a[kl * Stage<KT, ROW>::SK + rm * Stage<KT, ROW>::SM], S.t[kl], racc);
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&sm.empty[stg]));
+        ring_release(smem_u32(&sm.empty[stg]), lane);
     }
 }
 
@@ -306,8 +305,7 @@ __device__ __forceinline__ void run_segment_cs(double (&acc)[16][2][2], double& 
                 racc = fma(S.a[kl * LDT + rm], S.t[kl], racc);
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&sm.empty[stg]));
+        ring_release(smem_u32(&sm.empty[stg]), lane);
     }
 }
 
@@ -360,8 +358,7 @@ __device__ __forceinline__ void run_segment_rp(double (&acc)[17][2], double& rac
             const int kl = rhalf * (KT / 2) + k;
             racc = fma(S.a[kl * Stage<KT, ROW>::SK + rm * Stage<KT, ROW>::SM], S.t[kl], racc);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&sm.empty[stg]));
+        ring_release(smem_u32(&sm.empty[stg]), lane);
     }
 }
 
@@ -409,8 +406,8 @@ __global__ void __launch_bounds__(ROW ? gk::THREADS_ROW : gk::THREADS, 1) gram_t
     }
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) {
-            mbar_init(smem_u32(&sm.full[i]), NPRODUCERS);
-            mbar_init(smem_u32(&sm.empty[i]), CONSUMER_WARPS);
+            mbar_init(smem_u32(&sm.full[i]), NPRODUCERS * RING_LANES);
+            mbar_init(smem_u32(&sm.empty[i]), CONSUMER_WARPS * RING_LANES);
         }
         mbar_fence_init();
     }
@@ -472,9 +469,7 @@ __global__ void __launch_bounds__(ROW ? gk::THREADS_ROW : gk::THREADS, 1) gram_t
                         // feature-major input: one copy per feature row of the panel (its kc observations); this warp
                         // owns rows [64 half, 64 half + 64) of its panel, the first warp of a panel also brings s / t
                         const int my_rows = have_panel ? max(0, min(TM / 2, rows - half * (TM / 2))) : 0;
-                        if (lane == 0)
-                            mbar_arrive_expect_tx(bar, (uint32_t)kc * (uint32_t)my_rows * 8u + (half == 0 ? KT * 8u : 0u));
-                        __syncwarp();
+                        ring_expect(bar, (uint32_t)kc * (uint32_t)my_rows * 8u + (half == 0 ? KT * 8u : 0u), lane);
                         double* panel = pw == 0 ? S.a : S.b;
                         const int r0 = pw == 0 ? i0 : j0;
 #pragma unroll
@@ -494,9 +489,7 @@ __global__ void __launch_bounds__(ROW ? gk::THREADS_ROW : gk::THREADS, 1) gram_t
                         const int kcnt = diag ? KT / 4 : KT / 2;
                         const int my_k = (diag || have_panel) ? max(0, min(kcnt, kc - kbeg)) : 0;
                         const int rws = diag ? rowsA : rows;
-                        if (lane == 0)
-                            mbar_arrive_expect_tx(bar, (uint32_t)my_k * (uint32_t)rws * 8u + (half == 0 ? KT * 8u : 0u));
-                        __syncwarp();
+                        ring_expect(bar, (uint32_t)my_k * (uint32_t)rws * 8u + (half == 0 ? KT * 8u : 0u), lane);
                         const int kl = kbeg + lane;
                         if (lane < my_k)
                             bulk_g2s(smem_u32(((diag || pw == 0) ? S.a : S.b) + kl * LDT),

@@ -134,8 +134,8 @@ __global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams
     }
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) {
-            mbar_init(smem_u32(&sm.full[i]), PRODUCER_WARPS);
-            mbar_init(smem_u32(&sm.empty[i]), CONSUMER_WARPS);
+            mbar_init(smem_u32(&sm.full[i]), PRODUCER_WARPS * RING_LANES);
+            mbar_init(smem_u32(&sm.empty[i]), CONSUMER_WARPS * RING_LANES);
         }
         mbar_fence_init();
     }
@@ -169,9 +169,7 @@ __global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams
                     const int kc = min(KT, p.D - k0);                 // features present (D even => kc even)
                     const bool with_mw = (ps == npass - 1);
                     if (pw < 2) {  // 8 columns of W each
-                        if (lane == 0)
-                            mbar_arrive_expect_tx(bar, (uint32_t)(KT / 2) * rows * 8u + ((pw == 0 && with_mw) ? KT * 8u : 0u));
-                        __syncwarp();
+                        ring_expect(bar, (uint32_t)(KT / 2) * rows * 8u + ((pw == 0 && with_mw) ? KT * 8u : 0u), lane);
                         if (lane < KT / 2) {
                             const int kr = pw * (KT / 2) + lane;
                             bulk_g2s(smem_u32(&S.a[kr * C::LDA + (r_lo - r_base)]), p.Wp + (int64_t)(k0 + kr) * p.ldw + r_lo,
@@ -181,8 +179,7 @@ __global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams
                     } else {       // 16 points each
                         const int pbase = (pw - 2) * (NP / 2);
                         const int my_pts = max(0, min(NP / 2, npts - pbase));
-                        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)my_pts * kc * 8u);
-                        __syncwarp();
+                        ring_expect(bar, (uint32_t)my_pts * kc * 8u, lane);
                         if (lane < my_pts)
                             bulk_g2s(smem_u32(&S.b[(pbase + lane) * LDB]), p.X + (p0 + pbase + lane) * p.ld + k0,
                                      (uint32_t)kc * 8u, bar);
@@ -238,8 +235,7 @@ __global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams
 #pragma unroll
                     for (int j = 0; j < PP; ++j) macc[j] = fma(mwk, S.b[(PP * mpg + j) * LDB + mk], macc[j]);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&sm.empty[stg]));
+                ring_release(smem_u32(&sm.empty[stg]), lane);
             }
             // fold this pass: squares over the warp's rows (registers, then the 8 fragment rows by shuffle) into the
             // warp's per-point slots in shared memory (each slot has a single owner lane: no synchronisation needed)
@@ -394,8 +390,8 @@ __global__ void __launch_bounds__(rk::THREADS, 1) rand_tma_kernel(const RandPara
     }
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) {
-            mbar_init(smem_u32(&sm.full[i]), PRODUCER_WARPS);
-            mbar_init(smem_u32(&sm.empty[i]), CONSUMER_WARPS);
+            mbar_init(smem_u32(&sm.full[i]), PRODUCER_WARPS * RING_LANES);
+            mbar_init(smem_u32(&sm.empty[i]), CONSUMER_WARPS * RING_LANES);
         }
         mbar_fence_init();
     }
@@ -422,8 +418,7 @@ __global__ void __launch_bounds__(rk::THREADS, 1) rand_tma_kernel(const RandPara
                     const uint32_t bar = smem_u32(&sm.full[stg]);
                     const int kc = min(KT, p.D - k0);
                     const int my_pts = max(0, min(TP / 4, npts - pw * (TP / 4)));
-                    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)my_pts * kc * 8u + (uint32_t)(KT / 4) * TS * 8u);
-                    __syncwarp();
+                    ring_expect(bar, (uint32_t)my_pts * kc * 8u + (uint32_t)(KT / 4) * TS * 8u, lane);
                     {
                         const int pt = pw * (TP / 4) + lane;
                         if (pt < npts) bulk_g2s(smem_u32(&S.a[pt * LDA]), p.X + (p0 + pt) * p.ld + k0, (uint32_t)kc * 8u, bar);
@@ -469,8 +464,7 @@ __global__ void __launch_bounds__(rk::THREADS, 1) rand_tma_kernel(const RandPara
 #pragma unroll
                         for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&sm.empty[stg]));
+                ring_release(smem_u32(&sm.empty[stg]), lane);
             }
             // epilogue: add the observation noise and store (column-major N x S)
 #pragma unroll

@@ -76,6 +76,9 @@ def main():
         # every tile and every pipeline stage FULL (D % 128 == 0, N % 32 == 0, test points % 128 == 0, S == 64): no slot is ever
         # read beyond what the current phase wrote -- the control for racecheck's reports on the ragged cases above
         (256, 1536, "col", True, False, 384, 64, "aligned control: full tiles and stages only"),
+        # the cases above give each of the 148 Gram CTAs at most ONE pipeline stage: this one makes every CTA run ~10 stages
+        # through its 3-slot ring (slot reuse = the empty-barrier hand-over), still with full tiles and stages only
+        (256, 16384, "col", True, False, 384, 64, "aligned, Gram ring slots reused"),
     ]
     if which == "quick":
         cases = cases[3:5]

@@ -221,6 +221,16 @@ for w in (1,2,3,4,8,12,16):
         head -12 "$OUT/racecheck_case${c}_sites.txt"
         gzip -f "$OUT/racecheck_case$c.log"
       done;;
+    racecheck_strict)
+      # the same cases against the strict-arrive build (every lane arrives on the ring mbarriers itself; csrc/Makefile `strict`)
+      for c in ${RC_CASES:-4 7 8}; do
+        LIBBLR_CUDA=$PWD/bayesianlinearregressors.jl_b200/csrc/libblr_cuda_strict.so BLR_SANITIZE_SET=case:$c timeout 900 \
+          compute-sanitizer --tool racecheck --print-limit 100000 python tests/sanitize_small.py > "$OUT/racecheck_strict_case$c.log" 2>&1
+        echo "racecheck STRICT case $c exit $?: $(grep -E 'RACECHECK SUMMARY|max rel err' "$OUT/racecheck_strict_case$c.log" | tr '\n' ' ')"
+        grep -E "Race reported|and (Read|Write) access" "$OUT/racecheck_strict_case$c.log" | sed -E 's/\+0x[0-9a-f]+//; s/\[[0-9]+ hazards\]//; s/^=+ +//' | sort | uniq -c | sort -rn > "$OUT/racecheck_strict_case${c}_sites.txt"
+        head -6 "$OUT/racecheck_strict_case${c}_sites.txt"
+        gzip -f "$OUT/racecheck_strict_case$c.log"
+      done;;
     breakdown)
       for cfg in "256 1048576" "1024 1048576" "64 4194304"; do
         timeout 300 python tools/step_breakdown.py $cfg 50 2>> "$OUT/breakdown.err" | tee -a "$OUT/breakdown.jsonl"
