@@ -80,6 +80,21 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
         : "memory");
 }
 
+// 2-D tiled TMA load (tensor map built on the host by make_tmap_2d_f64, predict_tma.cu): box -> shared memory, completion on
+// an mbarrier.  c0 = coordinate along the contiguous (inner) dimension, c1 = along the outer one; elements outside the tensor
+// are filled with zeros and still count towards the transaction bytes (always the full box).
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+// Offset (in doubles) of element (row p, column k) of a box with 16 doubles (128 bytes) per row that TMA stored with
+// CU_TENSOR_MAP_SWIZZLE_128B: the 16-byte chunk index (k >> 1) is XORed with the row index modulo 8.  The destination must be
+// 1024-byte aligned.  With p = 8 j + g the eight rows g = 0..7 of an m8n8k4 fragment land in eight different chunks: the
+// fragment load is conflict-free (two wavefronts for 32 x 8 bytes) although the rows are a dense 128 bytes apart.
+__device__ __forceinline__ int swz128(int p, int k) { return p * 16 + ((((k >> 1) ^ (p & 7)) << 1) | (k & 1)); }
+
 // ------------------------------------------------------------------ fp64 tensor core
 // D(8x8) += A(8x4, row) * B(4x8, col).  Fragment ownership (PTX ISA, mma.m8n8k4 .f64):
 //   a  = A[lane>>2][lane&3]     b = B[lane&3][lane>>2]     c[0..1] = C[lane>>2][2*(lane&3) + {0,1}]

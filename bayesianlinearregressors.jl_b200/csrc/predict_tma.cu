@@ -8,18 +8,23 @@
 // Shape of the computation: α = W X is a triangular GEMM with M = D rows, N = points, K = D.  One persistent CTA
 // per SM owns tiles of 32 points and keeps α (up to 512 rows x 32 points = 128 KB) in registers as DMMA.8x8x4
 // accumulators: 8 consumer warps, warp tile 64 rows x 32 points.  The K dimension is streamed in stages of 16:
-//   A operand = 16 columns of W (rows >= the stage's first non-zero row), [k][row] in shared memory,
-//   B operand = 16 features of the 32 points, [point][k] in shared memory,
-// both filled by TMA bulk copies from a producer warp through a 3-stage mbarrier ring.  X is read from HBM exactly
+//   A operand = 16 columns of W (rows >= the stage's first non-zero row), [k][row] in shared memory, 1-D bulk copies (2 KB each),
+//   B operand = 16 features of the tile's points, [point][k] in shared memory: ONE 2-D tiled TMA load per producer warp and
+//               stage (cp.async.bulk.tensor.2d, tensor map over X, 128-byte swizzle instead of row padding, ragged edges
+//               zero-filled by the hardware) -- round 1 issued one 128-byte bulk copy per point, 64 per stage, and the
+//               serial issue of those copies (~100 cycles apiece) was as long as a stage takes to consume,
+// through a 3-stage mbarrier ring.  X is read from HBM exactly
 // once; W (2 MB at D = 512) streams from L2.
 // Triangular balance: warp w owns the 8-row blocks {w, 15 - w, 16 + w, 31 - w, ...}, so every warp loses sub-tiles
 // at the same rate as k advances; which sub-tile rows are live is a compile-time template parameter (run-time predication
 // of mma.sync serialises the tensor pipe, see gram.cu).
 // D > 512 is handled in row passes of 512 rows (the point tile is re-streamed per pass).
+#include <cuda.h>  // CUtensorMap types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked
 #include <math.h>
 #include <stdlib.h>
 
 #include <algorithm>
+#include <string>
 
 #include "common.cuh"
 #include "internal.h"
@@ -29,10 +34,10 @@ namespace blr {
 namespace vk {
 constexpr int KT = 16;          // features per stage
 constexpr int STAGES = 3;
-constexpr int LDB = KT + 4;     // B row stride (doubles): == 4 mod 16
+static_assert(KT == 16, "the point tile is one 128-byte swizzle span (16 doubles) per point");
 constexpr int CONSUMER_WARPS = 8;
 // cp.async.bulk is a uniform-datapath instruction: the per-lane copies of a warp are issued one after another.
-// Four producer warps (A columns 0-7 | A columns 8-15 | points 0-15 | points 16-31) keep the issue rate ahead of
+// Four producer warps (A columns 0-7 | A columns 8-15 | first half of the points | second half) keep the issue rate ahead of
 // the consumers; 12 warps x 168 registers is exactly the register file.
 constexpr int PRODUCER_WARPS = 4;
 constexpr int THREADS = (CONSUMER_WARPS + PRODUCER_WARPS) * 32;
@@ -44,9 +49,9 @@ struct Cfg {
     static constexpr int R = MI * 64;      // rows of α per pass
     static constexpr int LDA = R + 4;      // A row stride (doubles): == 4 mod 16
     static constexpr int NI = NP / 8;      // 8-point blocks per tile
-    struct __align__(16) Stage {
+    struct __align__(1024) Stage {
+        double b[NP * KT];    // [point][k], 128 bytes per point, 128-byte TMA swizzle (swz128); 1024-byte aligned
         double a[KT * LDA];   // [k][row - r_base]
-        double b[NP * LDB];   // [point][k]
         double mw[KT];
     };
     struct Smem {
@@ -63,9 +68,7 @@ struct VarParams {
     const double* Wp;   // padded inverse factor: ldw x dk, column-major, zeros outside the lower triangle / beyond D
     int64_t ldw;        // multiple of R
     int D;
-    const double* X;    // ColVecs
-    int64_t ld;
-    int64_t N;
+    int64_t N;          // test points (ColVecs, reached through the tensor map)
     const double* mwp;  // prior mean padded with zeros to a multiple of KT
     const double* sigma2;
     double sigma2_scalar;
@@ -76,12 +79,11 @@ struct VarParams {
 // one stage for one consumer warp; sub-tile rows mi >= M0 are live
 template <int MI, int NI, int M0>
 __device__ __forceinline__ void var_consume(double (&acc)[MI][NI][2], const double* __restrict__ As,
-                                            const double* __restrict__ Bs, int warp, int g, int kq) {
+                                            const double* __restrict__ Bs, int warp, int g, int kq, const int (&boff)[4]) {
     using C = vk::Cfg<MI, NI * 8>;
     // row block of (warp, mi): 8 mi + warp for even mi, 8 mi + 7 - warp for odd mi (see var_tma_kernel)
     const double* Ap0 = As + warp * 8 + g;
     const double* Ap1 = As + (7 - warp) * 8 + g;
-    const double* Bp = Bs + g * vk::LDB;
 #pragma unroll
     for (int kk = 0; kk < vk::KT / 4; ++kk) {
         const int kl = kk * 4 + kq;
@@ -89,7 +91,7 @@ __device__ __forceinline__ void var_consume(double (&acc)[MI][NI][2], const doub
 #pragma unroll
         for (int mi = M0; mi < MI; ++mi) a[mi] = ((mi & 1) ? Ap1 : Ap0)[kl * C::LDA + mi * 64];
 #pragma unroll
-        for (int ni = 0; ni < NI; ++ni) b[ni] = Bp[ni * 8 * vk::LDB + kl];
+        for (int ni = 0; ni < NI; ++ni) b[ni] = Bs[ni * 8 * vk::KT + boff[kk]];  // point 8 ni + g, feature 4 kk + kq
 #pragma unroll
         for (int mi = M0; mi < MI; ++mi)
 #pragma unroll
@@ -99,16 +101,16 @@ __device__ __forceinline__ void var_consume(double (&acc)[MI][NI][2], const doub
 
 template <int MI, int NI>
 __device__ __forceinline__ void var_consume_dispatch(double (&acc)[MI][NI][2], const double* As, const double* Bs,
-                                                     int warp, int g, int kq, int m0) {
+                                                     int warp, int g, int kq, int m0, const int (&boff)[4]) {
     // warp-uniform compare chain (a switch compiles to an indirect branch, measured 2.6 % slower)
-    if (m0 <= 0) var_consume<MI, NI, 0>(acc, As, Bs, warp, g, kq);
-    else if (m0 == 1) var_consume<MI, NI, (1 < MI ? 1 : MI)>(acc, As, Bs, warp, g, kq);
-    else if (m0 == 2) var_consume<MI, NI, (2 < MI ? 2 : MI)>(acc, As, Bs, warp, g, kq);
-    else if (m0 == 3) var_consume<MI, NI, (3 < MI ? 3 : MI)>(acc, As, Bs, warp, g, kq);
-    else if (m0 == 4) var_consume<MI, NI, (4 < MI ? 4 : MI)>(acc, As, Bs, warp, g, kq);
-    else if (m0 == 5) var_consume<MI, NI, (5 < MI ? 5 : MI)>(acc, As, Bs, warp, g, kq);
-    else if (m0 == 6) var_consume<MI, NI, (6 < MI ? 6 : MI)>(acc, As, Bs, warp, g, kq);
-    else if (m0 == 7) var_consume<MI, NI, (7 < MI ? 7 : MI)>(acc, As, Bs, warp, g, kq);
+    if (m0 <= 0) var_consume<MI, NI, 0>(acc, As, Bs, warp, g, kq, boff);
+    else if (m0 == 1) var_consume<MI, NI, (1 < MI ? 1 : MI)>(acc, As, Bs, warp, g, kq, boff);
+    else if (m0 == 2) var_consume<MI, NI, (2 < MI ? 2 : MI)>(acc, As, Bs, warp, g, kq, boff);
+    else if (m0 == 3) var_consume<MI, NI, (3 < MI ? 3 : MI)>(acc, As, Bs, warp, g, kq, boff);
+    else if (m0 == 4) var_consume<MI, NI, (4 < MI ? 4 : MI)>(acc, As, Bs, warp, g, kq, boff);
+    else if (m0 == 5) var_consume<MI, NI, (5 < MI ? 5 : MI)>(acc, As, Bs, warp, g, kq, boff);
+    else if (m0 == 6) var_consume<MI, NI, (6 < MI ? 6 : MI)>(acc, As, Bs, warp, g, kq, boff);
+    else if (m0 == 7) var_consume<MI, NI, (7 < MI ? 7 : MI)>(acc, As, Bs, warp, g, kq, boff);
     // m0 >= MI: nothing live for this warp in this stage
 }
 
@@ -119,12 +121,13 @@ __device__ __forceinline__ int var_stage_k0(int s, int nst) {
 }
 
 template <int MI, int NP>
-__global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams p) {
+__global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams p, const __grid_constant__ CUtensorMap tmx) {
     using namespace vk;
     using C = Cfg<MI, NP>;
     constexpr int NI = C::NI;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    typename C::Smem& sm = *reinterpret_cast<typename C::Smem*>(smem_raw);
+    extern __shared__ unsigned char smem_raw[];
+    // the swizzled point tiles need 1024-byte alignment: align by hand (the launcher asks for 1 KB more than sizeof(Smem))
+    typename C::Smem& sm = *reinterpret_cast<typename C::Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     {
@@ -152,7 +155,6 @@ __global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t p0 = tile * NP;
-            const int npts = (int)min((int64_t)NP, p.N - p0);
             for (int ps = 0; ps < npass; ++ps) {
                 const int r_base = ps * C::R;
                 const int kmax = min(p.D, r_base + C::R);  // W[row][k] = 0 for k > row
@@ -166,7 +168,6 @@ __global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams
                     const uint32_t bar = smem_u32(&sm.full[stg]);
                     const int r_lo = max(r_base, (k0 / 64) * 64);     // first row that can be non-zero in this stage
                     const int rows = r_base + C::R - r_lo;
-                    const int kc = min(KT, p.D - k0);                 // features present (D even => kc even)
                     const bool with_mw = (ps == npass - 1);
                     if (pw < 2) {  // 8 columns of W each
                         ring_expect(bar, (uint32_t)(KT / 2) * rows * 8u + ((pw == 0 && with_mw) ? KT * 8u : 0u), lane);
@@ -176,13 +177,11 @@ __global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams
                                      (uint32_t)rows * 8u, bar);
                         }
                         if (lane == 0 && pw == 0 && with_mw) bulk_g2s(smem_u32(S.mw), p.mwp + k0, KT * 8u, bar);
-                    } else {       // 16 points each
+                    } else {       // half of the tile's points each: one 2-D box {KT features, NP / 2 points}; whatever lies
+                                   // beyond D or N is zero-filled by the TMA unit and still counted, so the byte count is fixed
                         const int pbase = (pw - 2) * (NP / 2);
-                        const int my_pts = max(0, min(NP / 2, npts - pbase));
-                        ring_expect(bar, (uint32_t)my_pts * kc * 8u, lane);
-                        if (lane < my_pts)
-                            bulk_g2s(smem_u32(&S.b[(pbase + lane) * LDB]), p.X + (p0 + pbase + lane) * p.ld + k0,
-                                     (uint32_t)kc * 8u, bar);
+                        ring_expect(bar, (uint32_t)(NP / 2) * KT * 8u, lane);
+                        if (lane == 0) tma_load_2d(smem_u32(&S.b[pbase * KT]), &tmx, k0, (int)(p0 + pbase), bar);
                     }
                 }
             }
@@ -193,8 +192,11 @@ __global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams
     // ---------------------------------------------------------------- consumer warps (DMMA)
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");  // 128 x 40 + 256 x 232 = 384 x 168
     const int g = lane >> 2, kq = lane & 3;
+    int boff[4];  // swizzled offset of (point g, feature 4 kk + kq) within an 8-point block of the point tile
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) boff[kk] = swz128(g, kk * 4 + kq);
     constexpr int PP = NP / 16;               // mean: points per thread
-    const int mk = tid & 15, mpg = tid >> 4;  // mean: feature within the stage, point group (conflict-free smem reads)
+    const int mk = tid & 15, mpg = tid >> 4;  // mean: feature within the stage, point group
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t p0 = tile * NP;
@@ -229,11 +231,11 @@ __global__ void __launch_bounds__(vk::THREADS, 1) var_tma_kernel(const VarParams
                     m0 = min(ms, MI);
                     if (ms < MI && 8 * ((ms & 1) ? 7 - warp : warp) < rem) ++m0;
                 }
-                var_consume_dispatch<MI, NI>(acc, S.a, S.b, warp, g, kq, m0);
+                var_consume_dispatch<MI, NI>(acc, S.a, S.b, warp, g, kq, m0, boff);
                 if (ps == npass - 1) {  // the last row pass streams every feature k < D
                     const double mwk = S.mw[mk];
 #pragma unroll
-                    for (int j = 0; j < PP; ++j) macc[j] = fma(mwk, S.b[(PP * mpg + j) * LDB + mk], macc[j]);
+                    for (int j = 0; j < PP; ++j) macc[j] = fma(mwk, S.b[swz128(PP * mpg + j, mk)], macc[j]);
                 }
                 ring_release(smem_u32(&sm.empty[stg]), lane);
             }
@@ -287,21 +289,54 @@ __global__ void pad_inverse_factor_kernel(const double* __restrict__ W, int D, d
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dk; i += gridDim.x * blockDim.x) mwp[i] = (i < D) ? mw[i] : 0.0;
 }
 
+// Tensor map of a column-major fp64 matrix for 2-D tiled TMA loads: `inner` contiguous elements per column, `outer` columns
+// `ld` elements apart, boxes of box_inner x box_outer elements stored with the 128-byte swizzle (box_inner * 8 <= 128 bytes),
+// out-of-range elements read as zero.  cuTensorMapEncodeTiled is a host-side encoder; it is looked up through the runtime
+// (cudaGetDriverEntryPoint) so the library keeps linking against nothing but cudart.
+static int make_tmap_2d_f64(blr_ctx* ctx, CUtensorMap* out, const double* base, uint64_t inner, uint64_t outer, uint64_t ld,
+                            uint32_t box_inner, uint32_t box_outer) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        BLR_CUDA_OK(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn) return set_err(ctx, BLR_E_CUDA, "cuTensorMapEncodeTiled is not available");
+        encode = (encode_fn)fn;
+    }
+    if (box_inner * 8u > 128u || box_inner > 256u || box_outer > 256u || (ld & 1) || (reinterpret_cast<uintptr_t>(base) & 15) ||
+        outer >= (1ull << 31) || inner >= (1ull << 31))
+        return set_err(ctx, BLR_E_INVALID, "matrix not addressable by a 2-D tensor map");
+    const cuuint64_t dims[2] = {inner, outer};
+    const cuuint64_t strides[1] = {ld * sizeof(double)};  // bytes between columns (a multiple of 16: ld is even)
+    const cuuint32_t box[2] = {box_inner, box_outer};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(ctx, BLR_E_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return 0;
+}
+
 template <int MI, int NP>
-static int launch_var_tma(blr_ctx* ctx, const VarParams& vp) {
+static int launch_var_tma(blr_ctx* ctx, const VarParams& vp, const blr_x* x) {
     using C = vk::Cfg<MI, NP>;
-    const int smem = (int)sizeof(typename C::Smem);
+    const int smem = (int)sizeof(typename C::Smem) + 1024;  // + slack for the in-kernel 1024-byte alignment
     BLR_CUDA_OK(ctx, cudaFuncSetAttribute(var_tma_kernel<MI, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUtensorMap tmx;  // test points: D features (contiguous) x N points; one box = 16 features of half a point tile
+    BLR_TRY(make_tmap_2d_f64(ctx, &tmx, x->p, (uint64_t)x->D, (uint64_t)x->N, (uint64_t)x->ld, vk::KT, NP / 2));
     const int64_t ntiles = (vp.N + NP - 1) / NP;
     const int grid = (int)std::min<int64_t>(ntiles, ctx->sm_count);
-    var_tma_kernel<MI, NP><<<grid, vk::THREADS, smem, ctx->stream>>>(vp);
+    var_tma_kernel<MI, NP><<<grid, vk::THREADS, smem, ctx->stream>>>(vp, tmx);
     BLR_CHECK_LAUNCH(ctx, "var_tma_kernel");
     return 0;
 }
 
 bool predict_fast_eligible(const blr_post* p, const blr_x* x) {
     return x->layout == BLR_COLVECS && p->D >= 128 && (p->D % 2) == 0 && (x->ld % 2) == 0 &&
-           (reinterpret_cast<uintptr_t>(x->p) & 15) == 0 && x->N >= 32;
+           (reinterpret_cast<uintptr_t>(x->p) & 15) == 0 && x->N >= 32 && x->N < (1ll << 31);
 }
 
 int predict_mean_var_fast(blr_ctx* ctx, blr_post* p, const blr_x* x, const double* sigma2, double sigma2_scalar,
@@ -322,16 +357,14 @@ int predict_mean_var_fast(blr_ctx* ctx, blr_post* p, const blr_x* x, const doubl
     vp.Wp = p->Wp;
     vp.ldw = ldw;
     vp.D = D;
-    vp.X = x->p;
-    vp.ld = x->ld;
     vp.N = x->N;
     vp.mwp = p->Wp + ldw * dk;
     vp.sigma2 = sigma2;
     vp.sigma2_scalar = sigma2_scalar;
     vp.mean = mean_dev;
     vp.var = var_dev;
-    if (MI == 8) return launch_var_tma<8, 32>(ctx, vp);
-    return wide ? launch_var_tma<4, 64>(ctx, vp) : launch_var_tma<4, 32>(ctx, vp);
+    if (MI == 8) return launch_var_tma<8, 32>(ctx, vp, x);
+    return wide ? launch_var_tma<4, 64>(ctx, vp, x) : launch_var_tma<4, 32>(ctx, vp, x);
 }
 
 
@@ -347,14 +380,14 @@ constexpr int TP = 128;         // points per tile
 constexpr int TS = 64;          // samples per block
 constexpr int KT = 32;          // features per stage
 constexpr int STAGES = 4;
-constexpr int LDA = KT + 4;     // [point][k]
 constexpr int LDB = TS + 4;     // [k][sample]
 constexpr int CONSUMER_WARPS = 8;
-constexpr int PRODUCER_WARPS = 4;  // UBLKCP is a uniform-datapath op: per-lane copies serialise, so split them over 4 warps
+constexpr int PRODUCER_WARPS = 4;  // each: ONE 2-D TMA box (16 features x 64 points) + 8 bulk copies of sample-weight rows
+static_assert(KT == 32 && TP == 128, "producer warp pw loads feature half (pw & 1) of point half (pw >> 1)");
 constexpr int THREADS = (CONSUMER_WARPS + PRODUCER_WARPS) * 32;
-struct __align__(16) Stage {
-    double a[TP * LDA];
-    double b[KT * LDB];
+struct __align__(1024) Stage {
+    double a[KT / 16][TP * 16];  // points: two sub-tiles of 16 features, [point][k] with the 128-byte TMA swizzle (swz128)
+    double b[KT * LDB];          // sample weights [k][sample]
 };
 struct Smem {
     Stage st[STAGES];
@@ -364,8 +397,6 @@ struct Smem {
 }  // namespace rk
 
 struct RandParams {
-    const double* X;
-    int64_t ld;
     int D;
     int64_t N;
     const double* Wt;   // [nsb][dk][64]: transposed, zero-padded sample weights
@@ -378,10 +409,10 @@ struct RandParams {
     double* Y;          // N x S column-major
 };
 
-__global__ void __launch_bounds__(rk::THREADS, 1) rand_tma_kernel(const RandParams p) {
+__global__ void __launch_bounds__(rk::THREADS, 1) rand_tma_kernel(const RandParams p, const __grid_constant__ CUtensorMap tmx) {
     using namespace rk;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    extern __shared__ unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));  // swizzle: 1 KB aligned
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     {
         double* z = reinterpret_cast<double*>(sm.st);
@@ -407,7 +438,6 @@ __global__ void __launch_bounds__(rk::THREADS, 1) rand_tma_kernel(const RandPara
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int64_t p0 = tile * TP;
-            const int npts = (int)min((int64_t)TP, p.N - p0);
             for (int sb = 0; sb < nsb; ++sb) {
                 const double* Wsb = p.Wt + (int64_t)sb * p.dk * TS;
                 for (int k0 = 0; k0 < p.D; k0 += KT, ++it) {
@@ -416,13 +446,11 @@ __global__ void __launch_bounds__(rk::THREADS, 1) rand_tma_kernel(const RandPara
                     mbar_wait(smem_u32(&sm.empty[stg]), ph ^ 1u);
                     Stage& S = sm.st[stg];
                     const uint32_t bar = smem_u32(&sm.full[stg]);
-                    const int kc = min(KT, p.D - k0);
-                    const int my_pts = max(0, min(TP / 4, npts - pw * (TP / 4)));
-                    ring_expect(bar, (uint32_t)my_pts * kc * 8u + (uint32_t)(KT / 4) * TS * 8u, lane);
-                    {
-                        const int pt = pw * (TP / 4) + lane;
-                        if (pt < npts) bulk_g2s(smem_u32(&S.a[pt * LDA]), p.X + (p0 + pt) * p.ld + k0, (uint32_t)kc * 8u, bar);
-                    }
+                    // one box {16 features, 64 points} per warp; beyond D or N the TMA unit writes zeros and still counts the bytes
+                    ring_expect(bar, (uint32_t)(TP / 2) * 16u * 8u + (uint32_t)(KT / 4) * TS * 8u, lane);
+                    if (lane == 0)
+                        tma_load_2d(smem_u32(&S.a[pw & 1][(pw >> 1) * (TP / 2) * 16]), &tmx, k0 + 16 * (pw & 1),
+                                    (int)(p0 + (pw >> 1) * (TP / 2)), bar);
                     if (lane < KT / 4) {
                         const int kr = pw * (KT / 4) + lane;
                         bulk_g2s(smem_u32(&S.b[kr * LDB]), Wsb + (int64_t)(k0 + kr) * TS, TS * 8u, bar);
@@ -435,6 +463,9 @@ __global__ void __launch_bounds__(rk::THREADS, 1) rand_tma_kernel(const RandPara
 
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, kq = lane & 3;
+    int aoff[4];  // swizzled offset of (point wm * 32 + g, feature 4 j + kq) within a 16-feature sub-tile
+#pragma unroll
+    for (int j = 0; j < 4; ++j) aoff[j] = wm * 32 * 16 + swz128(g, j * 4 + kq);
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t p0 = tile * TP;
@@ -449,14 +480,13 @@ __global__ void __launch_bounds__(rk::THREADS, 1) rand_tma_kernel(const RandPara
                 const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
                 mbar_wait(smem_u32(&sm.full[stg]), ph);
                 const Stage& S = sm.st[stg];
-                const double* Ap = S.a + (wm * 32 + g) * LDA;
                 const double* Bp = S.b + wn * 32 + g;
 #pragma unroll
                 for (int kk = 0; kk < KT / 4; ++kk) {
                     const int kl = kk * 4 + kq;
                     double a[4], b[4];
 #pragma unroll
-                    for (int mi = 0; mi < 4; ++mi) a[mi] = Ap[mi * 8 * LDA + kl];
+                    for (int mi = 0; mi < 4; ++mi) a[mi] = S.a[kk >> 2][mi * 8 * 16 + aoff[kk & 3]];
 #pragma unroll
                     for (int ni = 0; ni < 4; ++ni) b[ni] = Bp[kl * LDB + ni * 8];
 #pragma unroll
@@ -508,7 +538,7 @@ __global__ void transpose_samples_kernel(const double* __restrict__ Wsamp, int D
 
 bool sample_fast_eligible(const blr_x* x) {
     return x->layout == BLR_COLVECS && x->D >= 64 && (x->D % 2) == 0 && (x->ld % 2) == 0 &&
-           (reinterpret_cast<uintptr_t>(x->p) & 15) == 0 && x->N >= 128;
+           (reinterpret_cast<uintptr_t>(x->p) & 15) == 0 && x->N >= 128 && x->N < (1ll << 31);
 }
 
 int sample_finite_fast(blr_ctx* ctx, const blr_x* x, const double* Wsamp_dev, int64_t S, const double* sigma2,
@@ -521,8 +551,6 @@ int sample_finite_fast(blr_ctx* ctx, const blr_x* x, const double* Wsamp_dev, in
     transpose_samples_kernel<<<std::min(ctx->sm_count * 4, nsb * dk), 256, 0, ctx->stream>>>(Wsamp_dev, D, (int)S, Wt, dk, nsb);
     BLR_CHECK_LAUNCH(ctx, "transpose_samples_kernel");
     RandParams rp;
-    rp.X = x->p;
-    rp.ld = x->ld;
     rp.D = D;
     rp.N = x->N;
     rp.Wt = Wt;
@@ -533,11 +561,19 @@ int sample_finite_fast(blr_ctx* ctx, const blr_x* x, const double* Wsamp_dev, in
     rp.Zy = Zy_dev;
     rp.seed = seed;
     rp.Y = Y_dev;
-    BLR_CUDA_OK(ctx, cudaFuncSetAttribute(rand_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(rk::Smem)));
-    const int64_t ntiles = (x->N + rk::TP - 1) / rk::TP;
-    rand_tma_kernel<<<(int)std::min<int64_t>(ntiles, ctx->sm_count), rk::THREADS, sizeof(rk::Smem), ctx->stream>>>(rp);
-    BLR_CHECK_LAUNCH(ctx, "rand_tma_kernel");
+    const int smem = (int)sizeof(rk::Smem) + 1024;  // + slack for the in-kernel 1024-byte alignment
+    CUtensorMap tmx;  // points: D features (contiguous) x N points; one box = 16 features of 64 points
+    int rc = make_tmap_2d_f64(ctx, &tmx, x->p, (uint64_t)x->D, (uint64_t)x->N, (uint64_t)x->ld, 16, rk::TP / 2);
+    cudaError_t e = (rc == 0) ? cudaFuncSetAttribute(rand_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) : cudaSuccess;
+    if (rc == 0 && e == cudaSuccess) {
+        const int64_t ntiles = (x->N + rk::TP - 1) / rk::TP;
+        rand_tma_kernel<<<(int)std::min<int64_t>(ntiles, ctx->sm_count), rk::THREADS, smem, ctx->stream>>>(rp, tmx);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
     dev_free(ctx->stream, Wt);
+    if (rc != 0) return rc;
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "launch rand_tma_kernel");
     return 0;
 }
 
