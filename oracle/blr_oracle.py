@@ -28,9 +28,12 @@ Pinning status (see tests/test_oracle_reference_suite.py): Julia cannot run in t
   * every property / known-answer-by-construction test the reference's own suite holds for
     this path (test/bayesian_linear_regression.jl:22-122, test/basis_function_regression.jl:13-41,
     test/sampling_functions.jl:3-47), restated with the same shapes and tolerances.
-Seed-specific Julia outputs (MersenneTwister streams) are NOT reproducible here; beyond the
-sqrt(eps)-level properties above and the doctest, bit-level agreement with Julia+OpenBLAS is
-"parity unpinned".
+  * round 2: an independent 50-digit evaluation (mpmath) of the mathematical definitions -- the naive N x N
+    Gaussian of test/bayesian_linear_regression.jl:22-38 and the closed-form posterior -- which this oracle
+    matches to 1e-12 on well-conditioned problems, dense and diagonal noise (tests/highprec.py,
+    tests/test_highprec_pins.py; the reference's own suite pins the same identity only to sqrt(eps)).
+What stays unpinned is what cannot be had without a Julia binary: seed-specific MersenneTwister streams and the
+last-bit rounding of Julia+OpenBLAS itself ("parity unpinned" at the bit level; pinned at 1e-12 against the truth).
 
 Conventions: X is always the D x N matrix of ``ColVecs`` (observation = column), exactly as
 ``x_as_colvecs`` produces (src/bayesian_linear_regression.jl:20-31).
