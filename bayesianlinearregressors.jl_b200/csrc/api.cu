@@ -275,6 +275,8 @@ int blr_ctx_create(blr_ctx** out, int device) {
     if (const char* v = getenv("BLR_GRAM_UNIT")) ctx->gram_unit = atoi(v) != 0 ? 1 : 0;
     if (const char* v = getenv("BLR_GRAM_CS")) ctx->gram_cs = atoi(v) != 0 ? 1 : 0;
     if (const char* v = getenv("BLR_VAR_CFG")) ctx->var_cfg = atoi(v) == 0 ? 0 : 1;
+    if (const char* v = getenv("BLR_RAND_PP")) ctx->rand_pp = std::max(0, std::min(2, atoi(v)));
+    if (const char* v = getenv("BLR_RAND_UNFUSED")) ctx->rand_unfused = atoi(v) != 0 ? 1 : 0;
     if (const char* w = getenv("BLR_DIAG_WEIGHT")) {
         const int v = atoi(w);
         if (v >= 8 && v <= 128) ctx->diag_weight = v;
@@ -1128,8 +1130,8 @@ int blr_rand_finite_dev(blr_ctx* ctx, blr_post* p, const blr_x* x, const blr_noi
         BLR_TRY(check_noise_vector(ctx, sig, x->N));  // `_cholesky(fx.Σy)` (:52): PosDefException for a non-positive variance
     }
     double* buf = nullptr;
-    BLR_CUDA_OK(ctx, dev_alloc(ctx, &buf, (size_t)2 * (D + 1) * S * sizeof(double)));
-    double *Zd = buf, *Wd = buf + (D + 1) * S;
+    BLR_CUDA_OK(ctx, dev_alloc(ctx, &buf, (size_t)(2 * (D + 1) * S + 2) * sizeof(double)));
+    double *Zd = buf, *Wd = buf + (((D + 1) * S + 1) & ~(int64_t)1);  // even offset: 16-byte aligned (a TMA source in the two-group rand kernel)
     int rc = 0;
     cudaError_t e = cudaSuccess;
     if (Zw_host)

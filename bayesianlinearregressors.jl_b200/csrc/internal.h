@@ -72,6 +72,11 @@ struct blr_ctx {
     int sched_T = 0, sched_nseg = 0;
     int64_t gram_period_obs = 0;  // observations per L2 period of the Gram kernel (0 = single period; BLR_GRAM_PERIOD_OBS)
     int gram_stages = 0;   // ring depth override for gram_kt == 16 (BLR_GRAM_STAGES = 6)
+    int rand_pp = 1;       // K7: 1 = two consumer groups on alternating point tiles when the draws are SUPPLIED (8.2 ms against 9.6 ms at
+                           // D = 512, N* = 2^22, S = 64), single-group kernel for device draws (9.79 ms; two-group 9.97); 0 = always
+                           // single-group, 2 = always two-group (BLR_RAND_PP)
+    int rand_unfused = 0;  // K7 two-group with device draws: 1 = draw a chunk's normals in a pass of their own (9.83 ms: no gain, the
+                           // generator costs the same 1.5 ms on its own) (BLR_RAND_UNFUSED)
     int var_cfg = 1;       // marginals fast path: 1 = <4 x 64 rows, 64 points> (default), 0 = <8 x 64 rows, 32 points> (BLR_VAR_CFG=0)
     int gram_unit = 1;     // homoscedastic noise: run the Gram kernel unscaled and apply 1/σ² in the reduction (BLR_GRAM_UNIT=0: off)
     int gram_cs = 1;       // Gram consumer tiling: 1 = hybrid (column strips, 1 x 8 warps, on off-diagonal tiles), 0 = 2 x 4 (BLR_GRAM_CS)

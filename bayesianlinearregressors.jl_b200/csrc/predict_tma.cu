@@ -407,6 +407,9 @@ struct RandParams {
     const double* Zy;   // N x S column-major, or null
     uint64_t seed;
     double* Y;          // N x S column-major
+    int64_t ldy, ldz;   // leading dimensions of Y and Zy (two-group kernel; the single-group kernel uses N for both)
+    int64_t n_global;   // index of this launch's first point in the whole problem and the whole problem's N: the Philox counter
+    int64_t N_global;   // of pair (n, s) is n + (s >> 1) N over the WHOLE problem, whatever the chunking
 };
 
 __global__ void __launch_bounds__(rk::THREADS, 1) rand_tma_kernel(const RandParams p, const __grid_constant__ CUtensorMap tmx) {
@@ -536,6 +539,9 @@ __global__ void transpose_samples_kernel(const double* __restrict__ Wsamp, int D
     }
 }
 
+int sample_finite_pp(blr_ctx* ctx, const blr_x* x, const double* Wsamp_dev, int64_t S, const double* sigma2,
+                     double sigma2_scalar, const double* Zy_dev, uint64_t seed, double* Y_dev);
+
 bool sample_fast_eligible(const blr_x* x) {
     return x->layout == BLR_COLVECS && x->D >= 64 && (x->D % 2) == 0 && (x->ld % 2) == 0 &&
            (reinterpret_cast<uintptr_t>(x->p) & 15) == 0 && x->N >= 128 && x->N < (1ll << 31);
@@ -544,6 +550,10 @@ bool sample_fast_eligible(const blr_x* x) {
 int sample_finite_fast(blr_ctx* ctx, const blr_x* x, const double* Wsamp_dev, int64_t S, const double* sigma2,
                        double sigma2_scalar, const double* Zy_dev, uint64_t seed, double* Y_dev) {
     const int D = (int)x->D;
+    if (ctx->rand_pp == 2 || (ctx->rand_pp == 1 && Zy_dev != nullptr)) {
+        const int r = sample_finite_pp(ctx, x, Wsamp_dev, S, sigma2, sigma2_scalar, Zy_dev, seed, Y_dev);
+        if (r <= 0) return r;  // 1: weights not 16-byte aligned -> the default kernel
+    }
     const int dk = ((D + rk::KT - 1) / rk::KT) * rk::KT;
     const int nsb = (int)((S + rk::TS - 1) / rk::TS);
     double* Wt = nullptr;
@@ -561,6 +571,9 @@ int sample_finite_fast(blr_ctx* ctx, const blr_x* x, const double* Wsamp_dev, in
     rp.Zy = Zy_dev;
     rp.seed = seed;
     rp.Y = Y_dev;
+    rp.ldy = rp.ldz = x->N;
+    rp.n_global = 0;
+    rp.N_global = x->N;
     const int smem = (int)sizeof(rk::Smem) + 1024;  // + slack for the in-kernel 1024-byte alignment
     CUtensorMap tmx;  // points: D features (contiguous) x N points; one box = 16 features of 64 points
     int rc = make_tmap_2d_f64(ctx, &tmx, x->p, (uint64_t)x->D, (uint64_t)x->N, (uint64_t)x->ld, 16, rk::TP / 2);
@@ -575,6 +588,244 @@ int sample_finite_fast(blr_ctx* ctx, const blr_x* x, const double* Wsamp_dev, in
     if (rc != 0) return rc;
     if (e != cudaSuccess) return cuda_fail(ctx, e, "launch rand_tma_kernel");
     return 0;
+}
+
+// ====================================================================================================
+// K7, two-group kernel (default when the draws are supplied; BLR_RAND_PP): TWO consumer groups of four warps, each with its own tiles of 128 points x 64 samples
+// (warp tile 32 x 64), its own 4-stage ring of 16-feature stages and its own producer warp; warps w and w + 4 share an SM
+// sub-partition, so while one group is in its epilogue the other group's warp has the DMMA pipe to itself.  Both operands by
+// 2-D tiled TMA (tensor maps over X and over the D x S sample-weight matrix itself; one swizzled offset table serves both
+// fragments).  Measurements and the dead ends on the way: DESIGN.md, section 4 (K7).
+// The per-pair epilogue (draw or load z, add the noise, store) as a real call instead of 32 inlined copies: with two groups executing DIFFERENT code at the same time
+// (one in its main loop, one in its epilogue) the unrolled epilogue (~64 KB of SASS) evicted the main loop from the instruction
+// cache -- ncu: no_instruction was the top stall (5.3 per issue), 64.9 ms at cfg4 against 38.8 ms for the single-group kernel.
+// Four pairs per call (one point, samples s0 + 8 j + {0, 1}, j = 0..3): the four Philox -> log / sincospi -> sqrt chains are
+// independent and interleave; 32 strictly serial single-pair calls made a group's epilogue nearly as long as the other
+// group's main loop (two-group kernel with device draws 9.94 ms against 8.57 ms with supplied draws, D = 512, N* = 2^22).
+__device__ __noinline__ void rand_emit4(double* __restrict__ Y, const double* __restrict__ Zy, int64_t ldy, int64_t ldz, int S,
+                                        uint64_t seed, uint64_t ctr0, uint64_t Ng, int64_t n, int s0, double sd, double a00,
+                                        double a01, double a10, double a11, double a20, double a21, double a30, double a31) {
+    const double a[4][2] = {{a00, a01}, {a10, a11}, {a20, a21}, {a30, a31}};
+    double z[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int s = s0 + 8 * j;
+        z[j][0] = z[j][1] = 0.0;
+        if (s < S) {
+            if (Zy) {
+                z[j][0] = Zy[(int64_t)s * ldz + n];
+                if (s + 1 < S) z[j][1] = Zy[(int64_t)(s + 1) * ldz + n];
+            } else {
+                philox_normal_pair(seed, 7, ctr0 + (uint64_t)n + (uint64_t)(s >> 1) * Ng, z[j][0], z[j][1]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int s = s0 + 8 * j;
+        if (s < S) Y[(int64_t)s * ldy + n] = fma(sd, z[j][0], a[j][0]);
+        if (s + 1 < S) Y[(int64_t)(s + 1) * ldy + n] = fma(sd, z[j][1], a[j][1]);
+    }
+}
+
+// The draws of points [0, cnt) of a chunk (global indices n_global + n) for all S samples, with exactly the counters of the fused
+// epilogue: pair (n, s even) = Philox(seed, stream 7, n + (s / 2) N_global) -> (z_s, z_{s+1}).  Z is cnt x S, ld = ldz.
+__global__ void __launch_bounds__(256) rand_draws_kernel(double* __restrict__ Z, int64_t ldz, int64_t cnt, int S, uint64_t seed,
+                                                         uint64_t n_global, uint64_t N_global) {
+    const int64_t npair_cols = (S + 1) / 2, total = npair_cols * cnt;
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+        const int64_t sp = e / cnt, n = e % cnt;
+        double z0, z1;
+        philox_normal_pair(seed, 7, n_global + (uint64_t)n + (uint64_t)sp * N_global, z0, z1);
+        Z[2 * sp * ldz + n] = z0;
+        if (2 * sp + 1 < S) Z[(2 * sp + 1) * ldz + n] = z1;
+    }
+}
+
+namespace rp {
+constexpr int TP = 128, TS = 64, KT = 16, STAGES = 4, GROUPS = 2, GROUP_WARPS = 4;
+constexpr int CONSUMER_WARPS = GROUPS * GROUP_WARPS;
+// setmaxnreg.sync.aligned is a WARPGROUP operation (four contiguous warps): the producer side is a full warpgroup, warps 8 and
+// 9 produce, warps 10 and 11 only hand their registers over and exit (a two-warp producer side hangs the kernel)
+constexpr int THREADS = (CONSUMER_WARPS + 4) * 32;
+struct __align__(1024) Stage {
+    double a[TP * 16];  // points:         [point][16 features], swz128
+    double b[TS * 16];  // sample weights: [sample][16 features], swz128
+};
+constexpr uint32_t STAGE_BYTES = (uint32_t)((TP + TS) * 16 * sizeof(double));
+struct Smem {
+    Stage st[GROUPS][STAGES];
+    unsigned long long full[GROUPS][STAGES];
+    unsigned long long empty[GROUPS][STAGES];
+    int go;  // group 0 is half way through its first tile: group 1 may start
+};
+}  // namespace rp
+
+__global__ void __launch_bounds__(rp::THREADS, 1) rand_pp_kernel(const RandParams p, const __grid_constant__ CUtensorMap tmx,
+                                                                 const __grid_constant__ CUtensorMap tmw) {
+    using namespace rp;
+    extern __shared__ unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int gi = 0; gi < GROUPS; ++gi)
+            for (int i = 0; i < STAGES; ++i) {
+                mbar_init(smem_u32(&sm.full[gi][i]), RING_LANES);
+                mbar_init(smem_u32(&sm.empty[gi][i]), GROUP_WARPS * RING_LANES);
+            }
+        sm.go = 0;
+        mbar_fence_init();
+    }
+    __syncthreads();  // no zero fill: every byte of a stage is written by the TMA boxes of the phase that is read
+    const int64_t ntiles = (p.N + TP - 1) / TP;
+    const int nsb = (p.S + TS - 1) / TS;
+    const int nst = (p.D + KT - 1) / KT;
+
+    if (warp >= CONSUMER_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        const int grp = warp - CONSUMER_WARPS;
+        if (grp >= GROUPS) return;
+        int it = 0;
+        // the CTA's j-th tile is blockIdx.x + j gridDim.x; group grp takes j = grp, grp + 2, ...
+        for (int64_t tile = blockIdx.x + (int64_t)grp * gridDim.x; tile < ntiles; tile += (int64_t)GROUPS * gridDim.x) {
+            const int p0 = (int)(tile * TP);
+            for (int sb = 0; sb < nsb; ++sb)
+                for (int si = 0; si < nst; ++si, ++it) {
+                    const int stg = it % STAGES;
+                    mbar_wait(smem_u32(&sm.empty[grp][stg]), ((uint32_t)(it / STAGES) & 1u) ^ 1u);
+                    Stage& S = sm.st[grp][stg];
+                    const uint32_t bar = smem_u32(&sm.full[grp][stg]);
+                    ring_expect(bar, STAGE_BYTES, lane);  // out-of-range features / points / samples are zero-filled and counted
+                    if (lane == 0) {
+                        tma_load_2d(smem_u32(S.a), &tmx, si * KT, p0, bar);
+                        tma_load_2d(smem_u32(S.b), &tmw, si * KT, sb * TS, bar);
+                    }
+                }
+        }
+        return;
+    }
+
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");  // 128 x 40 + 256 x 232 = 384 x 168
+    const int grp = warp / GROUP_WARPS, wq = warp % GROUP_WARPS, g = lane >> 2, kq = lane & 3;
+    int off[4];  // swizzled offset of (row g, feature 4 j + kq) within an 8-row block
+#pragma unroll
+    for (int j = 0; j < 4; ++j) off[j] = swz128(g, j * 4 + kq);
+    if (grp == 1) {  // start half a tile behind group 0
+        if (lane == 0)
+            while (*reinterpret_cast<volatile int*>(&sm.go) == 0) {
+            }
+        __syncwarp();
+    }
+    int it = 0;
+    bool first = true;
+    for (int64_t tile = blockIdx.x + (int64_t)grp * gridDim.x; tile < ntiles; tile += (int64_t)GROUPS * gridDim.x) {
+        const int64_t p0 = tile * TP;
+        for (int sb = 0; sb < nsb; ++sb) {
+            double acc[4][8][2];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 8; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            for (int si = 0; si < nst; ++si, ++it) {
+                const int stg = it % STAGES;
+                mbar_wait(smem_u32(&sm.full[grp][stg]), (uint32_t)(it / STAGES) & 1u);
+                const Stage& S = sm.st[grp][stg];
+#pragma unroll
+                for (int kk = 0; kk < KT / 4; ++kk) {
+                    const double* Ah = S.a + wq * 32 * 16 + off[kk];
+                    const double* Bh = S.b + off[kk];
+                    double a[4], b[8];
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) a[mi] = Ah[mi * 8 * 16];
+#pragma unroll
+                    for (int ni = 0; ni < 8; ++ni) b[ni] = Bh[ni * 8 * 16];
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
+                }
+                ring_release(smem_u32(&sm.empty[grp][stg]), lane);
+                if (first && grp == 0 && warp == 0 && lane == 0 && sb == 0 && si == nst / 2)
+                    *reinterpret_cast<volatile int*>(&sm.go) = 1;
+            }
+            first = false;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const int64_t n = p0 + wq * 32 + mi * 8 + g;
+                if (n < p.N) {
+                    const double sd = sqrt(p.sigma2 ? p.sigma2[n] : p.sigma2_scalar);
+#pragma unroll
+                    for (int nh = 0; nh < 2; ++nh) {
+                        const int s0 = sb * TS + nh * 32 + kq * 2;  // even; samples s0 + 8 j + {0, 1}
+                        if (s0 < p.S)
+                            rand_emit4(p.Y, p.Zy, p.ldy, p.ldz, p.S, p.seed, (uint64_t)p.n_global, (uint64_t)p.N_global, n, s0, sd, acc[mi][4 * nh][0], acc[mi][4 * nh][1], acc[mi][4 * nh + 1][0],
+                                       acc[mi][4 * nh + 1][1], acc[mi][4 * nh + 2][0], acc[mi][4 * nh + 2][1], acc[mi][4 * nh + 3][0],
+                                       acc[mi][4 * nh + 3][1]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// One launch of the two-group kernel on points [n0, n0 + cnt) of x
+static int launch_rand_pp(blr_ctx* ctx, const blr_x* x, int64_t n0, int64_t cnt, const double* Wsamp_dev, int64_t S,
+                          const double* sigma2, double sigma2_scalar, const double* Zy, int64_t ldz, uint64_t seed, double* Y_dev) {
+    RandParams rp_;
+    rp_.D = (int)x->D;
+    rp_.N = cnt;
+    rp_.Wt = nullptr;
+    rp_.dk = 0;
+    rp_.S = (int)S;
+    rp_.sigma2 = sigma2 ? sigma2 + n0 : nullptr;
+    rp_.sigma2_scalar = sigma2_scalar;
+    rp_.Zy = Zy;
+    rp_.seed = seed;
+    rp_.Y = Y_dev + n0;
+    rp_.ldy = x->N;
+    rp_.ldz = ldz;
+    rp_.n_global = n0;
+    rp_.N_global = x->N;
+    const int smem = (int)sizeof(rp::Smem) + 1024;
+    CUtensorMap tmx, tmw;
+    BLR_TRY(make_tmap_2d_f64(ctx, &tmx, x->p + n0 * x->ld, (uint64_t)x->D, (uint64_t)cnt, (uint64_t)x->ld, 16, rp::TP));
+    BLR_TRY(make_tmap_2d_f64(ctx, &tmw, Wsamp_dev, (uint64_t)x->D, (uint64_t)S, (uint64_t)x->D, 16, rp::TS));
+    BLR_CUDA_OK(ctx, cudaFuncSetAttribute(rand_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int64_t ntiles = (cnt + rp::TP - 1) / rp::TP;
+    const int grid = (int)std::min<int64_t>((ntiles + rp::GROUPS - 1) / rp::GROUPS, ctx->sm_count);
+    rand_pp_kernel<<<grid, rp::THREADS, smem, ctx->stream>>>(rp_, tmx, tmw);
+    BLR_CHECK_LAUNCH(ctx, "rand_pp_kernel");
+    return 0;
+}
+
+// Wsamp_dev must be 16-byte aligned (it is a TMA source); returns 1 if the variant does not apply.
+// Device draws (Zy_dev == nullptr) are UN-FUSED by default: the ~68 scalar fp64 instructions per pair of draws run on the pipe
+// DMMA runs on, and inside the GEMM's epilogue they cost 1.8 ms per 2^22 x 64 outputs against ~0.5 ms as a pass of their own
+// (rand_draws_kernel, same Philox counters) followed by the supplied-draws epilogue (two loads, two FMAs, two stores).  The
+// draws of a chunk of points live in a bounded scratch buffer.
+int sample_finite_pp(blr_ctx* ctx, const blr_x* x, const double* Wsamp_dev, int64_t S, const double* sigma2,
+                     double sigma2_scalar, const double* Zy_dev, uint64_t seed, double* Y_dev) {
+    if ((reinterpret_cast<uintptr_t>(Wsamp_dev) & 15) != 0) return 1;
+    const int64_t N = x->N;
+    if (Zy_dev || !ctx->rand_unfused) return launch_rand_pp(ctx, x, 0, N, Wsamp_dev, S, sigma2, sigma2_scalar, Zy_dev, N, seed, Y_dev);
+    // chunk: <= 64 Mi draws (512 MiB), a multiple of 2 x 128 points x #SMs so that every CTA gets whole tile pairs
+    const int64_t unit = (int64_t)rp::TP * rp::GROUPS * ctx->sm_count;
+    int64_t chunk = std::max<int64_t>(unit, ((int64_t)1 << 26) / std::max<int64_t>(S, 1) / unit * unit);
+    chunk = std::min(chunk, (N + 1) / 2 * 2);
+    double* Z = nullptr;
+    BLR_CUDA_OK(ctx, dev_alloc(ctx, &Z, (size_t)(chunk * S) * sizeof(double)));
+    int rc = 0;
+    for (int64_t n0 = 0; n0 < N && rc == 0; n0 += chunk) {
+        const int64_t cnt = std::min(chunk, N - n0);
+        const int64_t work = (S + 1) / 2 * cnt;
+        rand_draws_kernel<<<(int)std::min<int64_t>((work + 255) / 256, (int64_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(
+            Z, chunk, cnt, (int)S, seed, (uint64_t)n0, (uint64_t)N);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = set_err(ctx, BLR_E_CUDA, "launch rand_draws_kernel");
+        if (rc == 0) rc = launch_rand_pp(ctx, x, n0, cnt, Wsamp_dev, S, sigma2, sigma2_scalar, Z, chunk, seed, Y_dev);
+    }
+    dev_free(ctx->stream, Z);
+    return rc;
 }
 
 }  // namespace blr

@@ -638,6 +638,17 @@ def run_predict(args, E, c):
 
     ms_mv, launches, clocks, _ = timed_steps(E, args, mean_var)
     ms_r, _, clocks_r, _ = timed_steps(E, args, rand)
+    # rand with SUPPLIED draws resident on the device -- the reference-parity mode (src/bayesian_linear_regression.jl:51-52: the
+    # caller's RNG stream); the draws are generated once, outside the timed region (torch's generator: any N(0,1) stream will do)
+    Zs = torch.randn((S, n), dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(args.seed + 99))
+    torch.cuda.synchronize()
+
+    def rand_supplied():
+        ctx.check(ctx.lib.blr_rand_finite_dev(ctx.handle, dpost.handle, Xd.handle, C.byref(noise), S, None, C.c_void_p(Zs.data_ptr()),
+                                              7 + E.rank, C.c_void_p(Y.data_ptr())))
+
+    ms_rs, _, clocks_rs, _ = timed_steps(E, args, rand_supplied)
+    del Zs
     # parity on sampled blocks: x'm', |L^-1 x|² + σ² from the host posterior by torch (checker), rand with supplied draws
     Lp = np.linalg.cholesky(post.Λw.dense())
     cft, mt = torch.from_numpy(Lp).cuda(), torch.from_numpy(post.mw).cuda()
@@ -681,6 +692,11 @@ def run_predict(args, E, c):
             "rand": {"value": Nt / (ms_r * 1e-3), "unit": "points/s", "samples": S, "ms_per_step": ms_r, "clocks": clocks_r,
                      "tflops_per_gpu": fl_r / (ms_r * 1e-3) / 1e12, "frac_of_dmma_peak": fl_r / (ms_r * 1e-3) / 1e12 / peak,
                      "hbm_gbs_algorithmic_per_gpu": 8.0 * n * (D + S) / (ms_r * 1e-3) / 1e9, "draws": "device Philox4x32-10, Box-Muller"},
+            "rand_supplied_draws": {"value": Nt / (ms_rs * 1e-3), "unit": "points/s", "samples": S, "ms_per_step": ms_rs, "clocks": clocks_rs,
+                                    "tflops_per_gpu": fl_r / (ms_rs * 1e-3) / 1e12, "frac_of_dmma_peak": fl_r / (ms_rs * 1e-3) / 1e12 / peak,
+                                    "hbm_gbs_algorithmic_per_gpu": 8.0 * n * (D + 2 * S) / (ms_rs * 1e-3) / 1e9,
+                                    "draws": "N x S standard normals resident on the device (the reference's mode: the caller's RNG stream, "
+                                             ":51-52); two-group kernel"},
             "fit_logpdf": lp_fit,
             "parity": {"checked": True, "ok": bool(worst < 1e-9 and worst_r < 1e-9 and finite), "marginals_max_rel_err": worst,
                        "rand_rel_err": worst_r, "finite": finite,

@@ -350,6 +350,25 @@ def test_rand_matches_oracle_with_same_draws(D, N, S):
     assert blr.rand(np.random.default_rng(5), f(blr.ColVecs(X), σ2)).shape == (N,)
 
 
+def test_rand_device_draws_same_stream_across_kernels(monkeypatch):
+    """The three K7 paths -- single-group kernel with the draws in its epilogue, two-group kernel with the draws in its epilogue,
+    two-group kernel fed by the stand-alone draw pass chunk by chunk (the default) -- use the same Philox counters: for one seed
+    they must produce the same N x S sample matrix (ragged N and S, more than one chunk of draws)."""
+    D, N, S = 128, 40000, 70
+    X, mw, Λ, σ2, _ = problem(D, N, seed=5)
+    outs = []
+    for pp, unf in (("0", "0"), ("2", "0"), ("2", "1")):
+        monkeypatch.setenv("BLR_RAND_PP", pp)
+        monkeypatch.setenv("BLR_RAND_UNFUSED", unf)
+        ctx = blr.Context(0)
+        f = blr.BayesianLinearRegressor(mw, Λ)
+        fx = f(blr.ColVecs(blr.DeviceMatrix.upload(ctx, X, 0)), blr.DeviceVector.upload(ctx, σ2))
+        fx.ctx = ctx
+        outs.append(blr.rand(blr.DeviceRNG(11), fx, S))
+    assert np.isfinite(outs[0]).all() and outs[0].shape == (N, S)
+    assert relerr(outs[1], outs[0]) < 1e-13 and relerr(outs[2], outs[0]) < 1e-13
+
+
 def test_rand_device_rng_moments():
     """test/bayesian_linear_regression.jl:11-21 on the device generator (Philox): moments of 2e5 samples."""
     D, N, S = 3, 11, 200_000
