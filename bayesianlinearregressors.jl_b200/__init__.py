@@ -10,4 +10,4 @@ from .model import (AffineFeatures, TorchFeatureMap, BasisFunctionRegressor, Bay
                     mean_and_cov, mean_and_var, posterior, posterior_and_logpdf, posterior_and_logpdf_streamed, rand, rand_into, rand_with_draws, std, var)
 from .runtime import (Context, DeviceMatrix, DevicePosterior, DeviceVector, Stats, default_context,  # noqa: F401
                       set_default_context)
-from .sharding import ShardPlan, distributed_infer  # noqa: F401
+from .sharding import ShardPlan, packed_len  # noqa: F401

@@ -7,13 +7,8 @@ collective at all.
 """
 from __future__ import annotations
 
-import ctypes as C
 from dataclasses import dataclass
-from typing import Callable, Optional, Tuple
-
-import numpy as np
-
-from . import _lib as L
+from typing import Tuple
 
 
 @dataclass(frozen=True)
@@ -44,34 +39,3 @@ class ShardPlan:
 
 def packed_len(D: int) -> int:
     return D * D + D + 3
-
-
-def pack_stats(G: np.ndarray, r: np.ndarray, q: float, ℓ: float, n: float) -> np.ndarray:
-    D = r.shape[0]
-    out = np.empty(packed_len(D))
-    out[: D * D] = np.asarray(G, dtype=np.float64).reshape(-1, order="F")
-    out[D * D : D * D + D] = r
-    out[D * D + D :] = (q, ℓ, n)
-    return out
-
-
-def unpack_stats(p: np.ndarray, D: int):
-    return p[: D * D].reshape(D, D, order="F"), p[D * D : D * D + D], p[D * D + D], p[D * D + D + 1], p[D * D + D + 2]
-
-
-def distributed_infer(local_stats: Callable[[int, int], np.ndarray], N: int, D: int, allreduce: Callable[[np.ndarray], np.ndarray],
-                      rank: int, world: int, solve: Callable[[np.ndarray], object], align: int = 16):
-    """Host-side control flow of the sharded path, with the three device stages injected:
-
-        local_stats(lo, hi) -> packed statistics of observations [lo, hi)   (blr_stats_accumulate)
-        allreduce(packed)   -> elementwise sum over ranks                    (blr_stats_allreduce / NCCL)
-        solve(packed)       -> posterior + logpdf from reduced statistics    (blr_infer_from_stats)
-
-    In production the stages are the C-ABI calls named on the right (see model._infer, which runs them inside
-    blr_infer); the indirection exists so the N > 1 control flow is testable under gloo on CPU boxes.
-    """
-    lo, hi = ShardPlan(N, world, align).bounds(rank)
-    packed = local_stats(lo, hi)
-    if packed.shape[0] != packed_len(D):
-        raise ValueError("packed statistics have the wrong length")
-    return solve(allreduce(packed))

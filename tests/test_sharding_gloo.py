@@ -11,7 +11,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from blr_b200.sharding import ShardPlan, distributed_infer, pack_stats, packed_len, unpack_stats
+from blr_b200.sharding import ShardPlan, packed_len
+from tests.sharding_scaffold import distributed_infer, pack_stats, unpack_stats
 from oracle import blr_oracle as ref
 
 
