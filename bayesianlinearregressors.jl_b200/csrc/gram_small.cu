@@ -198,6 +198,141 @@ __global__ void __launch_bounds__(gs::THREADS, gs::ctas_per_sm(MI))
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// 16 < D <= 64, D a multiple of 8, ColVecs with 16-byte aligned observations: the same warp-owns-the-Gram-matrix scheme, but the
+// observations reach the operand fragments through a PER-WARP ring in shared memory fed by TMA bulk copies, so that every warp
+// keeps three stages of observations in flight.  The register-fed kernel above has one batch of two k4-steps in flight per
+// warp and only 8 warps per SM at D = 64 (the accumulators take the register file): it is latency-bound between the HBM and
+// the tensor roofline (D = 64: 44 % of the DMMA peak, D = 32: 70 % of HBM).  The block grid is exactly D / 8 wide (the kernel
+// above rounds 33..64 features up to 8 x 8 blocks: 36 block-MMAs per step at D = 40 instead of 15).
+// One stage = 8 observations = two k4-steps; with ld == D a stage is ONE contiguous bulk copy (8 D doubles), otherwise one
+// copy per observation.  The warp that consumes a slot is the warp that refills it (program order + __syncwarp), so the ring
+// needs full barriers only.  Dense rows of D doubles give a 4-way conflict on the fragment loads (the four observations of a
+// k4-step sit D doubles apart): 32 wavefronts per 36 block-MMAs at D = 64, far from binding.
+namespace gr {
+constexpr int WARPS = 8;
+constexpr int THREADS = WARPS * 32;
+constexpr int KO = 8;      // observations per stage
+constexpr int STAGES = 4;  // per warp
+constexpr int ctas_per_sm(int MI) { return MI <= 5 ? 2 : 1; }  // registers: <= 128 per thread up to D = 40; ring: 10 KB x D / 8 x ... per CTA
+}  // namespace gr
+
+template <int MI>
+__global__ void __launch_bounds__(gr::THREADS, gr::ctas_per_sm(MI))
+    gram_small_ring_kernel(const double* __restrict__ X, int64_t ld, int64_t N, const double* __restrict__ s,
+                           const double* __restrict__ t, double* __restrict__ P, double* __restrict__ Pr, int64_t obs_per_warp) {
+    using namespace gr;
+    constexpr int DP = MI * 8;  // == D
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* ring_all = reinterpret_cast<double*>(smem_raw);                                    // [WARPS][STAGES][KO * DP]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring_all + WARPS * STAGES * KO * DP);  // [WARPS][STAGES]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, kq = lane & 3;
+    double* ring = ring_all + warp * (STAGES * KO * DP);
+    const int64_t wid = (int64_t)blockIdx.x * WARPS + warp;
+    const int64_t n0 = min(N, wid * obs_per_warp), n1 = min(N, n0 + obs_per_warp);
+    const int nstages = (int)((n1 - n0 + KO - 1) / KO);
+
+    for (int e = tid; e < WARPS * STAGES * KO * DP; e += THREADS) ring_all[e] = 0.0;  // a partial last stage reads finite values
+    if (lane == 0)
+        for (int i = 0; i < STAGES; ++i) mbar_init(smem_u32(&bars[warp * STAGES + i]), 1);
+    mbar_fence_init();
+    fence_proxy_async();
+    __syncthreads();
+
+    const bool dense = (ld == DP);
+    auto issue = [&](int j) {  // stage j of this warp -> slot j % STAGES
+        if (j >= nstages) return;
+        const int64_t nb = n0 + (int64_t)j * KO;
+        const int cnt = (int)min((int64_t)KO, n1 - nb);
+        const uint32_t bar = smem_u32(&bars[warp * STAGES + j % STAGES]);
+        double* dst = ring + (j % STAGES) * (KO * DP);
+        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)cnt * DP * 8u);
+        __syncwarp();
+        if (dense) {
+            if (lane == 0) bulk_g2s(smem_u32(dst), X + nb * ld, (uint32_t)cnt * DP * 8u, bar);
+        } else if (lane < cnt) {
+            bulk_g2s(smem_u32(dst + lane * DP), X + (nb + lane) * ld, DP * 8u, bar);
+        }
+    };
+
+    double acc[MI][MI][2];
+    double racc[MI];
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi) {
+        racc[mi] = 0.0;
+#pragma unroll
+        for (int ni = 0; ni < MI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    }
+#pragma unroll 1
+    for (int j = 0; j < STAGES - 1; ++j) issue(j);
+    double skn[2], tkn[2];  // s, t of the NEXT stage's fragment lanes (one stage of prefetch hides their global-load latency)
+    auto load_st = [&](int j) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int64_t nk = n0 + (int64_t)j * KO + 4 * u + kq;
+            const bool ok = nk < n1;
+            skn[u] = ok ? s[nk] : 0.0;
+            tkn[u] = ok ? t[nk] : 0.0;
+        }
+    };
+    load_st(0);
+#pragma unroll 1
+    for (int i = 0; i < nstages; ++i) {
+        issue(i + STAGES - 1);  // refills the slot this warp finished reading in iteration i - 1
+        const double sk[2] = {skn[0], skn[1]}, tk[2] = {tkn[0], tkn[1]};
+        load_st(i + 1);
+        mbar_wait(smem_u32(&bars[warp * STAGES + i % STAGES]), (uint32_t)(i / STAGES) & 1u);
+        const double* st = ring + (i % STAGES) * (KO * DP) + g;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            double a[MI], b[MI];
+#pragma unroll
+            for (int mi = 0; mi < MI; ++mi) a[mi] = st[(4 * u + kq) * DP + mi * 8];
+#pragma unroll
+            for (int mi = 0; mi < MI; ++mi) {
+                racc[mi] = fma(a[mi], tk[u], racc[mi]);
+                b[mi] = a[mi] * sk[u];
+            }
+#pragma unroll
+            for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+                for (int ni = 0; ni <= mi; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
+        }
+        __syncwarp();  // every lane is done with the slot before lane 0 refills it in the next iteration
+    }
+    // r: fold the four observation lanes of every feature
+#pragma unroll
+    for (int mi = 0; mi < MI; ++mi) {
+        racc[mi] += __shfl_xor_sync(0xffffffffu, racc[mi], 1);
+        racc[mi] += __shfl_xor_sync(0xffffffffu, racc[mi], 2);
+    }
+    // CTA reduction in warp order (fixed => bit-reproducible); the tile aliases the (now idle) rings
+    __syncthreads();
+    double* tile = ring_all;
+    double* rsum = ring_all + DP * DP;
+    for (int e = tid; e < DP * DP + DP; e += THREADS) tile[e] = 0.0;
+    for (int w = 0; w < WARPS; ++w) {
+        __syncthreads();
+        if (warp == w) {
+#pragma unroll
+            for (int mi = 0; mi < MI; ++mi) {
+#pragma unroll
+                for (int ni = 0; ni <= mi; ++ni) {
+                    double* dst = &tile[(mi * 8 + g) * DP + ni * 8 + kq * 2];
+                    dst[0] += acc[mi][ni][0];
+                    dst[1] += acc[mi][ni][1];
+                }
+                if (kq == 0) rsum[mi * 8 + g] += racc[mi];
+            }
+        }
+    }
+    __syncthreads();
+    double* Pt = P + (int64_t)blockIdx.x * (DP * DP);
+    for (int e = tid; e < DP * DP; e += THREADS) Pt[e] = tile[e];
+    if (tid < DP) Pr[(int64_t)blockIdx.x * DP + tid] = rsum[tid];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // D <= 8: one THREAD per observation.  With so few features an m8n8k4 tile is mostly padding and the warp-per-4-
 // observations schedule above is bound by instruction issue (~11 warp instructions per observation); here a warp
 // instruction advances 32 observations: D (D + 1) / 2 + 2 D + 3 DFMAs, one divide and one log per observation per lane,
@@ -368,6 +503,35 @@ static int launch_small(blr_ctx* ctx, blr_stats* st, const blr_x* x, const doubl
     return 0;
 }
 
+template <int MI>
+static int launch_ring(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double* s, const double* t, double* partial,
+                       int partial_blocks) {
+    constexpr int DP = MI * 8;
+    const int64_t N = x->N;
+    const int smem = gr::WARPS * gr::STAGES * gr::KO * DP * (int)sizeof(double) + gr::WARPS * gr::STAGES * (int)sizeof(unsigned long long);
+    BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_small_ring_kernel<MI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int64_t groups = (N + 31) / 32;
+    const int nblocks = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * gr::ctas_per_sm(MI), (groups + gr::WARPS - 1) / gr::WARPS));
+    const int64_t total_warps = (int64_t)nblocks * gr::WARPS;
+    const int64_t obs_per_warp = ((groups + total_warps - 1) / total_warps) * 32;
+    BLR_TRY(ensure_ws(ctx, (size_t)nblocks * (DP * DP + DP) * sizeof(double)));
+    double* P = ctx->ws;
+    double* Pr = ctx->ws + (size_t)nblocks * DP * DP;
+    gram_small_ring_kernel<MI><<<nblocks, gr::THREADS, smem, ctx->stream>>>(x->p, x->ld, N, s, t, P, Pr, obs_per_warp);
+    BLR_CHECK_LAUNCH(ctx, "gram_small_ring_kernel");
+    BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    gram_small_reduce_kernel<<<(DP * DP + 255) / 256, 256, 0, ctx->stream>>>(P, Pr, DP, nblocks, DP, st->G(), st->r(), st->scal(),
+                                                                            partial, partial_blocks, (double)N);
+    BLR_CHECK_LAUNCH(ctx, "gram_small_reduce_kernel");
+    return 0;
+}
+
+// the ring kernel applies to: ColVecs, 16 < D <= 64 with D % 8 == 0, observations 16-byte aligned (BLR_SMALL_RING=0: off)
+static bool ring_eligible(const blr_ctx* ctx, const blr_x* x) {
+    return ctx->small_ring && x->layout == BLR_COLVECS && x->D > 16 && x->D <= 64 && (x->D % 8) == 0 && (x->ld % 2) == 0 &&
+           (reinterpret_cast<uintptr_t>(x->p) & 15) == 0 && x->N >= 64;
+}
+
 bool gram_small_fused(int64_t D) { return D <= 16; }
 
 template <int DT>
@@ -411,6 +575,16 @@ int gram_small(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double* y, con
     if (D <= 8) return launch_tiny<8>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, partial);
     if (D <= 16)
         return launch_small<2, true>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, s, t, partial, partial_blocks);
+    if (ring_eligible(ctx, x)) {
+        switch (D / 8) {
+            case 3: return launch_ring<3>(ctx, st, x, s, t, partial, partial_blocks);
+            case 4: return launch_ring<4>(ctx, st, x, s, t, partial, partial_blocks);
+            case 5: return launch_ring<5>(ctx, st, x, s, t, partial, partial_blocks);
+            case 6: return launch_ring<6>(ctx, st, x, s, t, partial, partial_blocks);
+            case 7: return launch_ring<7>(ctx, st, x, s, t, partial, partial_blocks);
+            default: return launch_ring<8>(ctx, st, x, s, t, partial, partial_blocks);
+        }
+    }
     if (D <= 32)
         return launch_small<4, false>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, s, t, partial, partial_blocks);
     return launch_small<8, false>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, s, t, partial, partial_blocks);

@@ -72,6 +72,7 @@ struct blr_ctx {
     int sched_T = 0, sched_nseg = 0;
     int64_t gram_period_obs = 0;  // observations per L2 period of the Gram kernel (0 = single period; BLR_GRAM_PERIOD_OBS)
     int gram_stages = 0;   // ring depth override for gram_kt == 16 (BLR_GRAM_STAGES = 6)
+    int small_ring = 1;    // K1s: per-warp TMA ring for 16 < D <= 64, D % 8 == 0, aligned ColVecs (BLR_SMALL_RING=0: register-fed kernel)
     int rand_pp = 1;       // K7: 1 = two consumer groups on alternating point tiles when the draws are SUPPLIED (8.2 ms against 9.6 ms at
                            // D = 512, N* = 2^22, S = 64), single-group kernel for device draws (9.79 ms; two-group 9.97); 0 = always
                            // single-group, 2 = always two-group (BLR_RAND_PP)

@@ -602,7 +602,12 @@ int sample_finite_fast(blr_ctx* ctx, const blr_x* x, const double* Wsamp_dev, in
 // Four pairs per call (one point, samples s0 + 8 j + {0, 1}, j = 0..3): the four Philox -> log / sincospi -> sqrt chains are
 // independent and interleave; 32 strictly serial single-pair calls made a group's epilogue nearly as long as the other
 // group's main loop (two-group kernel with device draws 9.94 ms against 8.57 ms with supplied draws, D = 512, N* = 2^22).
-__device__ __noinline__ void rand_emit4(double* __restrict__ Y, const double* __restrict__ Zy, int64_t ldy, int64_t ldz, int S,
+#ifdef BLR_EMIT_INLINE  // experiment only: the epilogue inlined 8 x per thread (instruction-cache bound, see above)
+#define BLR_EMIT_ATTR __forceinline__
+#else
+#define BLR_EMIT_ATTR __noinline__
+#endif
+__device__ BLR_EMIT_ATTR void rand_emit4(double* __restrict__ Y, const double* __restrict__ Zy, int64_t ldy, int64_t ldz, int S,
                                         uint64_t seed, uint64_t ctr0, uint64_t Ng, int64_t n, int s0, double sd, double a00,
                                         double a01, double a10, double a11, double a20, double a21, double a30, double a31) {
     const double a[4][2] = {{a00, a01}, {a10, a11}, {a20, a21}, {a30, a31}};
@@ -657,7 +662,7 @@ struct Smem {
     Stage st[GROUPS][STAGES];
     unsigned long long full[GROUPS][STAGES];
     unsigned long long empty[GROUPS][STAGES];
-    int go;  // group 0 is half way through its first tile: group 1 may start
+    unsigned long long go;  // mbarrier, one arrival: group 0 is half way through its first tile, group 1 may start
 };
 }  // namespace rp
 
@@ -673,9 +678,10 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rand_pp_kernel(const RandParam
                 mbar_init(smem_u32(&sm.full[gi][i]), RING_LANES);
                 mbar_init(smem_u32(&sm.empty[gi][i]), GROUP_WARPS * RING_LANES);
             }
-        sm.go = 0;
+        mbar_init(smem_u32(&sm.go), 1);
         mbar_fence_init();
     }
+    fence_proxy_async();
     __syncthreads();  // no zero fill: every byte of a stage is written by the TMA boxes of the phase that is read
     const int64_t ntiles = (p.N + TP - 1) / TP;
     const int nsb = (p.S + TS - 1) / TS;
@@ -710,12 +716,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rand_pp_kernel(const RandParam
     int off[4];  // swizzled offset of (row g, feature 4 j + kq) within an 8-row block
 #pragma unroll
     for (int j = 0; j < 4; ++j) off[j] = swz128(g, j * 4 + kq);
-    if (grp == 1) {  // start half a tile behind group 0
-        if (lane == 0)
-            while (*reinterpret_cast<volatile int*>(&sm.go) == 0) {
-            }
-        __syncwarp();
-    }
+    if (grp == 1) mbar_wait(smem_u32(&sm.go), 0u);  // start half a tile behind group 0
     int it = 0;
     bool first = true;
     for (int64_t tile = blockIdx.x + (int64_t)grp * gridDim.x; tile < ntiles; tile += (int64_t)GROUPS * gridDim.x) {
@@ -745,8 +746,7 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rand_pp_kernel(const RandParam
                         for (int ni = 0; ni < 8; ++ni) dmma884(acc[mi][ni], a[mi], b[ni]);
                 }
                 ring_release(smem_u32(&sm.empty[grp][stg]), lane);
-                if (first && grp == 0 && warp == 0 && lane == 0 && sb == 0 && si == nst / 2)
-                    *reinterpret_cast<volatile int*>(&sm.go) = 1;
+                if (first && grp == 0 && warp == 0 && lane == 0 && sb == 0 && si == nst / 2) mbar_arrive(smem_u32(&sm.go));
             }
             first = false;
 #pragma unroll

@@ -98,6 +98,43 @@ def test_sufficient_statistics(D, N, zero_mean, scalar_noise, layout):
     assert abs(ℓ - 2 * ℓo) <= 1e-11 * max(abs(2 * ℓo), 1.0)
 
 
+@pytest.mark.parametrize("D", [24, 32, 40, 48, 56, 64])
+@pytest.mark.parametrize("N,zero_mean,scalar_noise,pad", [(1003, False, False, 0), (40013, True, True, 0), (5000, False, False, 6)])
+def test_small_d_ring_kernel(D, N, zero_mean, scalar_noise, pad, monkeypatch):
+    """K1s with the per-warp TMA ring (16 < D <= 64, D % 8 == 0, aligned ColVecs): every block width D / 8 = 3..8, ragged N
+    (partial last stage, warps without work), dense columns (one bulk copy per stage) and a padded leading dimension (one copy
+    per observation), against the oracle -- and against the register-fed kernel it replaces (BLR_SMALL_RING=0)."""
+    import ctypes as C
+
+    import torch
+
+    from blr_b200.runtime import make_noise
+
+    X, mw, _, σ2, y = problem(D, N, seed=D * 11 + N, zero_mean=zero_mean, scalar_noise=scalar_noise)
+    Go, ro, qo, ℓo = ref.gram_stats(X, y, σ2, mw, chunk=4096)
+    got = []
+    for ring in ("1", "0"):
+        monkeypatch.setenv("BLR_SMALL_RING", ring)
+        ctx = blr.Context(0)
+        if pad:
+            Xt = torch.zeros((N, D + pad), dtype=torch.float64, device="cuda")  # ColVecs with ld = D + pad (even)
+            Xt[:, :D] = torch.from_numpy(np.ascontiguousarray(X.T)).cuda()
+            Xd = blr.DeviceMatrix.wrap_torch(ctx, Xt[:, :D], 0)
+        else:
+            Xd = blr.DeviceMatrix.upload(ctx, X, 0)
+        yd = blr.DeviceVector.upload(ctx, y)
+        noise, keep = make_noise(ctx, σ2, N)
+        st = blr.Stats(ctx, D)
+        mwc = np.ascontiguousarray(mw)
+        ctx.check(ctx.lib.blr_stats_accumulate(ctx.handle, st.handle, mwc.ctypes.data_as(C.c_void_p), Xd.handle, yd.handle, C.byref(noise)))
+        G, r, q, ℓ, n = st.unpack()
+        assert n == N and np.array_equal(G, G.T)
+        assert relerr(G, Go) < 1e-12 and relerr(r, ro) < 1e-11
+        assert abs(q - qo) <= 1e-11 * abs(qo) and abs(ℓ - ℓo) <= 1e-11 * max(abs(ℓo), 1.0)
+        got.append((G, r))
+    assert relerr(got[0][0], got[1][0]) < 1e-13 and relerr(got[0][1], got[1][1]) < 1e-12
+
+
 def test_statistics_bit_reproducible():
     X, mw, _, σ2, y = problem(256, 30011, seed=5)
     ctx = blr.default_context()
