@@ -602,12 +602,7 @@ int sample_finite_fast(blr_ctx* ctx, const blr_x* x, const double* Wsamp_dev, in
 // Four pairs per call (one point, samples s0 + 8 j + {0, 1}, j = 0..3): the four Philox -> log / sincospi -> sqrt chains are
 // independent and interleave; 32 strictly serial single-pair calls made a group's epilogue nearly as long as the other
 // group's main loop (two-group kernel with device draws 9.94 ms against 8.57 ms with supplied draws, D = 512, N* = 2^22).
-#ifdef BLR_EMIT_INLINE  // experiment only: the epilogue inlined 8 x per thread (instruction-cache bound, see above)
-#define BLR_EMIT_ATTR __forceinline__
-#else
-#define BLR_EMIT_ATTR __noinline__
-#endif
-__device__ BLR_EMIT_ATTR void rand_emit4(double* __restrict__ Y, const double* __restrict__ Zy, int64_t ldy, int64_t ldz, int S,
+__device__ __noinline__ void rand_emit4(double* __restrict__ Y, const double* __restrict__ Zy, int64_t ldy, int64_t ldz, int S,
                                         uint64_t seed, uint64_t ctr0, uint64_t Ng, int64_t n, int s0, double sd, double a00,
                                         double a01, double a10, double a11, double a20, double a21, double a30, double a31) {
     const double a[4][2] = {{a00, a01}, {a10, a11}, {a20, a21}, {a30, a31}};
@@ -659,10 +654,11 @@ struct __align__(1024) Stage {
 };
 constexpr uint32_t STAGE_BYTES = (uint32_t)((TP + TS) * 16 * sizeof(double));
 struct Smem {
-    Stage st[GROUPS][STAGES];
+    // barriers first; the stages follow at the next 1 KB boundary
     unsigned long long full[GROUPS][STAGES];
     unsigned long long empty[GROUPS][STAGES];
     unsigned long long go;  // mbarrier, one arrival: group 0 is half way through its first tile, group 1 may start
+    Stage st[GROUPS][STAGES];
 };
 }  // namespace rp
 
@@ -691,6 +687,11 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rand_pp_kernel(const RandParam
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         const int grp = warp - CONSUMER_WARPS;
         if (grp >= GROUPS) return;
+        // Barrier addresses as plain registers, opaque to the optimiser: ptxas otherwise addresses both barriers with NEGATIVE
+        // immediates off one shared base register ([R + -0x100]), which compute-sanitizer synccheck mis-resolves -- it reported
+        // every first wait as "Missing init" and faulted the kernel (tool-only; same SASS otherwise).
+        uint32_t ebase = smem_u32(&sm.empty[grp][0]), fbase = smem_u32(&sm.full[grp][0]);
+        asm volatile("" : "+r"(ebase), "+r"(fbase));
         int it = 0;
         // the CTA's j-th tile is blockIdx.x + j gridDim.x; group grp takes j = grp, grp + 2, ...
         for (int64_t tile = blockIdx.x + (int64_t)grp * gridDim.x; tile < ntiles; tile += (int64_t)GROUPS * gridDim.x) {
@@ -698,9 +699,9 @@ __global__ void __launch_bounds__(rp::THREADS, 1) rand_pp_kernel(const RandParam
             for (int sb = 0; sb < nsb; ++sb)
                 for (int si = 0; si < nst; ++si, ++it) {
                     const int stg = it % STAGES;
-                    mbar_wait(smem_u32(&sm.empty[grp][stg]), ((uint32_t)(it / STAGES) & 1u) ^ 1u);
+                    mbar_wait(ebase + 8u * (uint32_t)stg, ((uint32_t)(it / STAGES) & 1u) ^ 1u);
                     Stage& S = sm.st[grp][stg];
-                    const uint32_t bar = smem_u32(&sm.full[grp][stg]);
+                    const uint32_t bar = fbase + 8u * (uint32_t)stg;
                     ring_expect(bar, STAGE_BYTES, lane);  // out-of-range features / points / samples are zero-filled and counted
                     if (lane == 0) {
                         tma_load_2d(smem_u32(S.a), &tmx, si * KT, p0, bar);
