@@ -992,7 +992,7 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
     BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], sm));
 
     // ---- smallest D: one warp holds the whole Gram matrix, observations stream straight from HBM, K0 fused in
-    if (gram_small_fused(D)) {
+    if (gram_small_fused(ctx, x)) {
         BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[1], sm));
         BLR_TRY(gram_small(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, nullptr, nullptr, ctx->small + SMALL_PREP, 0));
         BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], sm));

@@ -216,10 +216,15 @@ constexpr int STAGES = 4;  // per warp
 constexpr int ctas_per_sm(int MI) { return MI <= 5 ? 2 : 1; }  // registers: <= 128 per thread up to D = 40; ring: 10 KB x D / 8 x ... per CTA
 }  // namespace gr
 
-template <int MI>
+// The preparation pass is fused in exactly as in the D <= 16 kernel: per trip of 32 observations (four stages) lane L handles
+// observation n + L on its own (coalesced loads of y and σ², one divide and one log per observation, next trip prefetched),
+// the fragment lanes of a k4-step fetch s and y by shuffle and, with a non-zero prior mean, form x'mw from the fragments they
+// already hold (three xor-shuffles over the feature lanes).  No s / t arrays, no second pass over X for mw != 0.
+template <int MI, bool HAS_MEAN>
 __global__ void __launch_bounds__(gr::THREADS, gr::ctas_per_sm(MI))
-    gram_small_ring_kernel(const double* __restrict__ X, int64_t ld, int64_t N, const double* __restrict__ s,
-                           const double* __restrict__ t, double* __restrict__ P, double* __restrict__ Pr, int64_t obs_per_warp) {
+    gram_small_ring_kernel(const double* __restrict__ X, int64_t ld, int64_t N, const double* __restrict__ y,
+                           const double* __restrict__ sigma2, double sigma2_scalar, const double* __restrict__ mw,
+                           double* __restrict__ P, double* __restrict__ Pr, double* __restrict__ Pq, int64_t obs_per_warp) {
     using namespace gr;
     constexpr int DP = MI * 8;  // == D
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -256,31 +261,69 @@ __global__ void __launch_bounds__(gr::THREADS, gr::ctas_per_sm(MI))
     };
 
     double acc[MI][MI][2];
-    double racc[MI];
+    double racc[MI], mwr[MI];
 #pragma unroll
     for (int mi = 0; mi < MI; ++mi) {
         racc[mi] = 0.0;
+        mwr[mi] = HAS_MEAN ? mw[mi * 8 + g] : 0.0;
 #pragma unroll
         for (int ni = 0; ni < MI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
     }
-#pragma unroll 1
-    for (int j = 0; j < STAGES - 1; ++j) issue(j);
-    double skn[2], tkn[2];  // s, t of the NEXT stage's fragment lanes (one stage of prefetch hides their global-load latency)
-    auto load_st = [&](int j) {
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int64_t nk = n0 + (int64_t)j * KO + 4 * u + kq;
-            const bool ok = nk < n1;
-            skn[u] = ok ? s[nk] : 0.0;
-            tkn[u] = ok ? t[nk] : 0.0;
+    double qacc = 0.0, lacc = 0.0;
+    // Σ log σ² without a log per observation (the scalar fp64 pipe is the tensor pipe): σ² = m 2^e with m in [1, 2); the lane keeps
+    // the running product of the m's and the integer sum of the e's and takes ONE log per 512 observations (the product of 512
+    // mantissas is < 2^512 and carries a relative error of ~512 eps = 6e-14, i.e. an absolute error of 6e-14 in its log).
+    // Anything that is not a positive normal number (<= 0, NaN, inf, denormal) goes through log() itself, which also keeps the
+    // "ℓ not finite => a noise variance is not positive" contract.
+    double lmant = 1.0;
+    int lexp = 0, lcnt = 0;
+    auto log_acc = [&](double v) {
+        const long long bits = __double_as_longlong(v);
+        const int ef = (int)((bits >> 52) & 0x7ff);
+        if (bits > 0 && ef != 0 && ef != 0x7ff) {
+            lmant *= __longlong_as_double((bits & 0x000fffffffffffffll) | 0x3ff0000000000000ll);
+            lexp += ef - 1023;
+            if (++lcnt == 512) {
+                lacc += fma((double)lexp, 0.69314718055994530942, log(lmant));
+                lmant = 1.0;
+                lexp = 0;
+                lcnt = 0;
+            }
+        } else {
+            lacc += log(v);
         }
     };
-    load_st(0);
+#pragma unroll 1
+    for (int j = 0; j < STAGES - 1; ++j) issue(j);
+    // lane-own observation of the current trip (vo, yo -> so) and of the next one (vn, yn)
+    double vo = 1.0, yo = 0.0, so = 0.0, vn, yn;
+    auto load_vy = [&](int64_t nb, double& v, double& yy) {
+        const int64_t no = nb + lane;
+        const bool ok = no < n1;
+        v = ok ? (sigma2 ? sigma2[no] : sigma2_scalar) : 1.0;
+        yy = ok ? y[no] : 0.0;
+    };
+    load_vy(n0, vn, yn);
 #pragma unroll 1
     for (int i = 0; i < nstages; ++i) {
         issue(i + STAGES - 1);  // refills the slot this warp finished reading in iteration i - 1
-        const double sk[2] = {skn[0], skn[1]}, tk[2] = {tkn[0], tkn[1]};
-        load_st(i + 1);
+        if ((i & 3) == 0) {     // a new trip of 32 observations
+            const int64_t nb32 = n0 + (int64_t)i * KO;
+            vo = vn;
+            yo = yn;
+            so = (nb32 + lane < n1) ? __drcp_rn(vo) : 0.0;  // correctly rounded: == 1.0 / vo
+            log_acc(vo);                                        // vo == 1 beyond the range
+            load_vy(nb32 + 32, vn, yn);
+        }
+        // s and y of this stage's fragment lanes, fetched from the owning lanes BEFORE waiting for the stage (they do not depend
+        // on its data; inside the k4-steps the shuffles sat on the critical path in front of the first block-MMA)
+        double skv[2], ykv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int src = 8 * (i & 3) + 4 * u + kq;
+            skv[u] = __shfl_sync(0xffffffffu, so, src);
+            ykv[u] = __shfl_sync(0xffffffffu, yo, src);
+        }
         mbar_wait(smem_u32(&bars[warp * STAGES + i % STAGES]), (uint32_t)(i / STAGES) & 1u);
         const double* st = ring + (i % STAGES) * (KO * DP) + g;
 #pragma unroll
@@ -288,10 +331,23 @@ __global__ void __launch_bounds__(gr::THREADS, gr::ctas_per_sm(MI))
             double a[MI], b[MI];
 #pragma unroll
             for (int mi = 0; mi < MI; ++mi) a[mi] = st[(4 * u + kq) * DP + mi * 8];
+            const double sku = skv[u];
+            double dk = ykv[u];
+            if (HAS_MEAN) {
+                double dot = 0.0;
+#pragma unroll
+                for (int mi = 0; mi < MI; ++mi) dot = fma(a[mi], mwr[mi], dot);
+                dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+                dot += __shfl_xor_sync(0xffffffffu, dot, 8);
+                dot += __shfl_xor_sync(0xffffffffu, dot, 16);
+                dk -= dot;
+            }
+            const double tku = sku * dk;
+            qacc = fma(tku, dk, qacc);  // identical on the eight feature lanes of an observation; lanes g == 0 count
 #pragma unroll
             for (int mi = 0; mi < MI; ++mi) {
-                racc[mi] = fma(a[mi], tk[u], racc[mi]);
-                b[mi] = a[mi] * sk[u];
+                racc[mi] = fma(a[mi], tku, racc[mi]);
+                b[mi] = a[mi] * sku;
             }
 #pragma unroll
             for (int mi = 0; mi < MI; ++mi)
@@ -306,11 +362,21 @@ __global__ void __launch_bounds__(gr::THREADS, gr::ctas_per_sm(MI))
         racc[mi] += __shfl_xor_sync(0xffffffffu, racc[mi], 1);
         racc[mi] += __shfl_xor_sync(0xffffffffu, racc[mi], 2);
     }
+    // q: the four observation lanes with g == 0; ℓ: all 32 lanes (xor tree: fixed order)
+    if (g != 0) qacc = 0.0;
+    qacc = warp_sum(qacc);
+    lacc += fma((double)lexp, 0.69314718055994530942, log(lmant));
+    lacc = warp_sum(lacc);
     // CTA reduction in warp order (fixed => bit-reproducible); the tile aliases the (now idle) rings
     __syncthreads();
     double* tile = ring_all;
     double* rsum = ring_all + DP * DP;
+    double* qsum = rsum + DP;  // [WARPS][2]
     for (int e = tid; e < DP * DP + DP; e += THREADS) tile[e] = 0.0;
+    if (lane == 0) {
+        qsum[2 * warp] = qacc;
+        qsum[2 * warp + 1] = lacc;
+    }
     for (int w = 0; w < WARPS; ++w) {
         __syncthreads();
         if (warp == w) {
@@ -330,6 +396,15 @@ __global__ void __launch_bounds__(gr::THREADS, gr::ctas_per_sm(MI))
     double* Pt = P + (int64_t)blockIdx.x * (DP * DP);
     for (int e = tid; e < DP * DP; e += THREADS) Pt[e] = tile[e];
     if (tid < DP) Pr[(int64_t)blockIdx.x * DP + tid] = rsum[tid];
+    if (tid == 0) {
+        double q = 0.0, l = 0.0;
+        for (int w = 0; w < WARPS; ++w) {
+            q += qsum[2 * w];
+            l += qsum[2 * w + 1];
+        }
+        Pq[2 * blockIdx.x] = q;
+        Pq[2 * blockIdx.x + 1] = l;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -504,12 +579,11 @@ static int launch_small(blr_ctx* ctx, blr_stats* st, const blr_x* x, const doubl
 }
 
 template <int MI>
-static int launch_ring(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double* s, const double* t, double* partial,
-                       int partial_blocks) {
+static int launch_ring(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double* y, const double* sigma2, double sigma2_scalar,
+                       const double* mw_dev, bool mw_is_zero, double* partial) {
     constexpr int DP = MI * 8;
     const int64_t N = x->N;
     const int smem = gr::WARPS * gr::STAGES * gr::KO * DP * (int)sizeof(double) + gr::WARPS * gr::STAGES * (int)sizeof(unsigned long long);
-    BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_small_ring_kernel<MI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int64_t groups = (N + 31) / 32;
     const int nblocks = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * gr::ctas_per_sm(MI), (groups + gr::WARPS - 1) / gr::WARPS));
     const int64_t total_warps = (int64_t)nblocks * gr::WARPS;
@@ -517,11 +591,19 @@ static int launch_ring(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double
     BLR_TRY(ensure_ws(ctx, (size_t)nblocks * (DP * DP + DP) * sizeof(double)));
     double* P = ctx->ws;
     double* Pr = ctx->ws + (size_t)nblocks * DP * DP;
-    gram_small_ring_kernel<MI><<<nblocks, gr::THREADS, smem, ctx->stream>>>(x->p, x->ld, N, s, t, P, Pr, obs_per_warp);
+    if (mw_is_zero) {
+        BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_small_ring_kernel<MI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        gram_small_ring_kernel<MI, false><<<nblocks, gr::THREADS, smem, ctx->stream>>>(x->p, x->ld, N, y, sigma2, sigma2_scalar, mw_dev, P, Pr,
+                                                                                      partial, obs_per_warp);
+    } else {
+        BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_small_ring_kernel<MI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        gram_small_ring_kernel<MI, true><<<nblocks, gr::THREADS, smem, ctx->stream>>>(x->p, x->ld, N, y, sigma2, sigma2_scalar, mw_dev, P, Pr,
+                                                                                     partial, obs_per_warp);
+    }
     BLR_CHECK_LAUNCH(ctx, "gram_small_ring_kernel");
     BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     gram_small_reduce_kernel<<<(DP * DP + 255) / 256, 256, 0, ctx->stream>>>(P, Pr, DP, nblocks, DP, st->G(), st->r(), st->scal(),
-                                                                            partial, partial_blocks, (double)N);
+                                                                            partial, nblocks, (double)N);
     BLR_CHECK_LAUNCH(ctx, "gram_small_reduce_kernel");
     return 0;
 }
@@ -532,7 +614,8 @@ static bool ring_eligible(const blr_ctx* ctx, const blr_x* x) {
            (reinterpret_cast<uintptr_t>(x->p) & 15) == 0 && x->N >= 64;
 }
 
-bool gram_small_fused(int64_t D) { return D <= 16; }
+// true: the small-D kernel forms s, t, q, ℓ itself (no separate preparation pass, `partial` receives 2 doubles per CTA)
+bool gram_small_fused(const blr_ctx* ctx, const blr_x* x) { return x->D <= 16 || ring_eligible(ctx, x); }
 
 template <int DT>
 static int launch_tiny(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double* y, const double* sigma2,
@@ -577,12 +660,12 @@ int gram_small(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double* y, con
         return launch_small<2, true>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, s, t, partial, partial_blocks);
     if (ring_eligible(ctx, x)) {
         switch (D / 8) {
-            case 3: return launch_ring<3>(ctx, st, x, s, t, partial, partial_blocks);
-            case 4: return launch_ring<4>(ctx, st, x, s, t, partial, partial_blocks);
-            case 5: return launch_ring<5>(ctx, st, x, s, t, partial, partial_blocks);
-            case 6: return launch_ring<6>(ctx, st, x, s, t, partial, partial_blocks);
-            case 7: return launch_ring<7>(ctx, st, x, s, t, partial, partial_blocks);
-            default: return launch_ring<8>(ctx, st, x, s, t, partial, partial_blocks);
+            case 3: return launch_ring<3>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, partial);
+            case 4: return launch_ring<4>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, partial);
+            case 5: return launch_ring<5>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, partial);
+            case 6: return launch_ring<6>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, partial);
+            case 7: return launch_ring<7>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, partial);
+            default: return launch_ring<8>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, partial);
         }
     }
     if (D <= 32)

@@ -148,7 +148,7 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
 
 // ---- gram_small.cu: D <= 64, any layout / alignment; adds this shard's statistics into st.  D <= 16: K0 fused (reads
 // y, σ² itself, s / t unused, `partial` is scratch for 2 doubles per CTA); otherwise s, t, partial come from prep_kernel.
-bool gram_small_fused(int64_t D);
+bool gram_small_fused(const blr_ctx* ctx, const blr_x* x);
 int gram_small(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double* y, const double* sigma2, double sigma2_scalar,
                const double* mw_dev, bool mw_is_zero, const double* s, const double* t, double* partial, int partial_blocks);
 

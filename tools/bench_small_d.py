@@ -20,7 +20,8 @@ for D, N in [(2, 1 << 26), (8, 1 << 26), (16, 1 << 25), (24, 1 << 25), (32, 1 <<
     s2, y = blr.DeviceVector.alloc(ctx, N), blr.DeviceVector.alloc(ctx, N)
     ctx.check(ctx.lib.blr_vec_synth_noise(ctx.handle, s2.handle, 0, 0))
     ctx.check(ctx.lib.blr_vec_synth_targets(ctx.handle, X.handle, s2.handle, 0, 0, y.handle))
-    f = blr.BayesianLinearRegressor(np.zeros(D), blr.Diagonal(np.ones(D)))
+    mw0 = 0.1 * np.random.default_rng(3).standard_normal(D) if os.environ.get("BLR_BENCH_MW") == "1" else np.zeros(D)
+    f = blr.BayesianLinearRegressor(mw0, blr.Diagonal(np.ones(D)))
     fx = f(blr.ColVecs(X), s2)
     for _ in range(3):
         blr.posterior_and_logpdf(fx, y)
