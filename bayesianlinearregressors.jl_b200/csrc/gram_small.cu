@@ -198,11 +198,11 @@ __global__ void __launch_bounds__(gs::THREADS, gs::ctas_per_sm(MI))
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// 16 < D <= 64, D a multiple of 8, ColVecs with 16-byte aligned observations: the same warp-owns-the-Gram-matrix scheme, but the
+// 16 < D <= 64, D even, ColVecs with 16-byte aligned observations: the same warp-owns-the-Gram-matrix scheme, but the
 // observations reach the operand fragments through a PER-WARP ring in shared memory fed by TMA bulk copies, so that every warp
 // keeps three stages of observations in flight.  The register-fed kernel above has one batch of two k4-steps in flight per
 // warp and only 8 warps per SM at D = 64 (the accumulators take the register file): it is latency-bound between the HBM and
-// the tensor roofline (D = 64: 44 % of the DMMA peak, D = 32: 70 % of HBM).  The block grid is exactly D / 8 wide (the kernel
+// the tensor roofline (D = 64: 44 % of the DMMA peak, D = 32: 70 % of HBM).  The block grid is exactly ceil(D / 8) wide (the kernel
 // above rounds 33..64 features up to 8 x 8 blocks: 36 block-MMAs per step at D = 40 instead of 15).
 // One stage = 8 observations = two k4-steps; with ld == D a stage is ONE contiguous bulk copy (8 D doubles), otherwise one
 // copy per observation.  The warp that consumes a slot is the warp that refills it (program order + __syncwarp), so the ring
@@ -222,11 +222,14 @@ constexpr int ctas_per_sm(int MI) { return MI <= 5 ? 2 : 1; }  // registers: <= 
 // already hold (three xor-shuffles over the feature lanes).  No s / t arrays, no second pass over X for mw != 0.
 template <int MI, bool HAS_MEAN>
 __global__ void __launch_bounds__(gr::THREADS, gr::ctas_per_sm(MI))
-    gram_small_ring_kernel(const double* __restrict__ X, int64_t ld, int64_t N, const double* __restrict__ y,
+    gram_small_ring_kernel(const double* __restrict__ X, int64_t ld, int D, int64_t N, const double* __restrict__ y,
                            const double* __restrict__ sigma2, double sigma2_scalar, const double* __restrict__ mw,
                            double* __restrict__ P, double* __restrict__ Pr, double* __restrict__ Pq, int64_t obs_per_warp) {
     using namespace gr;
-    constexpr int DP = MI * 8;  // == D
+    // D (even) features in DP = 8 MI >= D block rows.  A stage slot holds KO observations D doubles apart (dense, as they arrive) in
+    // a buffer of KO * DP doubles: fragment rows >= D read the head of the next observation (finite values inside the slot) and
+    // only ever feed accumulator rows / columns >= D, which are never written out.
+    constexpr int DP = MI * 8;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* ring_all = reinterpret_cast<double*>(smem_raw);                                    // [WARPS][STAGES][KO * DP]
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(ring_all + WARPS * STAGES * KO * DP);  // [WARPS][STAGES]
@@ -244,19 +247,19 @@ __global__ void __launch_bounds__(gr::THREADS, gr::ctas_per_sm(MI))
     fence_proxy_async();
     __syncthreads();
 
-    const bool dense = (ld == DP);
+    const bool dense = (ld == D);
     auto issue = [&](int j) {  // stage j of this warp -> slot j % STAGES
         if (j >= nstages) return;
         const int64_t nb = n0 + (int64_t)j * KO;
         const int cnt = (int)min((int64_t)KO, n1 - nb);
         const uint32_t bar = smem_u32(&bars[warp * STAGES + j % STAGES]);
         double* dst = ring + (j % STAGES) * (KO * DP);
-        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)cnt * DP * 8u);
+        if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)cnt * (uint32_t)D * 8u);
         __syncwarp();
         if (dense) {
-            if (lane == 0) bulk_g2s(smem_u32(dst), X + nb * ld, (uint32_t)cnt * DP * 8u, bar);
+            if (lane == 0) bulk_g2s(smem_u32(dst), X + nb * ld, (uint32_t)cnt * (uint32_t)D * 8u, bar);
         } else if (lane < cnt) {
-            bulk_g2s(smem_u32(dst + lane * DP), X + (nb + lane) * ld, DP * 8u, bar);
+            bulk_g2s(smem_u32(dst + lane * D), X + (nb + lane) * ld, (uint32_t)D * 8u, bar);
         }
     };
 
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(gr::THREADS, gr::ctas_per_sm(MI))
 #pragma unroll
     for (int mi = 0; mi < MI; ++mi) {
         racc[mi] = 0.0;
-        mwr[mi] = HAS_MEAN ? mw[mi * 8 + g] : 0.0;
+        mwr[mi] = (HAS_MEAN && mi * 8 + g < D) ? mw[mi * 8 + g] : 0.0;  // rows >= D must not enter x'mw
 #pragma unroll
         for (int ni = 0; ni < MI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
     }
@@ -330,7 +333,7 @@ __global__ void __launch_bounds__(gr::THREADS, gr::ctas_per_sm(MI))
         for (int u = 0; u < 2; ++u) {
             double a[MI], b[MI];
 #pragma unroll
-            for (int mi = 0; mi < MI; ++mi) a[mi] = st[(4 * u + kq) * DP + mi * 8];
+            for (int mi = 0; mi < MI; ++mi) a[mi] = st[(4 * u + kq) * D + mi * 8];
             const double sku = skv[u];
             double dk = ykv[u];
             if (HAS_MEAN) {
@@ -591,26 +594,27 @@ static int launch_ring(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double
     BLR_TRY(ensure_ws(ctx, (size_t)nblocks * (DP * DP + DP) * sizeof(double)));
     double* P = ctx->ws;
     double* Pr = ctx->ws + (size_t)nblocks * DP * DP;
+    const int D = (int)x->D;
     if (mw_is_zero) {
         BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_small_ring_kernel<MI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        gram_small_ring_kernel<MI, false><<<nblocks, gr::THREADS, smem, ctx->stream>>>(x->p, x->ld, N, y, sigma2, sigma2_scalar, mw_dev, P, Pr,
-                                                                                      partial, obs_per_warp);
+        gram_small_ring_kernel<MI, false><<<nblocks, gr::THREADS, smem, ctx->stream>>>(x->p, x->ld, D, N, y, sigma2, sigma2_scalar, mw_dev, P,
+                                                                                      Pr, partial, obs_per_warp);
     } else {
         BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_small_ring_kernel<MI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        gram_small_ring_kernel<MI, true><<<nblocks, gr::THREADS, smem, ctx->stream>>>(x->p, x->ld, N, y, sigma2, sigma2_scalar, mw_dev, P, Pr,
-                                                                                     partial, obs_per_warp);
+        gram_small_ring_kernel<MI, true><<<nblocks, gr::THREADS, smem, ctx->stream>>>(x->p, x->ld, D, N, y, sigma2, sigma2_scalar, mw_dev, P,
+                                                                                     Pr, partial, obs_per_warp);
     }
     BLR_CHECK_LAUNCH(ctx, "gram_small_ring_kernel");
     BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-    gram_small_reduce_kernel<<<(DP * DP + 255) / 256, 256, 0, ctx->stream>>>(P, Pr, DP, nblocks, DP, st->G(), st->r(), st->scal(),
+    gram_small_reduce_kernel<<<(DP * DP + 255) / 256, 256, 0, ctx->stream>>>(P, Pr, DP, nblocks, D, st->G(), st->r(), st->scal(),
                                                                             partial, nblocks, (double)N);
     BLR_CHECK_LAUNCH(ctx, "gram_small_reduce_kernel");
     return 0;
 }
 
-// the ring kernel applies to: ColVecs, 16 < D <= 64 with D % 8 == 0, observations 16-byte aligned (BLR_SMALL_RING=0: off)
+// the ring kernel applies to: ColVecs, 16 < D <= 64 with D even, observations 16-byte aligned (BLR_SMALL_RING=0: off)
 static bool ring_eligible(const blr_ctx* ctx, const blr_x* x) {
-    return ctx->small_ring && x->layout == BLR_COLVECS && x->D > 16 && x->D <= 64 && (x->D % 8) == 0 && (x->ld % 2) == 0 &&
+    return ctx->small_ring && x->layout == BLR_COLVECS && x->D > 16 && x->D <= 64 && (x->D % 2) == 0 && (x->ld % 2) == 0 &&
            (reinterpret_cast<uintptr_t>(x->p) & 15) == 0 && x->N >= 64;
 }
 
@@ -659,7 +663,7 @@ int gram_small(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double* y, con
     if (D <= 16)
         return launch_small<2, true>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, s, t, partial, partial_blocks);
     if (ring_eligible(ctx, x)) {
-        switch (D / 8) {
+        switch ((D + 7) / 8) {
             case 3: return launch_ring<3>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, partial);
             case 4: return launch_ring<4>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, partial);
             case 5: return launch_ring<5>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, partial);

@@ -98,10 +98,10 @@ def test_sufficient_statistics(D, N, zero_mean, scalar_noise, layout):
     assert abs(ℓ - 2 * ℓo) <= 1e-11 * max(abs(2 * ℓo), 1.0)
 
 
-@pytest.mark.parametrize("D", [24, 32, 40, 48, 56, 64])
+@pytest.mark.parametrize("D", [18, 24, 32, 40, 48, 50, 56, 62, 64])
 @pytest.mark.parametrize("N,zero_mean,scalar_noise,pad", [(1003, False, False, 0), (40013, True, True, 0), (5000, False, False, 6)])
 def test_small_d_ring_kernel(D, N, zero_mean, scalar_noise, pad, monkeypatch):
-    """K1s with the per-warp TMA ring (16 < D <= 64, D % 8 == 0, aligned ColVecs): every block width D / 8 = 3..8, ragged N
+    """K1s with the per-warp TMA ring (16 < D <= 64, D even, aligned ColVecs): every block width ceil(D / 8) = 3..8, D not a multiple of 8 (the reference's D = 50 example shape), ragged N
     (partial last stage, warps without work), dense columns (one bulk copy per stage) and a padded leading dimension (one copy
     per observation), against the oracle -- and against the register-fed kernel it replaces (BLR_SMALL_RING=0)."""
     import ctypes as C

@@ -15,7 +15,7 @@ import blr_b200 as blr  # noqa: E402
 ctx = blr.Context(0)
 blr.set_default_context(ctx)
 hbm = ctx.calibrate()["hbm_gbs"]
-for D, N in [(2, 1 << 26), (8, 1 << 26), (16, 1 << 25), (24, 1 << 25), (32, 1 << 25), (40, 1 << 24), (48, 1 << 24), (64, 1 << 24)]:
+for D, N in [(2, 1 << 26), (8, 1 << 26), (16, 1 << 25), (24, 1 << 25), (32, 1 << 25), (40, 1 << 24), (48, 1 << 24), (50, 1 << 24), (64, 1 << 24)]:
     X = blr.DeviceMatrix.alloc(ctx, D, N).synth_(0)
     s2, y = blr.DeviceVector.alloc(ctx, N), blr.DeviceVector.alloc(ctx, N)
     ctx.check(ctx.lib.blr_vec_synth_noise(ctx.handle, s2.handle, 0, 0))
