@@ -43,8 +43,10 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(const double* __rest
                                                             double* __restrict__ t, double* __restrict__ partial) {
     __shared__ double red[32];
     double q = 0.0, l = 0.0;
-    if (HAS_MEAN && LAYOUT == BLR_COLVECS) {
-        // one warp per observation: the column is contiguous, lanes stride over features.
+    if (HAS_MEAN && LAYOUT == BLR_COLVECS && D > 64) {
+        // one warp per observation: the column is contiguous, lanes stride over features.  (Only for D > 64: with fewer features
+        // most lanes idle and a warp per observation is an order of magnitude too many warps -- 13.7 ms for 2^25 observations of
+        // 24 features; those take the thread-per-observation branch below, whose strided loads are served sector by sector from L1.)
         const int lane = threadIdx.x & 31;
         const int64_t warps = (int64_t)gridDim.x * (PREP_THREADS / 32);
         // 16-byte streaming loads with four independent accumulator chains when the columns are 16-byte aligned (D and ld even):
@@ -97,8 +99,13 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(const double* __rest
         for (int64_t n = (int64_t)blockIdx.x * PREP_THREADS + threadIdx.x; n < npad; n += stride) {
             if (n < N) {
                 double dot = 0.0;
-                if (HAS_MEAN) {  // RowVecs: feature-contiguous, threads of a warp read consecutive n
-                    for (int d = 0; d < D; ++d) dot = fma(X[(int64_t)d * ld + n], __ldg(mw + d), dot);
+                if (HAS_MEAN) {
+                    if (LAYOUT == BLR_COLVECS) {  // small D: each thread walks its own (contiguous) observation
+                        const double* col = X + n * ld;
+                        for (int d = 0; d < D; ++d) dot = fma(col[d], __ldg(mw + d), dot);
+                    } else {  // RowVecs: feature-contiguous, threads of a warp read consecutive n
+                        for (int d = 0; d < D; ++d) dot = fma(X[(int64_t)d * ld + n], __ldg(mw + d), dot);
+                    }
                 }
                 const double v = sigma2 ? sigma2[n] : sigma2_scalar;
                 const double sn = 1.0 / v, dl = y[n] - dot;
@@ -1007,7 +1014,7 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
     double* t = ctx->nbuf + npad;
     const int max_blocks = ctx->sm_count * 8;
     int prep_blocks;
-    const bool warp_per_obs = (!mw_is_zero && x->layout == BLR_COLVECS);
+    const bool warp_per_obs = (!mw_is_zero && x->layout == BLR_COLVECS && D > 64);  // must match prep_kernel's branch
     {
         const int64_t per_block = warp_per_obs ? PREP_THREADS / 32 : PREP_THREADS;
         prep_blocks = (int)std::min<int64_t>((npad + per_block - 1) / per_block, max_blocks);
