@@ -42,6 +42,8 @@ SIGNATURES = {
     "blr_last_error": (C.c_char_p, [C.c_void_p]),
     "blr_ctx_sync": (C.c_int, [C.c_void_p]),
     "blr_ctx_stream": (C.c_int, [C.c_void_p, c_void_pp]),
+    "blr_ctx_set_form": (C.c_int, [C.c_void_p, C.c_int]),
+    "blr_ctx_get_form": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "blr_ctx_wait_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "blr_stream_wait_ctx": (C.c_int, [C.c_void_p, C.c_void_p]),
     "blr_launch_count": (C.c_int64, [C.c_void_p]),

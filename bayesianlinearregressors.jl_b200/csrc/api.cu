@@ -272,6 +272,7 @@ int blr_ctx_create(blr_ctx** out, int device) {
         if (atoi(k) == 32) ctx->gram_kt = 32;
     }
     if (const char* v = getenv("BLR_DXD")) ctx->dxd_legacy = (strcmp(v, "legacy") == 0) ? 1 : 0;
+    if (const char* v = getenv("BLR_FORM")) ctx->form = (strcmp(v, "whitened") == 0) ? BLR_FORM_WHITENED : BLR_FORM_DIRECT;
     if (const char* v = getenv("BLR_GRAM_UNIT")) ctx->gram_unit = atoi(v) != 0 ? 1 : 0;
     if (const char* v = getenv("BLR_GRAM_CS")) ctx->gram_cs = atoi(v) != 0 ? 1 : 0;
     if (const char* v = getenv("BLR_VAR_CFG")) ctx->var_cfg = atoi(v) == 0 ? 0 : 1;
@@ -323,6 +324,19 @@ int blr_ctx_sync(blr_ctx* ctx) {
     BLR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
+int blr_ctx_set_form(blr_ctx* ctx, int form) {
+    if (!ctx) return BLR_E_INVALID;
+    if (form != BLR_FORM_DIRECT && form != BLR_FORM_WHITENED) return set_err(ctx, BLR_E_INVALID, "unknown numerical form");
+    ctx->form = form;
+    return 0;
+}
+
+int blr_ctx_get_form(const blr_ctx* ctx, int* form_out) {
+    if (!ctx || !form_out) return BLR_E_INVALID;
+    *form_out = ctx->form;
+    return 0;
+}
+
 int blr_ctx_stream(blr_ctx* ctx, void** stream_out) {
     if (!ctx || !stream_out) return BLR_E_INVALID;
     *stream_out = (void*)ctx->stream;

@@ -575,8 +575,27 @@ int infer_solve(blr_ctx* ctx, const blr_prior* prior, const blr_stats* st, doubl
         logdet_w = sc + 0;
     }
 
-    // ---- Λ' = Λw + G  (kept in p->Lam), a copy to factor in p->L, rhs = r
+    // ---- the reference's whitened form (opt-in): keep the prior factor Lw -- the assembly below overwrites p->L
     const int64_t n2 = D * D;
+    const bool whitened = ctx->form == BLR_FORM_WHITENED;
+    double* Lw = nullptr;
+    auto fail_w = [&](int code) {
+        dev_free(sm, Lw);
+        return fail(code);
+    };
+    if (whitened) {
+        cudaError_t e = dev_alloc(ctx, &Lw, (size_t)n2 * sizeof(double));
+        if (e != cudaSuccess) return fail(cuda_fail(ctx, e, "cudaMalloc(Lw)"));
+        if (diagonal) {
+            rc = diag_factor_dense(ctx, diagd, D, Lw);
+            if (rc != 0) return fail_w(rc);
+        } else {
+            e = cudaMemcpyAsync(Lw, p->L, (size_t)n2 * sizeof(double), cudaMemcpyDeviceToDevice, sm);
+            if (e != cudaSuccess) return fail_w(cuda_fail(ctx, e, "copy Lw"));
+        }
+    }
+
+    // ---- Λ' = Λw + G  (kept in p->Lam), a copy to factor in p->L, rhs = r
     assemble_posterior_kernel<<<(int)std::min<int64_t>((n2 + 255) / 256, ctx->sm_count * 8), 256, 0, sm>>>(
         p->Lam, p->L, st->G(), diagonal ? diagd : nullptr, (int)D, st->r(), rhs);
     BLR_CHECK_LAUNCH(ctx, "assemble_posterior_kernel");
@@ -590,7 +609,13 @@ int infer_solve(blr_ctx* ctx, const blr_prior* prior, const blr_stats* st, doubl
         BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[7], ctx->copy_stream));
         lam_on_copy_stream = true;
     }
-    if (!ctx->dxd_legacy) {
+    if (whitened) {
+        // Lε = chol(Lw^-1 G Lw^-T + I), ..., L' = Lw Lε: the reference's own evaluation order (whitened.cu)
+        rc = dxd_whitened(ctx, p, Lw, st, rhs, usol, mwd, sc, info_post);
+        dev_free(sm, Lw);
+        Lw = nullptr;
+        if (rc != 0) return fail(rc);
+    } else if (!ctx->dxd_legacy) {
         // L = chol(Λ'), z = L^-1 r, u = L^-T z, logdet, z'z, m' = mw + u, logpdf: one cooperative launch (chol_tiled.cu)
         DxdFinalize fin;
         fin.stat_scal = st->scal();

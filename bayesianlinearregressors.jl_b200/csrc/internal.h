@@ -63,6 +63,7 @@ struct blr_ctx {
     size_t tflags_n = 0;
     int dxd_occ = 0;         // resident CTAs per SM of dxd_fused_kernel (occupancy query, cached)
     int dxd_legacy = 0;      // BLR_DXD=legacy: round-1 multi-launch D x D phase (A/B and fallback for debugging)
+    int form = 0;            // BLR_FORM_DIRECT / BLR_FORM_WHITENED (blr_ctx_set_form, BLR_FORM=whitened): whitened.cu
     cudaEvent_t ev[8] = {};
     bool ev_valid[4] = {};
     // stream-K schedule of the Gram fast path (cached by shape)
@@ -164,6 +165,15 @@ struct DxdFinalize {
 // One cooperative launch: A (lower triangle in) -> Cholesky factor (lower, strict upper zeroed); optionally z = L^-1 z in
 // place, u = L^-T z, and the finalize step.  info_dev: 4 device ints, [0] = LAPACK-style info, [1] = noise flag, [3] = abort.
 int dxd_fused(blr_ctx* ctx, double* A, int64_t D, int* info_dev, double* z, double* u, const DxdFinalize* fin);
+
+// ---- whitened.cu (the reference's literal numerical form, opt-in: blr_ctx::form == BLR_FORM_WHITENED)
+int trsm_lower(blr_ctx* ctx, const double* L, int64_t ldl, int64_t D, double* B, int64_t ldb, int64_t K, bool trans);
+int dxd_whitened(blr_ctx* ctx, blr_post* p, const double* Lw, const blr_stats* st, double* rhs, double* usol, const double* mwd,
+                 double* sc, int* info_post);
+int diag_factor_dense(blr_ctx* ctx, const double* diag_dev, int64_t D, double* Lw);
+int solve_alpha(blr_ctx* ctx, const blr_post* p, const blr_x* x, int64_t n0, int64_t n, double* alpha);
+int predict_mean_var_literal(blr_ctx* ctx, blr_post* p, const blr_x* x, const double* sigma2, double sigma2_scalar,
+                             double* mean_dev, double* var_dev);
 
 // ---- chol.cu
 // In-place lower Cholesky of the column-major D x D matrix A (only the lower triangle is read);

@@ -278,6 +278,7 @@ static int launch_var_small(blr_ctx* ctx, blr_post* p, const blr_x* x, const dou
 int predict_mean_var(blr_ctx* ctx, blr_post* p, const blr_x* x, const double* sigma2, double sigma2_scalar,
                      double* mean_dev, double* var_dev) {
     if (x->N == 0) return 0;
+    if (ctx->form == BLR_FORM_WHITENED) return predict_mean_var_literal(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
     if (var_dev && predict_fast_eligible(p, x))
         return predict_mean_var_fast(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
     if (var_dev && p->D <= 64) {
@@ -367,12 +368,14 @@ __global__ void add_diag_noise_kernel(double* __restrict__ C, int64_t N, const d
 int predict_cov(blr_ctx* ctx, blr_post* p, const blr_x* x, const double* sigma2, double sigma2_scalar, double* C_dev) {
     const int64_t D = p->D, N = x->N;
     if (N == 0) return 0;
-    BLR_TRY(post_ensure_W(ctx, p));
+    const bool literal = ctx->form == BLR_FORM_WHITENED;
+    if (!literal) BLR_TRY(post_ensure_W(ctx, p));
     double* alpha = nullptr;
     BLR_CUDA_OK(ctx, cudaMallocAsync(&alpha, (size_t)D * N * sizeof(double), ctx->stream));
     const bool colv = x->layout == BLR_COLVECS;
-    // α (D x N, column-major) = W (D x D, column-major) * X
-    int rc = gemm_generic(ctx, D, N, D, p->W, 1, D, x->p, colv ? 1 : x->ld, colv ? x->ld : 1, alpha, 1, D, 0.0);
+    // α (D x N, column-major) = W (D x D, column-major) * X;  literal form: α = Uw' \ X by triangular solve (:36)
+    int rc = literal ? solve_alpha(ctx, p, x, 0, N, alpha)
+                     : gemm_generic(ctx, D, N, D, p->W, 1, D, x->p, colv ? 1 : x->ld, colv ? x->ld : 1, alpha, 1, D, 0.0);
     // C = α'α
     if (rc == 0) rc = gemm_generic(ctx, N, N, D, alpha, D, 1, alpha, 1, D, C_dev, 1, N, 0.0);
     if (rc == 0) {
@@ -395,9 +398,15 @@ __global__ void add_col_vector_kernel(double* __restrict__ A, int64_t D, int64_t
 int sample_weights(blr_ctx* ctx, blr_post* p, int64_t S, const double* Z_dev, double* W_dev) {
     const int64_t D = p->D;
     if (S == 0) return 0;
-    BLR_TRY(post_ensure_W(ctx, p));
-    // (W' Z)[d, s] = Σ_k W[k, d] Z[k, s]
-    BLR_TRY(gemm_generic(ctx, D, S, D, p->W, D, 1, Z_dev, 1, D, W_dev, 1, D, 0.0));
+    if (ctx->form == BLR_FORM_WHITENED) {
+        // literal form: Uw \ Z by back substitution against the factor (:51)
+        BLR_CUDA_OK(ctx, cudaMemcpyAsync(W_dev, Z_dev, (size_t)D * S * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        BLR_TRY(trsm_lower(ctx, p->L, D, D, W_dev, D, S, true));
+    } else {
+        BLR_TRY(post_ensure_W(ctx, p));
+        // (W' Z)[d, s] = Σ_k W[k, d] Z[k, s]
+        BLR_TRY(gemm_generic(ctx, D, S, D, p->W, D, 1, Z_dev, 1, D, W_dev, 1, D, 0.0));
+    }
     add_col_vector_kernel<<<(int)std::min<int64_t>((D * S + 255) / 256, (int64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(
         W_dev, D, S, p->mw);
     BLR_CHECK_LAUNCH(ctx, "add_col_vector_kernel");

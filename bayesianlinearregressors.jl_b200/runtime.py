@@ -77,6 +77,20 @@ class Context:
     def sync(self):
         self.check(self.lib.blr_ctx_sync(self.handle))
 
+    def set_form(self, form: str):
+        """Numerical form of the D x D phase and the factor applications: "direct" (default; chol(Λw + G), inverse-factor GEMMs)
+        or "whitened" -- the reference's literal evaluation order (src/bayesian_linear_regression.jl:81,86,64-68 and the
+        triangular solves of :36,:41,:51).  See include/blr_cuda.h, blr_ctx_set_form."""
+        forms = {"direct": 0, "whitened": 1}
+        if form not in forms:
+            raise ValueError(f"form must be one of {sorted(forms)}")
+        self.check(self.lib.blr_ctx_set_form(self.handle, forms[form]))
+
+    def form(self) -> str:
+        v = C.c_int()
+        self.check(self.lib.blr_ctx_get_form(self.handle, C.byref(v)))
+        return ("direct", "whitened")[v.value]
+
     def stream(self) -> int:
         s = C.c_void_p()
         self.check(self.lib.blr_ctx_stream(self.handle, C.byref(s)))

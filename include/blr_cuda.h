@@ -85,6 +85,18 @@ const char* blr_last_error(const blr_ctx* ctx);
 int blr_ctx_sync(blr_ctx* ctx);
 /* cudaStream_t all kernels of this context are launched on (for CUDA-event timing by the host). */
 int blr_ctx_stream(blr_ctx* ctx, void** stream_out);
+/* Numerical form of the D x D phase and of the factor applications (per context; default BLR_FORM_DIRECT, or the
+ * environment variable BLR_FORM=whitened at blr_ctx_create).
+ *   BLR_FORM_DIRECT   : L' = chol(Λw + G); `var` / `rand` apply an explicit inverse factor (tensor-core GEMMs).
+ *   BLR_FORM_WHITENED : the reference's own evaluation order -- Λεy = chol(Uw⁻ᵀ G Uw⁻¹ + I)
+ *                       (src/bayesian_linear_regression.jl:81,86), mεy = Λεy \ (Bt'δy) (:64), T = Λεy.U * Uw (:67),
+ *                       m' = mw + Uw \ mεy (:68), and triangular SOLVES `Uw' \ X` in var / cov (:36,:41) and `Uw \ randn`
+ *                       in rand (:51); no inverse is formed anywhere.  About 8x the D x D flops and plain-DFMA solves in
+ *                       `var`; results agree with the direct form to rounding. */
+#define BLR_FORM_DIRECT 0
+#define BLR_FORM_WHITENED 1
+int blr_ctx_set_form(blr_ctx* ctx, int form);
+int blr_ctx_get_form(const blr_ctx* ctx, int* form_out);
 /* Stream ordering for BORROWED device buffers (blr_x_wrap_device / blr_vec_wrap_device, the *_dev outputs): the context
  * launches on its own non-blocking stream, which does not synchronise with the caller's streams implicitly.
  *   blr_ctx_wait_stream: everything already enqueued on `producer` (cudaStream_t, NULL = legacy default stream) happens

@@ -47,6 +47,20 @@ end
 const _ctx = Ref{Union{Nothing,Context}}(nothing)
 default_context() = something(_ctx[], (_ctx[] = Context(); _ctx[]))
 
+# Numerical form of the D x D phase and the factor applications (include/blr_cuda.h, blr_ctx_set_form):
+#   :direct   -- chol(Λw + G), inverse-factor GEMMs in var / rand (default);
+#   :whitened -- the package's own evaluation order (chol(Uw⁻ᵀ G Uw⁻¹ + I), T = Λεy.U * Uw, triangular solves in var / cov / rand).
+const FORMS = Dict(:direct => Cint(0), :whitened => Cint(1))
+function set_form!(ctx::Context, form::Symbol)
+    check(ctx, ccall((:blr_ctx_set_form, libblr), Cint, (Ptr{Cvoid}, Cint), ctx.ptr, FORMS[form]))
+    return ctx
+end
+function form(ctx::Context)
+    r = Ref{Cint}(0)
+    check(ctx, ccall((:blr_ctx_get_form, libblr), Cint, (Ptr{Cvoid}, Ref{Cint}), ctx.ptr, r))
+    return r[] == 0 ? :direct : :whitened
+end
+
 # status -> Julia exception, preserving the reference's error behaviour
 function check(ctx::Context, rc::Cint)
     rc == 0 && return nothing
