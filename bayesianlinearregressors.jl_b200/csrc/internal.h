@@ -145,7 +145,7 @@ int check_noise_vector(blr_ctx* ctx, const double* v, int64_t N);
 // ---- gram.cu
 // stats += local shard statistics.  s_noise: scalar σ² when sigma2 == nullptr.
 int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_is_zero, const blr_x* x,
-                    const double* y, const double* sigma2, double sigma2_scalar);
+                    const double* y, const double* sigma2, double sigma2_scalar, bool padded_odd = false);
 
 // ---- gram_small.cu: D <= 64, any layout / alignment; adds this shard's statistics into st.  D <= 16: K0 fused (reads
 // y, σ² itself, s / t unused, `partial` is scratch for 2 doubles per CTA); otherwise s, t, partial come from prep_kernel.
@@ -165,6 +165,8 @@ struct DxdFinalize {
 // One cooperative launch: A (lower triangle in) -> Cholesky factor (lower, strict upper zeroed); optionally z = L^-1 z in
 // place, u = L^-T z, and the finalize step.  info_dev: 4 device ints, [0] = LAPACK-style info, [1] = noise flag, [3] = abort.
 int dxd_fused(blr_ctx* ctx, double* A, int64_t D, int* info_dev, double* z, double* u, const DxdFinalize* fin);
+
+int repack_colvecs(blr_ctx* ctx, const double* X, int64_t ld, int64_t D, int64_t n, double* out, int64_t ldo);  // gram.cu
 
 // ---- whitened.cu (the reference's literal numerical form, opt-in: blr_ctx::form == BLR_FORM_WHITENED)
 int trsm_lower(blr_ctx* ctx, const double* L, int64_t ldl, int64_t D, double* B, int64_t ldb, int64_t K, bool trans);

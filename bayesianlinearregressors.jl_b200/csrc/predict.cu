@@ -119,6 +119,9 @@ __global__ void __launch_bounds__(bg::THREADS) var_kernel(const double* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
+#ifndef BLR_VAR_SMALL_GB34
+#define BLR_VAR_SMALL_GB34 2  // groups of 8 points in flight per warp trip for 16 < D <= 24 (MI = 4 would spill at two)
+#endif
 // Small-D marginals (D <= 64): W lives in shared memory, every warp streams groups of 8 test points straight from HBM
 // into m8n8k4 B fragments (lane (k, g) reads feature 4*kk + k of point p + g: whole 32-byte sectors in both layouts),
 // α = W x stays in 2 accumulators per 8-row block, squares are folded by shuffles; the mean rides on the same fragments.
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(256, 2) var_small_kernel(const double* __restr
 #pragma unroll
     for (int kk = 0; kk < KK; ++kk) a_mw[kk] = mws[kk * 4 + kq];
     // GB groups of 8 points per trip, loads first: like the small-D Gram kernel this is bound by bytes in flight
-    constexpr int GB = (MI == 1 ? 8 : (MI == 2 ? 4 : 1));
+    constexpr int GB = (MI == 1 ? 8 : (MI == 2 ? 4 : (MI == 3 ? BLR_VAR_SMALL_GB34 : 1)));
     for (int64_t grp0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * GB; grp0 < ngroups; grp0 += nwarps * GB) {
         double b[GB][KK];
 #pragma unroll
@@ -281,14 +284,58 @@ int predict_mean_var(blr_ctx* ctx, blr_post* p, const blr_x* x, const double* si
     if (ctx->form == BLR_FORM_WHITENED) return predict_mean_var_literal(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
     if (var_dev && predict_fast_eligible(p, x))
         return predict_mean_var_fast(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+    if (var_dev && p->D >= 128 && x->N >= 32) {
+        // Inputs the TMA kernel cannot address -- RowVecs, or ColVecs with an odd leading dimension (dense odd D) or a misaligned
+        // base -- are staged block by block into an aligned ColVecs buffer (one extra read + write of X: 32 / D of the pass)
+        // instead of running the DFMA-fed generic kernel.
+        const int64_t D = p->D, N = x->N, ldt = D + (D % 2);
+        const int64_t block = std::min<int64_t>(N, std::max<int64_t>((int64_t)1 << 16, ((int64_t)1 << 27) / ldt));
+        double* stage = nullptr;
+        BLR_CUDA_OK(ctx, cudaMallocAsync(&stage, (size_t)ldt * block * sizeof(double), ctx->stream));
+        int rc = 0;
+        for (int64_t a = 0; a < N && rc == 0; a += block) {
+            blr_x sub;
+            sub.p = stage;
+            sub.D = D;
+            sub.N = std::min(block, N - a);
+            sub.ld = ldt;
+            sub.layout = BLR_COLVECS;
+            if (x->layout == BLR_COLVECS) {
+                rc = repack_colvecs(ctx, x->p + a * x->ld, x->ld, D, sub.N, stage, ldt);
+            } else {
+                blr_x view = *x;
+                view.p = x->p + a;
+                view.N = sub.N;
+                view.owned = false;
+                rc = transpose_to_colvecs(ctx, &view, stage, ldt);  // the pad row (odd D) is never read: the tensor map has D rows
+            }
+            if (rc != 0) break;
+            if (sub.N >= 32) {
+                rc = predict_mean_var_fast(ctx, p, &sub, sigma2 ? sigma2 + a : nullptr, sigma2_scalar,
+                                           mean_dev ? mean_dev + a : nullptr, var_dev + a);
+            } else {  // a tail shorter than a point tile
+                rc = predict_mean_var(ctx, p, &sub, sigma2 ? sigma2 + a : nullptr, sigma2_scalar,
+                                      mean_dev ? mean_dev + a : nullptr, var_dev + a);
+            }
+        }
+        cudaFreeAsync(stage, ctx->stream);
+        return rc;
+    }
     if (var_dev && p->D <= 64) {
         BLR_TRY(post_ensure_W(ctx, p));
         if (p->D <= 2) return launch_var_tiny<2>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
         if (p->D <= 4) return launch_var_tiny<4>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
         if (p->D <= 8) return launch_var_tiny<8>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
-        if (p->D <= 16) return launch_var_small<2>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
-        if (p->D <= 32) return launch_var_small<4>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
-        return launch_var_small<8>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+        // one instantiation per multiple of 8 features: padding D = 24 to 32 or D = 40 to 64 costs 1.8x / 2.6x the tensor work
+        switch ((p->D + 7) / 8) {
+            case 2: return launch_var_small<2>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+            case 3: return launch_var_small<3>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+            case 4: return launch_var_small<4>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+            case 5: return launch_var_small<5>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+            case 6: return launch_var_small<6>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+            case 7: return launch_var_small<7>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+            default: return launch_var_small<8>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+        }
     }
     if (mean_dev) BLR_TRY(apply_weights(ctx, x, p->mw, mean_dev));
     if (var_dev) {

@@ -335,7 +335,9 @@ static int launch_var_tma(blr_ctx* ctx, const VarParams& vp, const blr_x* x) {
 }
 
 bool predict_fast_eligible(const blr_post* p, const blr_x* x) {
-    return x->layout == BLR_COLVECS && p->D >= 128 && (p->D % 2) == 0 && (x->ld % 2) == 0 &&
+    // (odd D is fine: the 2-D tensor map zero-fills beyond D and the inverse factor is zero-padded; only the row pitch and the
+    // base of X are bound by TMA's 16-byte rule)
+    return x->layout == BLR_COLVECS && p->D >= 128 && (x->ld % 2) == 0 &&
            (reinterpret_cast<uintptr_t>(x->p) & 15) == 0 && x->N >= 32 && x->N < (1ll << 31);
 }
 

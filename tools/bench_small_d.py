@@ -15,7 +15,10 @@ import blr_b200 as blr  # noqa: E402
 ctx = blr.Context(0)
 blr.set_default_context(ctx)
 hbm = ctx.calibrate()["hbm_gbs"]
-for D, N in [(2, 1 << 26), (8, 1 << 26), (16, 1 << 25), (24, 1 << 25), (32, 1 << 25), (40, 1 << 24), (48, 1 << 24), (50, 1 << 24), (64, 1 << 24)]:
+SHAPES = [(2, 1 << 26), (8, 1 << 26), (16, 1 << 25), (24, 1 << 25), (32, 1 << 25), (40, 1 << 24), (48, 1 << 24), (50, 1 << 24), (64, 1 << 24)]
+if os.environ.get("BLR_BENCH_DS"):  # e.g. BLR_BENCH_DS=72,96,100,127,128 -- the trough between the small-D kernels and the tiled ones
+    SHAPES = [(int(d), (1 << 30) // (int(d) * 8) // 1024 * 1024) for d in os.environ["BLR_BENCH_DS"].split(",")]
+for D, N in SHAPES:
     X = blr.DeviceMatrix.alloc(ctx, D, N).synth_(0)
     s2, y = blr.DeviceVector.alloc(ctx, N), blr.DeviceVector.alloc(ctx, N)
     ctx.check(ctx.lib.blr_vec_synth_noise(ctx.handle, s2.handle, 0, 0))
@@ -52,8 +55,10 @@ for D, N in [(2, 1 << 26), (8, 1 << 26), (16, 1 << 25), (24, 1 << 25), (32, 1 <<
     ctx.sync(); torch.cuda.synchronize()
     ms_mv = e0.elapsed_time(e1) / 5
     print(json.dumps({"config": f"small-D mean_and_var D={D} N*={N}", "points_per_s": N / ms_mv * 1e3, "ms": ms_mv,
-                      "hbm_gbs_algorithmic": 8.0 * N * (D + 2) / ms_mv / 1e6, "frac_of_measured_hbm": 8.0 * N * (D + 2) / ms_mv / 1e6 / hbm}))
+                      "hbm_gbs_algorithmic": 8.0 * N * (D + 2) / ms_mv / 1e6, "frac_of_measured_hbm": 8.0 * N * (D + 2) / ms_mv / 1e6 / hbm,
+                      "tflops_triangular": N * D * (D + 1.0) / ms_mv / 1e9}))
     del mv
     print(json.dumps({"config": f"small-D posterior+logpdf D={D} N={N}", "obs_per_s": N / ms * 1e3, "ms": ms, "gram_ms": tm["gram_ms"],
-                      "prep_ms": tm["prep_ms"], "hbm_gbs_algorithmic": gbs, "frac_of_measured_hbm": gbs / hbm}))
+                      "prep_ms": tm["prep_ms"], "hbm_gbs_algorithmic": gbs, "frac_of_measured_hbm": gbs / hbm,
+                      "gram_tflops": N * D * (D + 3.0) / tm["gram_ms"] / 1e9}))
     del X, s2, y, fx
