@@ -284,7 +284,7 @@ int predict_mean_var(blr_ctx* ctx, blr_post* p, const blr_x* x, const double* si
     if (ctx->form == BLR_FORM_WHITENED) return predict_mean_var_literal(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
     if (var_dev && predict_fast_eligible(p, x))
         return predict_mean_var_fast(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
-    if (var_dev && p->D >= 128 && x->N >= 32) {
+    if (var_dev && p->D > 64 && x->N >= 32) {
         // Inputs the TMA kernel cannot address -- RowVecs, or ColVecs with an odd leading dimension (dense odd D) or a misaligned
         // base -- are staged block by block into an aligned ColVecs buffer (one extra read + write of X: 32 / D of the pass)
         // instead of running the DFMA-fed generic kernel.

@@ -41,7 +41,7 @@ constexpr int CONSUMER_WARPS = 8;
 // the consumers; 12 warps x 168 registers is exactly the register file.
 constexpr int PRODUCER_WARPS = 4;
 constexpr int THREADS = (CONSUMER_WARPS + PRODUCER_WARPS) * 32;
-// MI: 64-row blocks of α per pass; NP: points per tile (32 or 64).  MI * NP / 8 = 32 accumulator tiles per warp either way:
+// MI: 64-row blocks of α per pass; NP: points per tile (32, 64 or 128).  MI * NP / 8 = 32 accumulator tiles per warp either way:
 // <8, 32> keeps all 512 rows of a D <= 512 problem in one pass; <4, 64> runs 256-row passes on twice the points (half the W
 // traffic per point, 25 % fewer pipeline stages per point and no 16-DMMA stages; the point tile is re-streamed per pass).
 template <int MI, int NP>
@@ -337,7 +337,7 @@ static int launch_var_tma(blr_ctx* ctx, const VarParams& vp, const blr_x* x) {
 bool predict_fast_eligible(const blr_post* p, const blr_x* x) {
     // (odd D is fine: the 2-D tensor map zero-fills beyond D and the inverse factor is zero-padded; only the row pitch and the
     // base of X are bound by TMA's 16-byte rule)
-    return x->layout == BLR_COLVECS && p->D >= 128 && (x->ld % 2) == 0 &&
+    return x->layout == BLR_COLVECS && p->D > 64 && (x->ld % 2) == 0 &&
            (reinterpret_cast<uintptr_t>(x->p) & 15) == 0 && x->N >= 32 && x->N < (1ll << 31);
 }
 
@@ -345,7 +345,9 @@ int predict_mean_var_fast(blr_ctx* ctx, blr_post* p, const blr_x* x, const doubl
                           double* mean_dev, double* var_dev) {
     const int D = (int)p->D;
     const bool wide = ctx->var_cfg == 1 && x->N >= 64;  // 256-row passes on 64-point tiles
-    const int MI = (D <= 256 || ctx->var_cfg == 1) ? 4 : 8;
+    // D <= 128: one 128-row pass on 128-point tiles (a 256-row pass would spend half its DMMAs on zero rows); the choice depends
+    // on D alone because the padded factor Wp is cached with the posterior in the layout of the chosen pass height
+    const int MI = D <= 128 ? 2 : ((D <= 256 || ctx->var_cfg == 1) ? 4 : 8);
     const int R = MI * 64;
     const int64_t ldw = ((D + R - 1) / R) * (int64_t)R;
     const int dk = ((D + vk::KT - 1) / vk::KT) * vk::KT;
@@ -365,6 +367,7 @@ int predict_mean_var_fast(blr_ctx* ctx, blr_post* p, const blr_x* x, const doubl
     vp.sigma2_scalar = sigma2_scalar;
     vp.mean = mean_dev;
     vp.var = var_dev;
+    if (MI == 2) return launch_var_tma<2, 128>(ctx, vp, x);
     if (MI == 8) return launch_var_tma<8, 32>(ctx, vp, x);
     return wide ? launch_var_tma<4, 64>(ctx, vp, x) : launch_var_tma<4, 32>(ctx, vp, x);
 }
