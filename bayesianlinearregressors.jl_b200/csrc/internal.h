@@ -219,8 +219,11 @@ int rhs_multi(blr_ctx* ctx, const blr_x* x, const double* Y, int64_t ldy, int64_
 // ---- predict_tma.cu
 bool predict_fast_eligible(const blr_post* p, const blr_x* x);
 bool sample_fast_eligible(const blr_x* x);
+struct RandChunk {
+    int64_t ldy, ldz, n_global, N_global;
+};
 int sample_finite_fast(blr_ctx* ctx, const blr_x* x, const double* Wsamp_dev, int64_t S, const double* sigma2,
-                       double sigma2_scalar, const double* Zy_dev, uint64_t seed, double* Y_dev);
+                       double sigma2_scalar, const double* Zy_dev, uint64_t seed, double* Y_dev, const RandChunk* chunk = nullptr);
 int predict_mean_var_fast(blr_ctx* ctx, blr_post* p, const blr_x* x, const double* sigma2, double sigma2_scalar,
                           double* mean_dev, double* var_dev);
 

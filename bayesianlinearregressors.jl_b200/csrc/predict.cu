@@ -487,6 +487,38 @@ int sample_finite(blr_ctx* ctx, const blr_x* x, const double* Wsamp_dev, int64_t
     if (N == 0 || S == 0) return 0;
     if (sample_fast_eligible(x)) return sample_finite_fast(ctx, x, Wsamp_dev, S, sigma2, sigma2_scalar, Zy_dev, seed, Y_dev);
     const bool colv = x->layout == BLR_COLVECS;
+    if (D >= 64 && N >= 128) {
+        // RowVecs, or ColVecs with an odd leading dimension / misaligned base: blocks of points staged into an aligned ColVecs
+        // buffer and run by the single-group TMA kernel (outputs, draws and Philox counters addressed in the whole problem)
+        const int64_t ldt = D + (D % 2);
+        const int64_t block = std::min<int64_t>(N, std::max<int64_t>((int64_t)1 << 16, ((int64_t)1 << 27) / ldt));
+        double* stage = nullptr;
+        BLR_CUDA_OK(ctx, cudaMallocAsync(&stage, (size_t)ldt * block * sizeof(double), ctx->stream));
+        int rc = 0;
+        for (int64_t a = 0; a < N && rc == 0; a += block) {
+            blr_x sub;
+            sub.p = stage;
+            sub.D = D;
+            sub.N = std::min(block, N - a);
+            sub.ld = ldt;
+            sub.layout = BLR_COLVECS;
+            if (colv) {
+                rc = repack_colvecs(ctx, x->p + a * x->ld, x->ld, D, sub.N, stage, ldt);
+            } else {
+                blr_x view = *x;
+                view.p = x->p + a;
+                view.N = sub.N;
+                view.owned = false;
+                rc = transpose_to_colvecs(ctx, &view, stage, ldt);
+            }
+            const RandChunk ck = {N, N, a, N};
+            if (rc == 0)
+                rc = sample_finite_fast(ctx, &sub, Wsamp_dev, S, sigma2 ? sigma2 + a : nullptr, sigma2_scalar,
+                                        Zy_dev ? Zy_dev + a : nullptr, seed, Y_dev + a, &ck);
+        }
+        cudaFreeAsync(stage, ctx->stream);
+        return rc;
+    }
     // Y (N x S) = X' Wsamp : A[m = n, k = d] = X[d, n]
     BLR_TRY(gemm_generic(ctx, N, S, D, x->p, colv ? x->ld : 1, colv ? 1 : x->ld, Wsamp_dev, 1, D, Y_dev, 1, N, 0.0));
     add_obs_noise_kernel<<<(int)std::min<int64_t>((N * S + 255) / 256, (int64_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(

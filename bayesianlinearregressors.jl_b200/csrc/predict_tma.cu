@@ -516,13 +516,14 @@ __global__ void __launch_bounds__(rk::THREADS, 1) rand_tma_kernel(const RandPara
                         if (s0 < p.S) {
                             double z0, z1;
                             if (p.Zy) {
-                                z0 = p.Zy[(int64_t)s0 * p.N + n];
-                                z1 = (s0 + 1 < p.S) ? p.Zy[(int64_t)(s0 + 1) * p.N + n] : 0.0;
+                                z0 = p.Zy[(int64_t)s0 * p.ldz + n];
+                                z1 = (s0 + 1 < p.S) ? p.Zy[(int64_t)(s0 + 1) * p.ldz + n] : 0.0;
                             } else {
-                                philox_normal_pair(p.seed, 7, (uint64_t)n + (uint64_t)(s0 >> 1) * (uint64_t)p.N, z0, z1);
+                                philox_normal_pair(p.seed, 7, (uint64_t)(p.n_global + n) + (uint64_t)(s0 >> 1) * (uint64_t)p.N_global, z0,
+                                                   z1);
                             }
-                            p.Y[(int64_t)s0 * p.N + n] = fma(sd, z0, acc[mi][ni][0]);
-                            if (s0 + 1 < p.S) p.Y[(int64_t)(s0 + 1) * p.N + n] = fma(sd, z1, acc[mi][ni][1]);
+                            p.Y[(int64_t)s0 * p.ldy + n] = fma(sd, z0, acc[mi][ni][0]);
+                            if (s0 + 1 < p.S) p.Y[(int64_t)(s0 + 1) * p.ldy + n] = fma(sd, z1, acc[mi][ni][1]);
                         }
                     }
                 }
@@ -548,14 +549,18 @@ int sample_finite_pp(blr_ctx* ctx, const blr_x* x, const double* Wsamp_dev, int6
                      double sigma2_scalar, const double* Zy_dev, uint64_t seed, double* Y_dev);
 
 bool sample_fast_eligible(const blr_x* x) {
-    return x->layout == BLR_COLVECS && x->D >= 64 && (x->D % 2) == 0 && (x->ld % 2) == 0 &&
+    // (odd D is fine for the single-group kernel: the tensor map over X zero-fills beyond D, the sample weights are re-packed)
+    return x->layout == BLR_COLVECS && x->D >= 64 && (x->ld % 2) == 0 &&
            (reinterpret_cast<uintptr_t>(x->p) & 15) == 0 && x->N >= 128 && x->N < (1ll << 31);
 }
 
+// chunk != nullptr: x holds points [n_global, n_global + x->N) of a problem of N_global points (a staged block of an input the
+// tensor map cannot address); sigma2 / Zy_dev / Y_dev already point at the block's first point, ldy / ldz span the whole problem.
 int sample_finite_fast(blr_ctx* ctx, const blr_x* x, const double* Wsamp_dev, int64_t S, const double* sigma2,
-                       double sigma2_scalar, const double* Zy_dev, uint64_t seed, double* Y_dev) {
+                       double sigma2_scalar, const double* Zy_dev, uint64_t seed, double* Y_dev, const RandChunk* chunk) {
     const int D = (int)x->D;
-    if (ctx->rand_pp == 2 || (ctx->rand_pp == 1 && Zy_dev != nullptr)) {
+    // the two-group kernel reads the sample weights through a tensor map over the D x S matrix itself: D must be even
+    if (!chunk && (D % 2) == 0 && (ctx->rand_pp == 2 || (ctx->rand_pp == 1 && Zy_dev != nullptr))) {
         const int r = sample_finite_pp(ctx, x, Wsamp_dev, S, sigma2, sigma2_scalar, Zy_dev, seed, Y_dev);
         if (r <= 0) return r;  // 1: weights not 16-byte aligned -> the default kernel
     }
@@ -576,9 +581,10 @@ int sample_finite_fast(blr_ctx* ctx, const blr_x* x, const double* Wsamp_dev, in
     rp.Zy = Zy_dev;
     rp.seed = seed;
     rp.Y = Y_dev;
-    rp.ldy = rp.ldz = x->N;
-    rp.n_global = 0;
-    rp.N_global = x->N;
+    rp.ldy = chunk ? chunk->ldy : x->N;
+    rp.ldz = chunk ? chunk->ldz : x->N;
+    rp.n_global = chunk ? chunk->n_global : 0;
+    rp.N_global = chunk ? chunk->N_global : x->N;
     const int smem = (int)sizeof(rk::Smem) + 1024;  // + slack for the in-kernel 1024-byte alignment
     CUtensorMap tmx;  // points: D features (contiguous) x N points; one box = 16 features of 64 points
     int rc = make_tmap_2d_f64(ctx, &tmx, x->p, (uint64_t)x->D, (uint64_t)x->N, (uint64_t)x->ld, 16, rk::TP / 2);

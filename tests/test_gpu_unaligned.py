@@ -153,3 +153,31 @@ def test_staged_marginals_many_blocks():
     mo, vo = ref.mean_and_var(ref.BayesianLinearRegressor(post.mw, post.Λw.dense() if hasattr(post.Λw, "dense") else post.Λw)(
         ref.ColVecs(Xs), 0.25))
     assert _rel(out["aligned"][:N][idx], mo) < RTOL and _rel(out["aligned"][N:][idx], vo) < RTOL
+
+
+@pytest.mark.parametrize("D,Nt", [(65, 128), (129, 1000), (257, 70_001), (130, 300)])
+def test_unaligned_rand_matches_oracle_and_aligned_device_draws(D, Nt):
+    """rand on test points the tensor map cannot address (dense odd D, RowVecs): supplied draws against the oracle; device draws
+    (Philox counters are a function of the point's index in the WHOLE problem) identical to the aligned evaluation of the same points."""
+    rng = np.random.default_rng(D + Nt)
+    B = rng.standard_normal((D, D)) / np.sqrt(D)
+    mw, Λ = rng.standard_normal(D), B @ B.T + np.eye(D)
+    f, fo = blr.BayesianLinearRegressor(mw, Λ), ref.BayesianLinearRegressor(mw, Λ)
+    Xt, σt = rng.standard_normal((D, Nt)), np.exp(rng.standard_normal(Nt))
+    ctx = blr.default_context()
+    Xpad = np.zeros((D + 2 - D % 2, Nt), order="F")       # aligned copy: even leading dimension
+    Xpad[:D] = Xt
+    inputs = {
+        "dense": blr.ColVecs(blr.DeviceMatrix.upload(ctx, Xt, 0)),
+        "rowvecs": blr.RowVecs(blr.DeviceMatrix.upload(ctx, np.ascontiguousarray(Xt.T), 1)),
+    }
+    σd = blr.DeviceVector.upload(ctx, σt)
+    for S in (3, 64, 70):
+        Zw, Zy = rng.standard_normal((D, S)), rng.standard_normal((Nt, S))
+        Yo = ref.rand(fo(ref.ColVecs(Xt), σt), Zw, Zy)
+        for tag, x in inputs.items():
+            assert _rel(blr.rand_with_draws(f(x, σd), Zw, Zy), Yo) < RTOL, (tag, S)
+    Yd = {tag: blr.rand(blr.DeviceRNG(7), f(x, σd), 5) for tag, x in inputs.items()}
+    assert _rel(Yd["rowvecs"], Yd["dense"]) < 1e-12
+    # the same draws as a plain numpy input gets (host arrays are uploaded as ColVecs with ld = D: the aligned path when D is even)
+    assert _rel(blr.rand(blr.DeviceRNG(7), f(blr.ColVecs(Xt), σt), 5), Yd["dense"]) < 1e-12
