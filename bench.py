@@ -417,9 +417,34 @@ def logpdf_parity(args, c, lp):
                     "the statistics behind it are Freivalds-checked at this size in tests/test_gpu_fullsize.py"}
 
 
+def cublas_dgemm_tflops(torch, n=8192, reps=5):
+    """Independent fp64 yardstick: cuBLAS Dgemm n^3 through torch, CUDA events.  Reported next to the library's
+    own DMMA issue-loop calibration; never on the product path."""
+    try:
+        a = torch.randn((n, n), dtype=torch.float64, device="cuda")
+        b = torch.randn((n, n), dtype=torch.float64, device="cuda")
+        c = torch.empty((n, n), dtype=torch.float64, device="cuda")
+        torch.mm(a, b, out=c)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.mm(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        tf = 2.0 * n ** 3 * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12
+        del a, b, c
+        torch.cuda.empty_cache()
+        return tf
+    except Exception:  # e.g. out of memory next to a device-filling workload: the yardstick is optional
+        return None
+
+
 def roofline_block(E, args, n_loc, D, g_ms, solve_ms, ms_per_step):
     achieved = gram_flops(n_loc, D) / (g_ms * 1e-3) / 1e12
     cal = E.ctx.calibrate() if not args.no_calibrate else {}
+    if cal:
+        cal["cublas_dgemm_8192_tflops"] = cublas_dgemm_tflops(E.torch)
     peak = cal.get("dmma_tflops") or NOMINAL_FP64_TFLOPS
     traffic, tsrc = None, None
     if os.path.exists(TRAFFIC_PATH):

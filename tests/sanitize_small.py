@@ -80,6 +80,22 @@ def main():
         # through its 3-slot ring (slot reuse = the empty-barrier hand-over), still with full tiles and stages only
         (256, 16384, "col", True, False, 384, 64, "aligned, Gram ring slots reused"),
     ]
+    late = [  # kernels added late in round 2 (BLR_SANITIZE_SET=late runs only these)
+        (129, 700, "col", True, False, 300, 5, "odd D: repack_colvecs + Gram on D + 1 features, staged var / rand"),
+        (129, 700, "row", True, False, 300, 5, "odd D feature-major"),
+        (96, 500, "col", True, False, 300, 5, "marginals 128-row pass on 128-point tiles"),
+        (24, 400, "col", True, False, 300, 3, "var_small<3>"),
+    ]
+    if which == "late":
+        for c in late:
+            one(ctx, *c)
+        ctxw = blr.Context(0)
+        ctxw.set_form("whitened")  # trsm_lower_kernel<false / true>, dxd_whitened, literal var / rand
+        one(ctxw, 100, 300, "col", True, False, 100, 5, "whitened form, dense prior")
+        one(ctxw, 70, 300, "row", False, True, 40, 3, "whitened form, diagonal prior")
+        print("sanitize_small: late set done", flush=True)
+        return
+    cases += late
     if which == "quick":
         cases = cases[3:5]
     if which.startswith("case:"):  # one case alone (to attribute a sanitizer report to a kernel configuration)

@@ -262,6 +262,12 @@ for w in (1,2,3,4,8,12,16):
       done;;
     bench_pm)
       timeout 1500 python bench.py --prior-mean random --steps 5 --warmup 3 --no-cpu --no-e2e > "$OUT/bench_cfg3_pm.json" 2> "$OUT/bench_cfg3_pm.err"; echo "bench_pm exit $?"; tail -c 1500 "$OUT/bench_cfg3_pm.json";;
+    sanitize_late)
+      # kernels added late in round 2: trsm_lower_kernel / dxd_whitened, repack_colvecs + padded-odd Gram, staged var / rand, Cfg<2,128>
+      for tool in ${SAN_TOOLS:-memcheck racecheck synccheck}; do
+        BLR_SANITIZE_SET=late timeout 1200 compute-sanitizer --tool $tool --print-limit 50 python tests/sanitize_small.py > "$OUT/sanitize_late_$tool.log" 2>&1
+        echo "sanitize_late $tool exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|max rel err|late set done" "$OUT/sanitize_late_$tool.log" | tail -12
+      done;;
     bench20)
       timeout 1500 python bench.py --gpus 1 --steps 20 --warmup 5 > "$OUT/bench20.json" 2> "$OUT/bench20.err"; echo "bench20 exit $?"; tail -c 3500 "$OUT/bench20.json"; tail -5 "$OUT/bench20.err";;
     *) echo "unknown stage $stage";;
