@@ -113,9 +113,19 @@ int synth_targets(blr_ctx* ctx, const blr_x* x, const double* sigma2, uint64_t s
     return 0;
 }
 
-// out[d + n * ldo] = scale * act(Σ_i W[d, i] x[i, n] + b[d]);  one CTA = 8 observations x all D features.
+// out[d + n * ldo] = scale * act(Σ_i W[d, i] x[i, n] + b[d]);  one CTA = 16 observations x all D features.
 // ACT: 0 cos (random Fourier features with scale = sqrt(2 / D)), 1 tanh, 2 relu, 3 identity, 4 sin.
-constexpr int RFF_OBS = 8;
+// A thread owns one feature at a time and 16 observations: per input dimension one coalesced load of W (re-read once per CTA
+// from L2), 8 broadcast LDS.128 of the observations' inputs ([i][observation] in shared memory) and 16 DFMA.  Measured at
+// cfg5's shape (d_in = 32, D = 4096, 2^19 inputs, tools/bench_features.py): 16 observations x 2 CTAs / SM 16.7 ms, 32 x 2 19.7,
+// 32 x 1 21.5, 8 x 2 20.2 -- about 60 % of the kernel's fp64 instruction bound (32 DFMA + ~50 for cos per output).
+#ifndef BLR_RFF_OBS
+#define BLR_RFF_OBS 16
+#endif
+#ifndef BLR_RFF_MINB
+#define BLR_RFF_MINB 2
+#endif
+constexpr int RFF_OBS = BLR_RFF_OBS;
 template <int ACT>
 __device__ __forceinline__ double feature_act(double z) {
     if (ACT == 0) return cos(z);
@@ -125,29 +135,36 @@ __device__ __forceinline__ double feature_act(double z) {
     return z;
 }
 template <int ACT>
-__global__ void __launch_bounds__(256) features_kernel(const double* __restrict__ Xin, int64_t ldx, int din, int64_t N,
+__global__ void __launch_bounds__(256, BLR_RFF_MINB) features_kernel(const double* __restrict__ Xin, int64_t ldx, int din, int64_t N,
                                                        const double* __restrict__ W, const double* __restrict__ b, int D,
                                                        double scale, double* __restrict__ out, int64_t ldo) {
-    extern __shared__ double xs[];  // [RFF_OBS][din]
+    extern __shared__ __align__(16) double xs[];  // [din][RFF_OBS]
     const int64_t n0 = (int64_t)blockIdx.x * RFF_OBS;
     for (int e = threadIdx.x; e < RFF_OBS * din; e += 256) {
-        const int o = e / din, i = e % din;
-        xs[e] = (n0 + o < N) ? Xin[(n0 + o) * ldx + i] : 0.0;
+        const int o = e / din, i = e % din;  // i fastest: coalesced over an observation's inputs
+        xs[i * RFF_OBS + o] = (n0 + o < N) ? Xin[(n0 + o) * ldx + i] : 0.0;
     }
     __syncthreads();
+    const int nobs = (int)min((int64_t)RFF_OBS, N - n0);
     for (int d = threadIdx.x; d < D; d += 256) {
         double acc[RFF_OBS];
         const double bd = b[d];
 #pragma unroll
         for (int o = 0; o < RFF_OBS; ++o) acc[o] = bd;
+#pragma unroll 4
         for (int i = 0; i < din; ++i) {
             const double w = W[(int64_t)i * D + d];
+            const double2* xi = reinterpret_cast<const double2*>(xs + i * RFF_OBS);
 #pragma unroll
-            for (int o = 0; o < RFF_OBS; ++o) acc[o] = fma(w, xs[o * din + i], acc[o]);
+            for (int o = 0; o < RFF_OBS / 2; ++o) {
+                const double2 x2 = xi[o];
+                acc[2 * o] = fma(w, x2.x, acc[2 * o]);
+                acc[2 * o + 1] = fma(w, x2.y, acc[2 * o + 1]);
+            }
         }
 #pragma unroll
         for (int o = 0; o < RFF_OBS; ++o)
-            if (n0 + o < N) out[(n0 + o) * ldo + d] = scale * feature_act<ACT>(acc[o]);
+            if (o < nobs) out[(n0 + o) * ldo + d] = scale * feature_act<ACT>(acc[o]);
     }
 }
 int affine_features(blr_ctx* ctx, const blr_x* xin, const double* W_dev, const double* b_dev, int64_t D, int act, double scale,
