@@ -242,3 +242,47 @@ def test_c_client_runs_on_device(tmp_path):
     assert abs(lp - ref.logpdf(fxo, y)) <= RTOL * abs(lp)
     assert relerr(np.array(mpost), po.mw) < RTOL
     assert relerr(np.array([p[0] for p in pred]), mo) < RTOL and relerr(np.array([p[1] for p in pred]), vo) < RTOL
+
+
+def test_maximum_dimension_and_beyond():
+    """The library's largest D (16 384: blr_ctx::small holds D-vectors of that length) and one past it.  At D = 16 384 the Gram
+    matrix is 2 GiB, the lower triangle 8 256 tiles, the fused D x D kernel 32 896 tile tasks.  N < D and a Diagonal prior keep the
+    host check cheap: by the Woodbury identity the posterior mean and the log marginal likelihood follow from the N x N system
+    S = Σy + X' Λw⁻¹ X (the naive Gaussian of test/bayesian_linear_regression.jl:22-38): m' = mw + Λw⁻¹ X S⁻¹ δ,
+    logpdf = -½ (N log 2π + logdet S + δ' S⁻¹ δ); the precision is checked entrywise on sampled rows of Λw + X Σy⁻¹ X'."""
+    import scipy.linalg as sl
+
+    ctx = blr.default_context()
+    D, N = 16384, 700
+    rng = np.random.default_rng(16384)
+    X = np.asfortranarray(rng.standard_normal((D, N)))
+    σ2 = np.exp(rng.standard_normal(N))
+    mw = 0.05 * rng.standard_normal(D)
+    lam = np.linspace(0.5, 2.0, D)
+    y = X.T @ (rng.standard_normal(D) / math.sqrt(D)) + np.sqrt(σ2) * rng.standard_normal(N)
+    post, lp = blr.posterior_and_logpdf(blr.BayesianLinearRegressor(mw, blr.Diagonal(lam))(blr.ColVecs(X), σ2), y)
+    δ = y - X.T @ mw
+    S = (X.T / lam) @ X + np.diag(σ2)
+    cS = sl.cho_factor(S, lower=True)
+    a = sl.cho_solve(cS, δ)
+    lp_o = -0.5 * (N * math.log(2 * math.pi) + 2.0 * np.log(np.diag(cS[0])).sum() + δ @ a)
+    m_o = mw + (X @ a) / lam
+    assert abs(lp - lp_o) / abs(lp_o) < RTOL, (lp, lp_o)
+    assert relerr(post.mw, m_o) < RTOL
+    rows = rng.choice(D, 64, replace=False)
+    P = post.Λw.dense()
+    Po = (X[rows] / σ2) @ X.T
+    Po[np.arange(64), rows] += lam[rows]
+    assert relerr(P[rows], Po) < RTOL
+    assert np.array_equal(P, P.T)
+    # marginals from the cached device factor on a few points: var = x' Λ'⁻¹ x + σ², Λ'⁻¹ x = Λw⁻¹ x - Λw⁻¹ X S⁻¹ X' Λw⁻¹ x
+    Xt = rng.standard_normal((D, 40))
+    m, v = blr.mean_and_var(post(blr.ColVecs(Xt), 0.3))
+    U = Xt / lam[:, None]
+    V = U - (X @ sl.cho_solve(cS, X.T @ U)) / lam[:, None]
+    assert relerr(m, Xt.T @ m_o) < RTOL and relerr(v, (Xt * V).sum(0) + 0.3) < RTOL
+    del post, P
+    # one past the maximum: a clean error, not a crash (the reference has no limit; the C ABI reports BLR_E_INVALID)
+    D2 = 16385
+    with pytest.raises(blr.BLRError):
+        blr.posterior(blr.BayesianLinearRegressor(np.zeros(D2), blr.Diagonal(np.ones(D2)))(blr.ColVecs(np.zeros((D2, 4))), 1.0), np.zeros(4))
