@@ -547,6 +547,15 @@ __global__ void __launch_bounds__(256) gram_small_reduce_kernel(const double* __
     }
 }
 
+// host wrapper for the other translation units that produce per-CTA partials in this layout (gram_mid.cu)
+int gram_small_reduce(blr_ctx* ctx, blr_stats* st, const double* P, const double* Pr, int DP, int nblocks, int D, const double* partial,
+                      int partial_blocks, double n_obs) {
+    gram_small_reduce_kernel<<<(DP * DP + 255) / 256, 256, 0, ctx->stream>>>(P, Pr, DP, nblocks, D, st->G(), st->r(), st->scal(), partial,
+                                                                            partial_blocks, n_obs);
+    BLR_CHECK_LAUNCH(ctx, "gram_small_reduce_kernel");
+    return 0;
+}
+
 // FUSED: `partial` receives this launch's per-CTA (q, ℓ) partials; otherwise it holds the preparation kernel's
 // `partial_blocks` partials and s, t are its outputs.
 template <int MI, bool FUSED>

@@ -73,6 +73,7 @@ struct blr_ctx {
     int sched_T = 0, sched_nseg = 0;
     int64_t gram_period_obs = 0;  // observations per L2 period of the Gram kernel (0 = single period; BLR_GRAM_PERIOD_OBS)
     int gram_stages = 0;   // ring depth override for gram_kt == 16 (BLR_GRAM_STAGES = 6)
+    int mid_ring = 1;      // K1m: team-of-two-warps ring kernel for 64 < D <= 96 (BLR_MID_RING=0: one padded 128-row tile of K1)
     int small_ring = 1;    // K1s: per-warp TMA ring for 16 < D <= 64, D % 8 == 0, aligned ColVecs (BLR_SMALL_RING=0: register-fed kernel)
     int rand_pp = 1;       // K7: 1 = two consumer groups on alternating point tiles when the draws are SUPPLIED (8.2 ms against 9.6 ms at
                            // D = 512, N* = 2^22, S = 64), single-group kernel for device draws (9.79 ms; two-group 9.97); 0 = always
@@ -166,6 +167,12 @@ struct DxdFinalize {
 // place, u = L^-T z, and the finalize step.  info_dev: 4 device ints, [0] = LAPACK-style info, [1] = noise flag, [3] = abort.
 int dxd_fused(blr_ctx* ctx, double* A, int64_t D, int* info_dev, double* z, double* u, const DxdFinalize* fin);
 
+int gram_small_reduce(blr_ctx* ctx, blr_stats* st, const double* P, const double* Pr, int DP, int nblocks, int D, const double* partial,
+                      int partial_blocks, double n_obs);  // gram_small.cu
+// ---- gram_mid.cu: 64 < D <= 96 (even, aligned ColVecs): two warps own the matrix together, preparation fused in
+bool gram_mid_eligible(const blr_ctx* ctx, const blr_x* x);
+int gram_mid(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double* y, const double* sigma2, double sigma2_scalar,
+             const double* mw_dev, bool mw_is_zero, double* partial);
 int repack_colvecs(blr_ctx* ctx, const double* X, int64_t ld, int64_t D, int64_t n, double* out, int64_t ldo);  // gram.cu
 
 // ---- whitened.cu (the reference's literal numerical form, opt-in: blr_ctx::form == BLR_FORM_WHITENED)

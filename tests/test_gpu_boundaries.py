@@ -82,3 +82,51 @@ def test_prediction_across_dispatch_seams(D):
             Y = blr.rand_with_draws(post(blr.ColVecs(Xt), σt), Zw, Zy)
             Yo = ref.rand(po(ref.ColVecs(Xt), σt), Zw, Zy)
             assert relerr(Y, Yo) < RTOL, (D, Nt, S, relerr(Y, Yo))
+
+
+@pytest.mark.parametrize("D", [66, 68, 72, 74, 80, 82, 88, 90, 96])
+@pytest.mark.parametrize("N", [64, 100, 1000, 40_003])
+def test_mid_ring_kernel_statistics(D, N):
+    """64 < D <= 96 (even, aligned ColVecs): the team-of-two-warps ring kernel (csrc/gram_mid.cu).  Every block-grid width
+    (9 .. 12 block rows, with and without a split leftover row), D on and off a multiple of 8, dense and strided observations
+    (ld = D and ld = D + 6), heteroscedastic and scalar noise, zero and non-zero prior mean, N from a single stage to several
+    ring revolutions per team with a ragged tail -- statistics against the oracle's Gram form, and against the same library with
+    the kernel switched off (BLR_MID_RING=0: one padded tile of K1)."""
+    import ctypes as C
+    import os
+
+    from blr_b200 import _lib as L
+
+    rng = np.random.default_rng(D * 1000 + N)
+    ctx = blr.default_context()
+    os.environ["BLR_MID_RING"] = "0"
+    try:
+        ctx_off = blr.Context(0)
+    finally:
+        del os.environ["BLR_MID_RING"]
+    for ld, scalar, zero_mean in ((D, False, False), (D + 6, False, True), (D, True, False)):
+        Xp = np.zeros((ld, N), order="F")
+        Xp[:D] = rng.standard_normal((D, N))
+        X = Xp[:D]
+        σ2 = np.full(N, 0.37) if scalar else np.exp(rng.standard_normal(N))
+        y = X.T @ rng.standard_normal(D) + np.sqrt(σ2) * rng.standard_normal(N)
+        mw = np.zeros(D) if zero_mean else rng.standard_normal(D)
+        Go, ro, qo, lo = ref.gram_stats(X, y, σ2, mw)
+        out = []
+        for c in (ctx, ctx_off):
+            Xd = blr.DeviceMatrix.upload(c, Xp, 0)                       # ld x N on the device ...
+            ptr, _ = Xd.device_ptr()
+            xh = C.c_void_p()                                             # ... viewed as D x N with leading dimension ld
+            c.check(c.lib.blr_x_wrap_device(c.handle, C.c_void_p(ptr), D, N, ld, L.COLVECS, C.byref(xh)))
+            st = blr.Stats(c, D)
+            yv = blr.DeviceVector.upload(c, y)
+            s2v = blr.DeviceVector.upload(c, σ2)
+            noise = L.Noise(L.NOISE_SCALAR, 0.37, None, None, 0) if scalar else L.Noise(L.NOISE_VECTOR, 0.0, s2v.handle, None, 0)
+            c.check(c.lib.blr_stats_accumulate(c.handle, st.handle, mw.ctypes.data_as(C.c_void_p), xh, yv.handle, C.byref(noise)))
+            G, r, q, ell, n = st.unpack()
+            c.check(c.lib.blr_x_free(c.handle, xh))
+            assert n == N and np.array_equal(G, G.T)
+            assert relerr(G, Go) < 1e-12 and relerr(r, ro) < 1e-11, (D, N, ld, relerr(G, Go), relerr(r, ro))
+            assert abs(q - qo) <= 1e-11 * abs(qo) and abs(ell - lo) <= 1e-11 * max(abs(lo), 1.0)
+            out.append((G, r, q, ell))
+        assert relerr(out[0][0], out[1][0]) < 1e-12 and relerr(out[0][1], out[1][1]) < 1e-11
