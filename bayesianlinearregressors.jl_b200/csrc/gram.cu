@@ -1044,9 +1044,9 @@ int gram_accumulate(blr_ctx* ctx, blr_stats* st, const double* mw_dev, bool mw_i
     BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], sm));
 
     // ---- 64 < D <= 96: two warps hold the Gram matrix together (gram_mid.cu), K0 fused in
-    if (gram_mid_eligible(ctx, x)) {
+    if (gram_mid_eligible(ctx, x, padded_odd)) {
         BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[1], sm));
-        BLR_TRY(gram_mid(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, ctx->small + SMALL_PREP));
+        BLR_TRY(gram_mid(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, ctx->small + SMALL_PREP, padded_odd));
         BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[3], sm));
         ctx->ev_valid[0] = ctx->ev_valid[1] = ctx->ev_valid[2] = true;
         return 0;

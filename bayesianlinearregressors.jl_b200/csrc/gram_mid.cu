@@ -43,7 +43,8 @@ __host__ __device__ constexpr int row_owner(int mi, int MI) { return block_owner
 struct MidArgs {
     const double* X;
     int64_t ld;
-    int D;
+    int D;   // features per observation as stored (even; D_logical + 1 with a zero feature for a staged odd-D input)
+    int Dm;  // features the prior mean has
     const double* y;
     const double* sigma2;
     double sigma2_scalar;
@@ -84,7 +85,7 @@ __device__ __forceinline__ void mid_member(const MidArgs& p, double* ring, unsig
 #pragma unroll
     for (int mi = 0; mi < MI; ++mi) {
         racc[mi] = 0.0;
-        mwr[mi] = (HAS_MEAN && mi * 8 + g < D) ? mw[mi * 8 + g] : 0.0;  // rows >= D must not enter x'mw
+        mwr[mi] = (HAS_MEAN && mi * 8 + g < p.Dm) ? mw[mi * 8 + g] : 0.0;  // rows >= D must not enter x'mw
 #pragma unroll
         for (int ni = 0; ni <= mi; ++ni)
             if (block_owner(mi, ni, MI) == MEMBER) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
@@ -211,7 +212,7 @@ __device__ __forceinline__ void mid_member(const MidArgs& p, double* ring, unsig
 
 template <int MI, bool HAS_MEAN>
 __global__ void __launch_bounds__(gm::THREADS, 1)
-    gram_mid_ring_kernel(const double* __restrict__ X, int64_t ld, int D, int64_t N, const double* __restrict__ y,
+    gram_mid_ring_kernel(const double* __restrict__ X, int64_t ld, int D, int Dm, int64_t N, const double* __restrict__ y,
                          const double* __restrict__ sigma2, double sigma2_scalar, const double* __restrict__ mw,
                          double* __restrict__ P, double* __restrict__ Pr, double* __restrict__ Pq, int64_t obs_per_team) {
     using namespace gm;
@@ -245,6 +246,7 @@ __global__ void __launch_bounds__(gm::THREADS, 1)
     p.X = X;
     p.ld = ld;
     p.D = D;
+    p.Dm = Dm;
     p.y = y;
     p.sigma2 = sigma2;
     p.sigma2_scalar = sigma2_scalar;
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(gm::THREADS, 1)
 
 template <int MI>
 static int launch_mid(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double* y, const double* sigma2, double sigma2_scalar,
-                      const double* mw_dev, bool mw_is_zero, double* partial) {
+                      const double* mw_dev, bool mw_is_zero, double* partial, bool padded_odd) {
     using namespace gm;
     constexpr int DP = MI * 8;
     constexpr int RING = TEAMS * STAGES * KO * DP, TILE = DP * DP + DP + 2 * TEAMS;
@@ -287,34 +289,38 @@ static int launch_mid(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double*
     BLR_TRY(ensure_ws(ctx, (size_t)nblocks * (DP * DP + DP) * sizeof(double)));
     double* P = ctx->ws;
     double* Pr = ctx->ws + (size_t)nblocks * DP * DP;
-    const int D = (int)x->D;
+    const int Dm = (int)x->D;                 // logical features (the statistics' dimension)
+    const int D = Dm + (padded_odd ? 1 : 0);  // as stored: a staged odd-D input carries one zero feature
     if (mw_is_zero) {
         BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_mid_ring_kernel<MI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        gram_mid_ring_kernel<MI, false><<<nblocks, THREADS, smem, ctx->stream>>>(x->p, x->ld, D, N, y, sigma2, sigma2_scalar, mw_dev, P, Pr,
-                                                                                partial, obs_per_team);
+        gram_mid_ring_kernel<MI, false><<<nblocks, THREADS, smem, ctx->stream>>>(x->p, x->ld, D, Dm, N, y, sigma2, sigma2_scalar, mw_dev, P,
+                                                                                Pr, partial, obs_per_team);
     } else {
         BLR_CUDA_OK(ctx, cudaFuncSetAttribute(gram_mid_ring_kernel<MI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        gram_mid_ring_kernel<MI, true><<<nblocks, THREADS, smem, ctx->stream>>>(x->p, x->ld, D, N, y, sigma2, sigma2_scalar, mw_dev, P, Pr,
-                                                                               partial, obs_per_team);
+        gram_mid_ring_kernel<MI, true><<<nblocks, THREADS, smem, ctx->stream>>>(x->p, x->ld, D, Dm, N, y, sigma2, sigma2_scalar, mw_dev, P,
+                                                                               Pr, partial, obs_per_team);
     }
     BLR_CHECK_LAUNCH(ctx, "gram_mid_ring_kernel");
     BLR_CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-    return gram_small_reduce(ctx, st, P, Pr, DP, nblocks, D, partial, nblocks, (double)N);
+    return gram_small_reduce(ctx, st, P, Pr, DP, nblocks, Dm, partial, nblocks, (double)N);  // drops the zero feature's row / column
 }
 
-// ColVecs, 64 < D <= 96 with D even, observations 16-byte aligned (BLR_MID_RING=0: off -> one padded tile of K1)
-bool gram_mid_eligible(const blr_ctx* ctx, const blr_x* x) {
-    return ctx->mid_ring && x->layout == BLR_COLVECS && x->D > 64 && x->D <= 96 && (x->D % 2) == 0 && (x->ld % 2) == 0 &&
+// ColVecs, 64 < D <= 96 with D even, observations 16-byte aligned (BLR_MID_RING=0: off -> one padded tile of K1).
+// padded_odd: x is the aligned staging buffer of an odd-D input (gram.cu, repack_colvecs): x->D is the logical (odd) dimension,
+// every observation carries D + 1 doubles, the last one zero.
+bool gram_mid_eligible(const blr_ctx* ctx, const blr_x* x, bool padded_odd) {
+    const int64_t Ds = x->D + (padded_odd ? 1 : 0);
+    return ctx->mid_ring && x->layout == BLR_COLVECS && Ds > 64 && Ds <= 96 && (Ds % 2) == 0 && (x->ld % 2) == 0 &&
            (reinterpret_cast<uintptr_t>(x->p) & 15) == 0 && x->N >= 64;
 }
 
 int gram_mid(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double* y, const double* sigma2, double sigma2_scalar,
-             const double* mw_dev, bool mw_is_zero, double* partial) {
-    switch ((x->D + 7) / 8) {
-        case 9: return launch_mid<9>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, partial);
-        case 10: return launch_mid<10>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, partial);
-        case 11: return launch_mid<11>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, partial);
-        default: return launch_mid<12>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, partial);
+             const double* mw_dev, bool mw_is_zero, double* partial, bool padded_odd) {
+    switch ((x->D + (padded_odd ? 1 : 0) + 7) / 8) {
+        case 9: return launch_mid<9>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, partial, padded_odd);
+        case 10: return launch_mid<10>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, partial, padded_odd);
+        case 11: return launch_mid<11>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, partial, padded_odd);
+        default: return launch_mid<12>(ctx, st, x, y, sigma2, sigma2_scalar, mw_dev, mw_is_zero, partial, padded_odd);
     }
 }
 

@@ -170,9 +170,9 @@ int dxd_fused(blr_ctx* ctx, double* A, int64_t D, int* info_dev, double* z, doub
 int gram_small_reduce(blr_ctx* ctx, blr_stats* st, const double* P, const double* Pr, int DP, int nblocks, int D, const double* partial,
                       int partial_blocks, double n_obs);  // gram_small.cu
 // ---- gram_mid.cu: 64 < D <= 96 (even, aligned ColVecs): two warps own the matrix together, preparation fused in
-bool gram_mid_eligible(const blr_ctx* ctx, const blr_x* x);
+bool gram_mid_eligible(const blr_ctx* ctx, const blr_x* x, bool padded_odd);
 int gram_mid(blr_ctx* ctx, blr_stats* st, const blr_x* x, const double* y, const double* sigma2, double sigma2_scalar,
-             const double* mw_dev, bool mw_is_zero, double* partial);
+             const double* mw_dev, bool mw_is_zero, double* partial, bool padded_odd);
 int repack_colvecs(blr_ctx* ctx, const double* X, int64_t ld, int64_t D, int64_t n, double* out, int64_t ldo);  // gram.cu
 
 // ---- whitened.cu (the reference's literal numerical form, opt-in: blr_ctx::form == BLR_FORM_WHITENED)

@@ -44,7 +44,9 @@ def _torch_stats(torch, Xv, y, s2, mw):
 
 
 @pytest.mark.parametrize("D,N,how", [
-    (67, (1 << 21) + 333, "odd-D"),          # three staging blocks of 2^27 / 68 observations, the last one ragged
+    (67, (1 << 21) + 333, "odd-D"),          # three staging blocks of 2^27 / 68 observations, the last one ragged (K1m on 68 features)
+    (81, 50_001, "odd-D"),                   # staged, then the team ring kernel (64 < D + 1 <= 96) on 82 stored features
+    (95, 10_000, "odd-D"),                   # D + 1 = 96: the widest block grid of that kernel
     (129, 300_001, "odd-D"),                 # two tile rows, D + 1 = 130
     (255, 70_000, "odd-D"),                  # D + 1 = 256 fills the tile row exactly
     (1025, 20_000, "odd-D"),                 # a bias feature next to 1024 learned ones: 9 tile rows
