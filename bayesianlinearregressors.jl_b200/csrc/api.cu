@@ -280,6 +280,7 @@ int blr_ctx_create(blr_ctx** out, int device) {
     if (const char* v = getenv("BLR_RAND_UNFUSED")) ctx->rand_unfused = atoi(v) != 0 ? 1 : 0;
     if (const char* v = getenv("BLR_SMALL_RING")) ctx->small_ring = atoi(v) != 0 ? 1 : 0;
     if (const char* v = getenv("BLR_MID_RING")) ctx->mid_ring = atoi(v) != 0 ? 1 : 0;
+    if (const char* v = getenv("BLR_VAR_SMALL_MAX")) ctx->var_small_max = std::max(64, std::min(128, atoi(v)));
     if (const char* w = getenv("BLR_DIAG_WEIGHT")) {
         const int v = atoi(w);
         if (v >= 8 && v <= 128) ctx->diag_weight = v;

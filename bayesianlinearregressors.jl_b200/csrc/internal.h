@@ -73,6 +73,7 @@ struct blr_ctx {
     int sched_T = 0, sched_nseg = 0;
     int64_t gram_period_obs = 0;  // observations per L2 period of the Gram kernel (0 = single period; BLR_GRAM_PERIOD_OBS)
     int gram_stages = 0;   // ring depth override for gram_kt == 16 (BLR_GRAM_STAGES = 6)
+    int var_small_max = 128;  // marginals: largest D served by the streaming small-D kernel (W in shared memory: 136 KB at D = 128); BLR_VAR_SMALL_MAX in [64, 128]
     int mid_ring = 1;      // K1m: team-of-two-warps ring kernel for 64 < D <= 96 (BLR_MID_RING=0: one padded 128-row tile of K1)
     int small_ring = 1;    // K1s: per-warp TMA ring for 16 < D <= 64, D % 8 == 0, aligned ColVecs (BLR_SMALL_RING=0: register-fed kernel)
     int rand_pp = 1;       // K7: 1 = two consumer groups on alternating point tiles when the draws are SUPPLIED (8.2 ms against 9.6 ms at

@@ -126,13 +126,14 @@ __global__ void __launch_bounds__(bg::THREADS) var_kernel(const double* __restri
 // into m8n8k4 B fragments (lane (k, g) reads feature 4*kk + k of point p + g: whole 32-byte sectors in both layouts),
 // α = W x stays in 2 accumulators per 8-row block, squares are folded by shuffles; the mean rides on the same fragments.
 template <int MI>
-__global__ void __launch_bounds__(256, 2) var_small_kernel(const double* __restrict__ W, const double* __restrict__ mw, int D,
+__global__ void __launch_bounds__(256, MI <= 8 ? 2 : 1) var_small_kernel(const double* __restrict__ W, const double* __restrict__ mw, int D,
                                                         const double* __restrict__ X, int64_t sd, int64_t sn, int64_t N,
                                                         const double* __restrict__ sigma2, double sigma2_scalar,
                                                         double* __restrict__ mean, double* __restrict__ var) {
     constexpr int DP = MI * 8, KK = DP / 4, LDW = DP + 4;
-    __shared__ double Ws[DP * LDW];  // Ws[k * LDW + m] = W[m, k]
-    __shared__ double mws[DP];
+    extern __shared__ __align__(16) double var_small_smem[];  // (D <= 128: up to 136 KB, hence dynamic)
+    double* Ws = var_small_smem;       // Ws[k * LDW + m] = W[m, k]
+    double* mws = Ws + DP * LDW;       // [DP]
     for (int e = threadIdx.x; e < DP * DP; e += 256) {
         const int m = e % DP, k = e / DP;
         Ws[k * LDW + m] = (m < D && k < D && m >= k) ? W[(int64_t)k * D + m] : 0.0;
@@ -271,9 +272,12 @@ static int launch_var_small(blr_ctx* ctx, blr_post* p, const blr_x* x, const dou
                             double* mean_dev, double* var_dev) {
     const bool colv = x->layout == BLR_COLVECS;
     const int64_t sd = colv ? 1 : x->ld, sn = colv ? x->ld : 1;
-    const int grid = (int)std::min<int64_t>(((x->N + 7) / 8 + 7) / 8, (int64_t)ctx->sm_count * 4);
-    var_small_kernel<MI><<<std::max(grid, 1), 256, 0, ctx->stream>>>(p->W, p->mw, (int)p->D, x->p, sd, sn, x->N, sigma2,
-                                                                   sigma2_scalar, mean_dev, var_dev);
+    constexpr int DP = MI * 8;
+    const int smem = (DP * (DP + 4) + DP) * (int)sizeof(double);
+    if (smem > 48 * 1024) BLR_CUDA_OK(ctx, cudaFuncSetAttribute(var_small_kernel<MI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int grid = (int)std::min<int64_t>(((x->N + 7) / 8 + 7) / 8, (int64_t)ctx->sm_count * (MI <= 8 ? 4 : 1));
+    var_small_kernel<MI><<<std::max(grid, 1), 256, smem, ctx->stream>>>(p->W, p->mw, (int)p->D, x->p, sd, sn, x->N, sigma2,
+                                                                      sigma2_scalar, mean_dev, var_dev);
     BLR_CHECK_LAUNCH(ctx, "var_small_kernel");
     return 0;
 }
@@ -282,6 +286,22 @@ int predict_mean_var(blr_ctx* ctx, blr_post* p, const blr_x* x, const double* si
                      double* mean_dev, double* var_dev) {
     if (x->N == 0) return 0;
     if (ctx->form == BLR_FORM_WHITENED) return predict_mean_var_literal(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+    if (var_dev && p->D > 64 && p->D <= ctx->var_small_max) {
+        // 64 < D <= 128 (BLR_VAR_SMALL_MAX): W still fits shared memory and the streaming kernel of the small-D regime beats the
+        // tiled one, whose 128-row pass and short per-tile pipeline leave it at 6 .. 19 TF here (measured per 2^20 .. 2^21 points:
+        // D = 66 1.47 -> 0.56 ms, D = 96 1.07 -> 0.60 ms, D = 128 0.89 -> 0.72 ms); any layout, any alignment, no staging
+        BLR_TRY(post_ensure_W(ctx, p));
+        switch ((p->D + 7) / 8) {
+            case 9: return launch_var_small<9>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+            case 10: return launch_var_small<10>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+            case 11: return launch_var_small<11>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+            case 12: return launch_var_small<12>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+            case 13: return launch_var_small<13>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+            case 14: return launch_var_small<14>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+            case 15: return launch_var_small<15>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+            default: return launch_var_small<16>(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
+        }
+    }
     if (var_dev && predict_fast_eligible(p, x))
         return predict_mean_var_fast(ctx, p, x, sigma2, sigma2_scalar, mean_dev, var_dev);
     if (var_dev && p->D > 64 && x->N >= 32) {

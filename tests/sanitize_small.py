@@ -85,7 +85,7 @@ def main():
         (129, 700, "row", True, False, 300, 5, "odd D feature-major"),
         (96, 500, "col", True, False, 300, 5, "marginals 128-row pass on 128-point tiles"),
         (24, 400, "col", True, False, 300, 3, "var_small<3>"),
-        (80, 700, "col", True, False, 300, 5, "K1m team ring, one stage per team"),
+        (80, 700, "col", True, False, 300, 5, "K1m team ring, one stage per team; streaming marginals with W in dynamic shared memory"),
         (90, 40000, "col", True, False, 100, 3, "K1m team ring, slots reused (empty-barrier hand-over), split leftover row"),
     ]
     if which == "late":
