@@ -18,6 +18,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "mid_deal.h"
 
 namespace blr {
 namespace gm {
@@ -29,15 +30,7 @@ constexpr int KO = 8;      // observations per stage
 constexpr int STAGES = 5;  // per team
 constexpr int AHEAD = 3;   // stages in flight: stage i + AHEAD is issued in iteration i, into the slot released in iteration i - 2
 
-// which member computes sub-tile (mi, ni), ni <= mi, of an MI x MI block grid
-__host__ __device__ constexpr int block_owner(int mi, int ni, int MI) {
-    const int full = (MI / 4) * 4, rem = MI - full;
-    if (mi < full) return ((mi & 3) == 0 || (mi & 3) == 3) ? 0 : 1;  // rows r have r + 1 sub-tiles: 0 + 3 == 1 + 2 per group of four
-    if ((rem & 1) && mi == MI - 1) return ni & 1;                    // a leftover odd row is split by column parity
-    return (mi - full) & 1;
-}
-// which member accumulates r for block row mi
-__host__ __device__ constexpr int row_owner(int mi, int MI) { return block_owner(mi, 0, MI); }
+// the deal of the sub-tiles (block_owner, row_owner): mid_deal.h
 }  // namespace gm
 
 struct MidArgs {

@@ -50,3 +50,16 @@ def test_schedule_with_flush_cost(exe, nt, n_stages, G, wd, flush):
     T = nt * (nt + 1) // 2
     total = n_stages * (nt * wd + (T - nt) * 64)
     assert int(mx) <= total // G + flush * (T // G + 3) + 3 * 64
+
+
+@pytest.mark.parametrize("MI", list(range(1, 17)))
+def test_mid_team_deal_is_a_balanced_partition(tmp_path, MI):
+    """csrc/mid_deal.h: the two warps of a K1m team (gram_mid.cu; MI = 9 .. 12 block rows in production) partition the lower
+    triangle and carry the same number of 8 x 8 sub-tiles up to one."""
+    out = tmp_path / "mid_deal_test"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", CSRC, os.path.join(ROOT, "tests", "cpp", "mid_deal_test.cpp"), "-o", str(out)], check=True)
+    res = subprocess.run([str(out), str(MI)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout
+    tag, c0, c1 = res.stdout.split()
+    assert tag == "ok" and int(c0) + int(c1) == MI * (MI + 1) // 2
+    assert abs(int(c0) - int(c1)) <= 1, (MI, c0, c1)
